@@ -1,0 +1,150 @@
+"""ctypes binding of libaclgan_b200.so (the C ABI declared in include/aclgan_b200.h).
+
+The shared library is built IN-TREE by `build()` (nvcc, sm_100a) so it travels to the GPU box with
+the repo snapshot.  There is no CPU or eager fallback: if the library is missing or a launch
+fails, the caller gets an exception.
+"""
+import ctypes as C
+import glob
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libaclgan_b200.so")
+
+MAX_TAPS = 64
+MAX_AVARIANTS = 4
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+OUT_BF16, OUT_F32, OUT_SPLIT, OUT_F32_ATOMIC = 0, 1, 2, 3
+
+
+class TmapSpec(C.Structure):
+    _fields_ = [("base", C.c_uint64), ("rank", C.c_uint32), ("elem_bytes", C.c_uint32),
+                ("dims", C.c_uint64 * 5), ("strides", C.c_uint64 * 5), ("box", C.c_uint32 * 5)]
+
+
+class OutSpec(C.Structure):
+    _fields_ = [("ptr", C.c_uint64 * 2), ("kind", C.c_int32), ("act", C.c_int32), ("slope", C.c_float),
+                ("mirror", C.c_int32), ("off", C.c_int64), ("sn", C.c_int64), ("sy", C.c_int64),
+                ("sx", C.c_int64), ("sc", C.c_int64), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("C", C.c_int32), ("bias", C.c_uint64), ("stats", C.c_uint64)]
+
+
+class IgemmPlan(C.Structure):
+    _fields_ = [("a", (TmapSpec * MAX_AVARIANTS) * 2), ("b", TmapSpec * 2),
+                ("planes", C.c_int32), ("nseg", C.c_int32), ("n_avariants", C.c_int32),
+                ("block_n", C.c_int32), ("n_tiles", C.c_int32),
+                ("box_x", C.c_int32), ("box_y", C.c_int32), ("box_z", C.c_int32),
+                ("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("tiles_z", C.c_int32),
+                ("cchunks", C.c_int32), ("num_taps", C.c_int32),
+                ("tap_dx", C.c_int32 * MAX_TAPS), ("tap_dy", C.c_int32 * MAX_TAPS),
+                ("tap_var", C.c_int32 * MAX_TAPS), ("tap_bk", C.c_int32 * MAX_TAPS),
+                ("flat", C.c_int32), ("flat_w", C.c_int32), ("flat_img", C.c_int32),
+                ("out", OutSpec)]
+
+
+class WgradPlan(C.Structure):
+    _fields_ = [("mop", (TmapSpec * MAX_AVARIANTS) * 2), ("nop", (TmapSpec * MAX_AVARIANTS) * 2),
+                ("planes", C.c_int32), ("nseg", C.c_int32),
+                ("n_mvariants", C.c_int32), ("n_nvariants", C.c_int32),
+                ("m_chunks", C.c_int32), ("n_chunks", C.c_int32), ("m_tiles", C.c_int32), ("n_tiles", C.c_int32),
+                ("box_x", C.c_int32), ("box_y", C.c_int32), ("box_z", C.c_int32),
+                ("blocks_x", C.c_int32), ("blocks_y", C.c_int32), ("blocks_z", C.c_int32),
+                ("ksplit", C.c_int32), ("num_taps", C.c_int32),
+                ("m_dx", C.c_int32 * MAX_TAPS), ("m_dy", C.c_int32 * MAX_TAPS), ("m_var", C.c_int32 * MAX_TAPS),
+                ("n_dx", C.c_int32 * MAX_TAPS), ("n_dy", C.c_int32 * MAX_TAPS), ("n_var", C.c_int32 * MAX_TAPS),
+                ("tap_out", C.c_int32 * MAX_TAPS),
+                ("dw", C.c_uint64), ("dw_sm", C.c_int64), ("dw_st", C.c_int64), ("M", C.c_int32), ("Nn", C.c_int32)]
+
+
+class Act(C.Structure):
+    _fields_ = [("data", C.c_uint64 * 2), ("planes", C.c_int32), ("n", C.c_int32), ("h", C.c_int32),
+                ("w", C.c_int32), ("c", C.c_int32), ("pad", C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("cin", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32), ("stride", C.c_int32),
+                ("pad", C.c_int32), ("window", C.c_int32)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu under csrc/ into libaclgan_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = sources()
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "aclgan_b200.h")]
+    if not force and os.path.exists(LIB_PATH):
+        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    for s in srcs:
+        o = os.path.join(CSRC, os.path.basename(s)[:-3] + ".o")
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(d) for d in deps if not d.endswith(".cu") or d == s):
+            cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                   "-Xcompiler", "-fPIC", "-c", s, "-o", o]
+            if verbose:
+                cmd.insert(1, "-Xptxas")
+                cmd.insert(2, "-v")
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise NativeError("nvcc failed for %s:\n%s\n%s" % (s, r.stdout, r.stderr))
+            if verbose:
+                print(r.stderr)
+        objs.append(o)
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise NativeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Loads the extension; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError("libaclgan_b200.so not built: run `python __graft_entry__.py` (build()) first")
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L):
+    L.aclgan_version.restype = C.c_int
+    L.aclgan_build_info.restype = C.c_char_p
+    L.aclgan_plan_conv_fwd.argtypes = [C.POINTER(ConvDesc), C.POINTER(Act), C.c_uint64 * 2, C.POINTER(OutSpec),
+                                       C.POINTER(IgemmPlan)]
+    L.aclgan_plan_conv_dgrad.argtypes = [C.POINTER(ConvDesc), C.POINTER(Act), C.c_uint64 * 2, C.c_int,
+                                         C.POINTER(OutSpec), C.POINTER(IgemmPlan)]
+    L.aclgan_packed_weight_shape.argtypes = [C.POINTER(ConvDesc), C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.aclgan_packed_weight_index.argtypes = [C.POINTER(ConvDesc), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.aclgan_packed_weight_index.restype = C.c_int64
+    L.aclgan_igemm_launch.argtypes = [C.POINTER(IgemmPlan), C.c_void_p]
+    L.aclgan_plan_conv_wgrad.argtypes = [C.POINTER(ConvDesc), C.POINTER(Act), C.POINTER(Act), C.c_uint64,
+                                         C.POINTER(WgradPlan)]
+    L.aclgan_wgrad_layout.argtypes = [C.POINTER(ConvDesc)]
+    L.aclgan_wgrad_launch.argtypes = [C.POINTER(WgradPlan), C.c_void_p]
+
+
+def check(rc, what):
+    if rc != 0:
+        raise NativeError("%s failed with status %d" % (what, rc))
+
+
+def exported_symbols():
+    """Symbols include/aclgan_b200.h declares (parsed from the header), for the ABI test."""
+    import re
+    hdr = open(os.path.join(HERE, "..", "include", "aclgan_b200.h")).read()
+    return sorted(set(re.findall(r"\b(aclgan_[a-z0-9_]+)\s*\(", hdr)))

@@ -1,0 +1,375 @@
+// Implicit-GEMM convolution (forward and data-gradient) on the 5th-gen tensor cores.
+//
+//   D[pixel][n] = sum_{segment} sum_{tap} sum_{chunk}  A_tap[pixel][64 ch] . B[n][k(tap, chunk) .. +64]
+//
+// * A tiles (128 pixels x 64 channels, bf16) are fetched straight from the padded NHWC activation in HBM
+//   by TMA (rank-4 tensor maps, one box per filter tap: the reflect padding / stride-2 parity / small-C
+//   pixel windows are all expressed in the tensor map + per-tap box offsets, nothing is im2col-materialised).
+// * B tiles (block_n x 64, bf16, K-major) come from the packed weights by TMA.
+// * both land in 128B-swizzled shared memory and feed tcgen05.mma (M=128, N=block_n, K=16) issued by one
+//   thread; the fp32 accumulator lives in TMEM (2 x 256 columns, double buffered across tiles).
+// * epilogue warps read TMEM with tcgen05.ld, add bias, apply the activation, and store bf16 / split-bf16 /
+//   fp32 with arbitrary (n, y, x, c) strides, optionally replicating border pixels into a reflect-pad halo.
+// * persistent CTAs (one per SM), 4-stage TMA->MMA mbarrier pipeline, warp-specialised roles.
+//
+// Replaces: nn.Conv2d forward inside Conv2dBlock.forward (reference networks.py:363,366) incl. the
+// ReflectionPad2d gather (networks.py:319) and, for no-norm blocks, bias + ReLU/LeakyReLU/tanh
+// (networks.py:345-353,370); the same kernel computes conv data gradients (autograd of networks.py:366).
+#include "common.cuh"
+
+namespace aclgan {
+
+constexpr int kStages = 4;
+constexpr int kTileM = 128;
+constexpr int kABytes = kTileM * 128;          // 128 rows x 64 bf16
+constexpr int kBBytesMax = 256 * 128;          // up to 256 rows x 64 bf16
+constexpr int kStageBytes = kABytes + kBBytesMax;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 256;
+
+struct alignas(64) IgemmKParams {
+    CUtensorMap a[2][ACLGAN_MAX_AVARIANTS];
+    CUtensorMap b[2];
+    int planes, nseg, block_n, n_tiles;
+    int box_x, box_y, box_z, tiles_x, tiles_y, tiles_z;
+    int cchunks, num_taps;
+    int flat, flat_w, flat_img;
+    int tap_dx[ACLGAN_MAX_TAPS];
+    int tap_dy[ACLGAN_MAX_TAPS];
+    int tap_var[ACLGAN_MAX_TAPS];
+    int tap_bk[ACLGAN_MAX_TAPS];
+    aclgan_out_spec out;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    if (act == ACLGAN_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACLGAN_ACT_LRELU) return v > 0.f ? v : v * slope;
+    if (act == ACLGAN_ACT_TANH) return tanhf(v);
+    return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// stores `cnt` (<= NV) consecutive channels starting at channel ch0 of the pixel at element offset `pix`
+template <int NV>
+__device__ __forceinline__ void store_channels(const aclgan_out_spec& o, int64_t pix, int ch0, int cnt,
+                                               const float (&v)[NV]) {
+    if (o.kind == ACLGAN_OUT_BF16 || o.kind == ACLGAN_OUT_SPLIT) {
+        const int planes = (o.kind == ACLGAN_OUT_SPLIT) ? 2 : 1;
+        for (int pl = 0; pl < planes; ++pl) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(o.ptr[pl]) + pix + (int64_t)ch0 * o.sc;
+            if (o.sc == 1 && cnt == NV && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < NV; i += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float x = v[i + j];
+                        if (pl == 1) x = x - __bfloat162float(__float2bfloat16_rn(x));
+                        f[j] = x;
+                    }
+                    uint4 q;
+                    q.x = pack_bf16x2(f[0], f[1]);
+                    q.y = pack_bf16x2(f[2], f[3]);
+                    q.z = pack_bf16x2(f[4], f[5]);
+                    q.w = pack_bf16x2(f[6], f[7]);
+                    *reinterpret_cast<uint4*>(dst + i) = q;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    if (i < cnt) {
+                        float x = v[i];
+                        if (pl == 1) x = x - __bfloat162float(__float2bfloat16_rn(x));
+                        dst[(int64_t)i * o.sc] = __float2bfloat16_rn(x);
+                    }
+                }
+            }
+        }
+    } else {
+        float* dst = reinterpret_cast<float*>(o.ptr[0]) + pix + (int64_t)ch0 * o.sc;
+        if (o.kind == ACLGAN_OUT_F32_ATOMIC) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                if (i < cnt) atomicAdd(dst + (int64_t)i * o.sc, v[i]);
+        } else if (o.sc == 1 && cnt == NV && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < NV; i += 4)
+                *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                if (i < cnt) dst[(int64_t)i * o.sc] = v[i];
+        }
+    }
+}
+
+// reflect-pad images of coordinate c in [0, L) for halo width p:  -c (1 <= c <= p) and 2(L-1)-c (L-1-p <= c <= L-2)
+__device__ __forceinline__ int mirror_coords(int c, int L, int p, int (&out)[3]) {
+    int n = 0;
+    out[n++] = c;
+    if (p > 0) {
+        if (c >= 1 && c <= p) out[n++] = -c;
+        if (c >= L - 1 - p && c <= L - 2) out[n++] = 2 * (L - 1) - c;
+    }
+    return n;
+}
+
+template <int NV>
+__device__ __forceinline__ void epilogue_chunk(const IgemmKParams& P, const uint32_t (&raw)[NV], int ch0, bool valid,
+                                               int64_t pix0, const int (&ys)[3], int ny, const int (&xs)[3], int nx,
+                                               int y, int x, int zn) {
+    const aclgan_out_spec& o = P.out;
+    int cnt = o.C - ch0;
+    if (cnt > NV) cnt = NV;
+    if (!valid || cnt <= 0) return;
+    float v[NV];
+    const float* bias = reinterpret_cast<const float*>(o.bias);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float t = __uint_as_float(raw[i]);
+        if (bias != nullptr && i < cnt) t += __ldg(bias + ch0 + i);
+        v[i] = apply_act(t, o.act, o.slope);
+    }
+    if (o.stats != 0) {
+        // per-(n, c) sum / sum of squares of the values the following norm layer will see
+        float* st = reinterpret_cast<float*>(o.stats) + ((int64_t)zn * o.C + ch0) * 2;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (i < cnt) {
+                atomicAdd(st + 2 * i, v[i]);
+                atomicAdd(st + 2 * i + 1, v[i] * v[i]);
+            }
+    }
+    for (int iy = 0; iy < ny; ++iy)
+        for (int ix = 0; ix < nx; ++ix) {
+            int64_t pix = pix0 + (int64_t)(ys[iy] - y) * o.sy + (int64_t)(xs[ix] - x) * o.sx;
+            store_channels<NV>(o, pix, ch0, cnt, v);
+        }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmKParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* full_bar = bars;                  // [kStages]
+    uint64_t* empty_bar = bars + kStages;       // [kStages]
+    uint64_t* tfull_bar = bars + 2 * kStages;   // [2]
+    uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int p = 0; p < P.planes; ++p) {
+            for (int v = 0; v < ACLGAN_MAX_AVARIANTS; ++v) tma_prefetch_desc(&P.a[p][v]);
+            tma_prefetch_desc(&P.b[p]);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_tiles = P.tiles_x * P.tiles_y * P.tiles_z;
+    const int total_tiles = m_tiles * P.n_tiles;
+    const int k_iters = P.nseg * P.num_taps * P.cchunks;
+    const uint32_t stage_tx = kABytes + P.block_n * 128;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % P.n_tiles;
+            int mt = tile / P.n_tiles;
+            const int tx = mt % P.tiles_x;
+            mt /= P.tiles_x;
+            const int ty = mt % P.tiles_y;
+            const int tz = mt / P.tiles_y;
+            const int x0 = tx * P.box_x, y0 = ty * P.box_y, z0 = tz * P.box_z;
+            for (int seg = 0; seg < P.nseg; ++seg) {
+                const int pa = (seg == 2) ? 1 : 0;   // A plane: hi, hi, lo
+                const int pb = (seg == 1) ? 1 : 0;   // B plane: hi, lo, hi
+                for (int t = 0; t < P.num_taps; ++t) {
+                    const CUtensorMap* am = &P.a[pa][P.tap_var[t]];
+                    const int ax = x0 + P.tap_dx[t], ay = y0 + P.tap_dy[t];
+                    const int bk = P.tap_bk[t];
+                    for (int cc = 0; cc < P.cchunks; ++cc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * kStageBytes;
+                        uint8_t* sb = sa + kABytes;
+                        mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+                        tma_load_4d(sa, am, &full_bar[stage], cc * 64, ax, ay, z0);
+                        tma_load_2d(sb, &P.b[pb], &full_bar[stage], bk + cc * 64, nt * P.block_n);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)P.block_n, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            for (int k = 0; k < k_iters; ++k) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                const uint32_t sb = sa + kABytes;
+                const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+                const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    // +32 bytes (= 16 bf16 of K) inside the 128B swizzle row -> +2 in the >>4 encoded address
+                    umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tfull_bar[acc]);
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue ----------------
+        const int q = warp & 3;              // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const aclgan_out_spec& o = P.out;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int nt = tile % P.n_tiles;
+            int mt = tile / P.n_tiles;
+            const int tx = mt % P.tiles_x;
+            mt /= P.tiles_x;
+            const int ty = mt % P.tiles_y;
+            const int tz = mt / P.tiles_y;
+            int x, y, z;
+            if (P.flat) {
+                const int64_t qq = (int64_t)tx * P.box_x + row;
+                z = (int)(qq / P.flat_img);
+                const int rem = (int)(qq % P.flat_img);
+                y = rem / P.flat_w;
+                x = rem % P.flat_w;
+            } else {
+                x = tx * P.box_x + row % P.box_x;
+                y = ty * P.box_y + (row / P.box_x) % P.box_y;
+                z = tz * P.box_z + row / (P.box_x * P.box_y);
+            }
+            const bool valid = (x < o.W) && (y < o.H) && (z < o.N);
+            const int64_t pix0 = o.off + (int64_t)z * o.sn + (int64_t)y * o.sy + (int64_t)x * o.sx;
+            int ys[3], xs[3];
+            const int ny = mirror_coords(y, o.H, o.mirror, ys);
+            const int nx = mirror_coords(x, o.W, o.mirror, xs);
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+            const int n0 = nt * P.block_n;
+            if (P.block_n >= 32) {
+                for (int c = 0; c < P.block_n; c += 32) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32(t_row + c, raw);
+                    tmem_ld_wait();
+                    epilogue_chunk<32>(P, raw, n0 + c, valid, pix0, ys, ny, xs, nx, y, x, z);
+                }
+            } else {
+                uint32_t raw[16];
+                tmem_ld_32x16(t_row, raw);
+                tmem_ld_wait();
+                epilogue_chunk<16>(P, raw, n0, valid, pix0, ys, ny, xs, nx, y, x, z);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int fill_kparams(const aclgan_igemm_plan* pl, IgemmKParams* kp) {
+    if (pl->planes < 1 || pl->planes > 2 || (pl->nseg != 1 && pl->nseg != 3)) return ACLGAN_ERR_SHAPE;
+    if (pl->nseg == 3 && pl->planes != 2) return ACLGAN_ERR_SHAPE;
+    if (pl->block_n != 16 && pl->block_n != 32 && pl->block_n != 64 && pl->block_n != 128 && pl->block_n != 256)
+        return ACLGAN_ERR_SHAPE;
+    if (pl->box_x * pl->box_y * pl->box_z != kTileM) return ACLGAN_ERR_SHAPE;
+    if (pl->num_taps < 1 || pl->num_taps > ACLGAN_MAX_TAPS || pl->cchunks < 1) return ACLGAN_ERR_SHAPE;
+    if (pl->n_avariants < 1 || pl->n_avariants > ACLGAN_MAX_AVARIANTS) return ACLGAN_ERR_SHAPE;
+    for (int p = 0; p < pl->planes; ++p) {
+        for (int v = 0; v < ACLGAN_MAX_AVARIANTS; ++v) {
+            const aclgan_tmap_spec* s = &pl->a[p][v < pl->n_avariants ? v : 0];
+            int rc = encode_tmap(s, &kp->a[p][v]);
+            if (rc) return rc;
+        }
+        int rc = encode_tmap(&pl->b[p], &kp->b[p]);
+        if (rc) return rc;
+    }
+    if (pl->planes == 1) {
+        for (int v = 0; v < ACLGAN_MAX_AVARIANTS; ++v) kp->a[1][v] = kp->a[0][v];
+        kp->b[1] = kp->b[0];
+    }
+    kp->planes = pl->planes; kp->nseg = pl->nseg; kp->block_n = pl->block_n; kp->n_tiles = pl->n_tiles;
+    kp->box_x = pl->box_x; kp->box_y = pl->box_y; kp->box_z = pl->box_z;
+    kp->tiles_x = pl->tiles_x; kp->tiles_y = pl->tiles_y; kp->tiles_z = pl->tiles_z;
+    kp->cchunks = pl->cchunks; kp->num_taps = pl->num_taps;
+    kp->flat = pl->flat; kp->flat_w = pl->flat_w > 0 ? pl->flat_w : 1; kp->flat_img = pl->flat_img > 0 ? pl->flat_img : 1;
+    for (int t = 0; t < ACLGAN_MAX_TAPS; ++t) {
+        kp->tap_dx[t] = pl->tap_dx[t]; kp->tap_dy[t] = pl->tap_dy[t];
+        kp->tap_var[t] = pl->tap_var[t]; kp->tap_bk[t] = pl->tap_bk[t];
+        if (t < pl->num_taps && (pl->tap_var[t] < 0 || pl->tap_var[t] >= pl->n_avariants)) return ACLGAN_ERR_SHAPE;
+    }
+    kp->out = pl->out;
+    return ACLGAN_OK;
+}
+
+}  // namespace aclgan
+
+extern "C" int aclgan_igemm_launch(const aclgan_igemm_plan* plan, void* stream) {
+    using namespace aclgan;
+    static bool attr_set = false;
+    IgemmKParams kp;
+    int rc = fill_kparams(plan, &kp);
+    if (rc) return rc;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int total = plan->tiles_x * plan->tiles_y * plan->tiles_z * plan->n_tiles;
+    if (total <= 0) return ACLGAN_OK;
+    const int grid = total < num_sms() ? total : num_sms();
+    igemm_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(kp);
+    return (int)cudaGetLastError();
+}

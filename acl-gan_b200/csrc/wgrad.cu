@@ -1,0 +1,216 @@
+// Convolution weight gradient on the tensor cores:
+//
+//   dW[m][tap][n] += sum_{pixels of this CTA's K range}  Mop[pixel][m] * Nop_tap[pixel][n]
+//
+// The reduction dimension is the pixel index, which is the OUTER (row) dimension of the NHWC planes, so both
+// operands are fed to tcgen05.mma in MN-major form: a TMA box of 64 pixels x 64 channels lands as 64 rows of
+// 128 B (128B swizzle) and is consumed as a [K=64 pixels][64 channels] block (descriptor LBO = distance between
+// 64-channel chunks, SBO = 8 pixel rows).  M = 128 channels of one operand (dY normally), N = up to 256 channels
+// of the other, taken at the filter-tap offset; fp32 accumulator in TMEM; split-K over pixel blocks with
+// fp32 vector atomics into the gradient buffer, which has the packed-weight layout.
+//
+// Replaces: the weight-gradient half of autograd's convolution_backward for nn.Conv2d (reference
+// networks.py:363,366 under loss.backward(), trainer.py:169,292).
+#include "common.cuh"
+
+namespace aclgan {
+
+constexpr int kWStages = 4;
+constexpr int kWChunkBytes = 64 * 128;               // 64 pixels x 64 channels bf16
+constexpr int kWMBytes = 2 * kWChunkBytes;           // M operand: up to 2 chunks
+constexpr int kWNBytes = 4 * kWChunkBytes;           // N operand: up to 4 chunks
+constexpr int kWStageBytes = kWMBytes + kWNBytes;    // 48 KB
+constexpr int kWSmemBytes = kWStages * kWStageBytes + 1024 + 256;
+constexpr int kWThreads = 256;
+
+struct alignas(64) WgradKParams {
+    CUtensorMap mop[2][ACLGAN_MAX_AVARIANTS];
+    CUtensorMap nop[2][ACLGAN_MAX_AVARIANTS];
+    int planes, nseg, m_chunks, n_chunks, m_tiles, n_tiles;
+    int box_x, box_y, box_z, blocks_x, blocks_y, blocks_z, ksplit, num_taps;
+    int m_dx[ACLGAN_MAX_TAPS], m_dy[ACLGAN_MAX_TAPS], m_var[ACLGAN_MAX_TAPS];
+    int n_dx[ACLGAN_MAX_TAPS], n_dy[ACLGAN_MAX_TAPS], n_var[ACLGAN_MAX_TAPS];
+    int tap_out[ACLGAN_MAX_TAPS];
+    float* dw;
+    long long dw_sm, dw_st;
+    int M, Nn;
+};
+
+__global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_constant__ WgradKParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWStages * kWStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kWStages;
+    uint64_t* done_bar = bars + 2 * kWStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWStages + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // tile decode: blockIdx.x = ((tap * m_tiles + mt) * n_tiles + nt) * ksplit + split
+    int id = blockIdx.x;
+    const int split = id % P.ksplit;  id /= P.ksplit;
+    const int nt = id % P.n_tiles;    id /= P.n_tiles;
+    const int mt = id % P.m_tiles;    id /= P.m_tiles;
+    const int tap = id;
+
+    const int blocks_total = P.blocks_x * P.blocks_y * P.blocks_z;
+    const int per = (blocks_total + P.ksplit - 1) / P.ksplit;
+    const int blk_begin = split * per;
+    const int blk_end = min(blocks_total, blk_begin + per);
+    const int n_iters = (blk_end > blk_begin ? blk_end - blk_begin : 0) * P.nseg;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kWStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t stage_tx = (uint32_t)(P.m_chunks + P.n_chunks) * kWChunkBytes;
+
+    if (n_iters > 0) {
+        if (warp == 0 && lane == 0) {
+            // ---------------- TMA producer ----------------
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int b = blk_begin; b < blk_end; ++b) {
+                const int bx = b % P.blocks_x;
+                const int by = (b / P.blocks_x) % P.blocks_y;
+                const int bz = b / (P.blocks_x * P.blocks_y);
+                const int x0 = bx * P.box_x, y0 = by * P.box_y, z0 = bz * P.box_z;
+                for (int seg = 0; seg < P.nseg; ++seg) {
+                    const int pm = (seg == 2) ? 1 : 0;
+                    const int pn = (seg == 1) ? 1 : 0;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sm = smem + stage * kWStageBytes;
+                    uint8_t* sn = sm + kWMBytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+                    const CUtensorMap* mm = &P.mop[pm][P.m_var[tap]];
+                    const CUtensorMap* nm = &P.nop[pn][P.n_var[tap]];
+                    for (int c = 0; c < P.m_chunks; ++c)
+                        tma_load_4d(sm + c * kWChunkBytes, mm, &full_bar[stage], (mt * 2 + c) * 64, x0 + P.m_dx[tap],
+                                    y0 + P.m_dy[tap], z0);
+                    for (int c = 0; c < P.n_chunks; ++c)
+                        tma_load_4d(sn + c * kWChunkBytes, nm, &full_bar[stage], (nt * P.n_chunks + c) * 64,
+                                    x0 + P.n_dx[tap], y0 + P.n_dy[tap], z0);
+                    if (++stage == kWStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ---------------- MMA issuer ----------------
+            const uint32_t idesc = make_idesc_bf16(128, (uint32_t)(64 * P.n_chunks), 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int k = 0; k < n_iters; ++k) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sm = smem_u32(smem + stage * kWStageBytes);
+                const uint32_t sn = sm + kWMBytes;
+                // MN-major, 128B swizzle: LBO = next 64-channel chunk (8 KB), SBO = next 8 pixel rows (1 KB)
+                const uint64_t dm = make_smem_desc_sw128(sm, kWChunkBytes, 1024);
+                const uint64_t dn = make_smem_desc_sw128(sn, kWChunkBytes, 1024);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    // 16 pixels (= one UMMA K) further down: 16 rows x 128 B = 2048 B -> +128 encoded
+                    umma_bf16(tmem_base, dm + 128 * kk, dn + 128 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == kWStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(done_bar);
+        } else if (warp >= 4) {
+            // ---------------- epilogue: fp32 vector atomics into dW ----------------
+            const int q = warp & 3;
+            const int m = mt * 128 + q * 32 + lane;
+            mbar_wait(done_bar, 0);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+            const int ncols = 64 * P.n_chunks;
+            const int n_base = nt * ncols;
+            float* row = P.dw + (long long)m * P.dw_sm + (long long)P.tap_out[tap] * P.dw_st;
+            for (int c = 0; c < ncols; c += 32) {
+                uint32_t raw[32];
+                tmem_ld_32x32(t_row + c, raw);
+                tmem_ld_wait();
+                if (m < P.M) {
+                    const int n0 = n_base + c;
+                    float* dst = row + n0;
+                    if (n0 + 32 <= P.Nn && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            atomicAdd(reinterpret_cast<float4*>(dst + i),
+                                      make_float4(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]),
+                                                  __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3])));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (n0 + i < P.Nn) atomicAdd(dst + i, __uint_as_float(raw[i]));
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+}  // namespace aclgan
+
+using namespace aclgan;
+
+extern "C" int aclgan_wgrad_launch(const aclgan_wgrad_plan* pl, void* stream) {
+    static bool attr_set = false;
+    if (pl->planes < 1 || pl->planes > 2 || (pl->nseg != 1 && pl->nseg != 3)) return ACLGAN_ERR_SHAPE;
+    if (pl->m_chunks < 1 || pl->m_chunks > 2 || pl->n_chunks < 1 || pl->n_chunks > 4) return ACLGAN_ERR_SHAPE;
+    if (pl->box_x * pl->box_y * pl->box_z != 64) return ACLGAN_ERR_SHAPE;
+    if (pl->num_taps < 1 || pl->num_taps > ACLGAN_MAX_TAPS || pl->ksplit < 1) return ACLGAN_ERR_SHAPE;
+    if (pl->n_mvariants < 1 || pl->n_mvariants > ACLGAN_MAX_AVARIANTS || pl->n_nvariants < 1 ||
+        pl->n_nvariants > ACLGAN_MAX_AVARIANTS)
+        return ACLGAN_ERR_SHAPE;
+    WgradKParams kp;
+    for (int p = 0; p < 2; ++p) {
+        const int sp = p < pl->planes ? p : 0;
+        for (int v = 0; v < ACLGAN_MAX_AVARIANTS; ++v) {
+            int rc = encode_tmap(&pl->mop[sp][v < pl->n_mvariants ? v : 0], &kp.mop[p][v]);
+            if (rc) return rc;
+            rc = encode_tmap(&pl->nop[sp][v < pl->n_nvariants ? v : 0], &kp.nop[p][v]);
+            if (rc) return rc;
+        }
+    }
+    kp.planes = pl->planes; kp.nseg = pl->nseg; kp.m_chunks = pl->m_chunks; kp.n_chunks = pl->n_chunks;
+    kp.m_tiles = pl->m_tiles; kp.n_tiles = pl->n_tiles;
+    kp.box_x = pl->box_x; kp.box_y = pl->box_y; kp.box_z = pl->box_z;
+    kp.blocks_x = pl->blocks_x; kp.blocks_y = pl->blocks_y; kp.blocks_z = pl->blocks_z;
+    kp.ksplit = pl->ksplit; kp.num_taps = pl->num_taps;
+    for (int t = 0; t < ACLGAN_MAX_TAPS; ++t) {
+        kp.m_dx[t] = pl->m_dx[t]; kp.m_dy[t] = pl->m_dy[t]; kp.m_var[t] = pl->m_var[t];
+        kp.n_dx[t] = pl->n_dx[t]; kp.n_dy[t] = pl->n_dy[t]; kp.n_var[t] = pl->n_var[t];
+        kp.tap_out[t] = pl->tap_out[t];
+    }
+    kp.dw = reinterpret_cast<float*>(pl->dw); kp.dw_sm = pl->dw_sm; kp.dw_st = pl->dw_st;
+    kp.M = pl->M; kp.Nn = pl->Nn;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int grid = pl->num_taps * pl->m_tiles * pl->n_tiles * pl->ksplit;
+    wgrad_kernel<<<grid, kWThreads, kWSmemBytes, (cudaStream_t)stream>>>(kp);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,149 @@
+/* aclgan_b200 - C ABI of the B200-native ACL-GAN convolutional training step.
+ *
+ * The reference (hyperplane-lab/ACL-GAN) has NO native/FFI layer: its hot path is eager PyTorch
+ * (networks.py / trainer.py -> ATen -> cuDNN).  This header is therefore the boundary SURVEY.md
+ * section 8(b) "Level 2" defines: plain `extern "C"` entry points, raw device pointers + sizes, a
+ * `cudaStream_t` passed as `void*`, int status return.  Each entry point names the reference
+ * call site (file:line under /root/reference) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch tensors); never retained/freed;
+ *   - launches go to the given stream, no hidden synchronisation, capturable in a CUDA graph;
+ *   - return 0 on success, < 0 = aclgan error (bad shape / alignment / unsupported option),
+ *     > 0 = cudaError_t / CUresult of the failing runtime call;
+ *   - activations are "padded NHWC planes": [N][H+2p][W+2p][C] bf16, C a multiple of 8, one plane
+ *     (bf16 mode) or two planes hi/lo (bf16x3 mode: x ~= hi + lo, products hi*hi + hi*lo + lo*hi
+ *     accumulate in fp32 on the tensor cores, giving ~fp32 products for the parity mode).
+ */
+#ifndef ACLGAN_B200_H
+#define ACLGAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACLGAN_ABI_VERSION 1
+#define ACLGAN_MAX_TAPS 64
+#define ACLGAN_MAX_AVARIANTS 4
+
+enum { ACLGAN_OK = 0, ACLGAN_ERR_SHAPE = -1, ACLGAN_ERR_ALIGN = -2, ACLGAN_ERR_UNSUPPORTED = -3, ACLGAN_ERR_DRIVER = -4 };
+enum { ACLGAN_ACT_NONE = 0, ACLGAN_ACT_RELU = 1, ACLGAN_ACT_LRELU = 2, ACLGAN_ACT_TANH = 3 };
+enum { ACLGAN_WINDOW_NONE = 0, ACLGAN_WINDOW_IN = 1 /* cin <= 8|16: first convs */, ACLGAN_WINDOW_OUT = 2 /* cout <= 8: final conv */ };
+enum { ACLGAN_OUT_BF16 = 0, ACLGAN_OUT_F32 = 1, ACLGAN_OUT_SPLIT = 2, ACLGAN_OUT_F32_ATOMIC = 3 };
+
+/* ---- generic TMA tensor-map description (bf16, 128B swizzle, zero fill out of bounds) ---- */
+typedef struct aclgan_tmap_spec {
+    uint64_t base;       /* device address of element (0,...,0) */
+    uint32_t rank;       /* 2..5 */
+    uint32_t elem_bytes; /* 2 */
+    uint64_t dims[5];    /* extent per dimension, innermost first */
+    uint64_t strides[5]; /* byte stride per dimension (strides[0] == elem_bytes) */
+    uint32_t box[5];     /* box extent per dimension */
+} aclgan_tmap_spec;
+
+/* ---- epilogue / output description shared by the implicit-GEMM kernels ---- */
+typedef struct aclgan_out_spec {
+    uint64_t ptr[2];        /* plane pointers (bf16 hi[/lo]) or fp32 buffer in ptr[0] */
+    int32_t kind;           /* ACLGAN_OUT_* */
+    int32_t act;            /* ACLGAN_ACT_* applied after the bias */
+    float slope;            /* LeakyReLU negative slope */
+    int32_t mirror;         /* reflect-pad width to replicate border pixels into (0 = none) */
+    int64_t off;            /* element offset of logical pixel (n=0, y=0, x=0), channel 0 */
+    int64_t sn, sy, sx, sc; /* element strides */
+    int32_t N, H, W, C;     /* valid logical extent: rows outside are not stored; channels >= C dropped */
+    uint64_t bias;          /* fp32 [C] or 0 */
+    uint64_t stats;         /* fp32 [N][C][2] (sum, sum of squares) accumulated with atomics, or 0 */
+} aclgan_out_spec;
+
+/* ---- implicit GEMM plan:  D[pixel][n] = sum_seg sum_tap sum_chunk A_tap[pixel][64] * B[n][k(tap,chunk) + 64] ---- */
+typedef struct aclgan_igemm_plan {
+    aclgan_tmap_spec a[2][ACLGAN_MAX_AVARIANTS]; /* [plane][variant] rank-4 maps (c, x, y, z) */
+    aclgan_tmap_spec b[2];                       /* [plane] rank-2 maps (k, n) */
+    int32_t planes;      /* 1 | 2 */
+    int32_t nseg;        /* 1 | 3 */
+    int32_t n_avariants; /* maps used in a[.][] */
+    int32_t block_n;     /* UMMA N (16,32,64,128,256) */
+    int32_t n_tiles;     /* tiles along n */
+    int32_t box_x, box_y, box_z; /* A box: box_x*box_y*box_z == 128 pixels */
+    int32_t tiles_x, tiles_y, tiles_z;
+    int32_t cchunks;     /* 64-wide K chunks per tap */
+    int32_t num_taps;
+    int32_t tap_dx[ACLGAN_MAX_TAPS];
+    int32_t tap_dy[ACLGAN_MAX_TAPS];
+    int32_t tap_var[ACLGAN_MAX_TAPS]; /* which a[.][variant] map the tap loads through */
+    int32_t tap_bk[ACLGAN_MAX_TAPS];  /* first k element of the tap in B */
+    int32_t flat;        /* 0: tile rows decode as (x,y,z) box coordinates; 1: q = x0 + row, decoded with pitches */
+    int32_t flat_w;      /* flat: x = q % flat_w */
+    int32_t flat_img;    /* flat: z = q / flat_img, y = (q % flat_img) / flat_w */
+    aclgan_out_spec out;
+} aclgan_igemm_plan;
+
+/* ---- weight-gradient plan:  acc[m][n] = sum_pixels Mop[pixel][m] * Nop_tap[pixel][n]   (both operands MN-major:
+ *      a smem row is one pixel, 64 channels wide), accumulated with fp32 atomics into dw[m][tap][n] ---- */
+typedef struct aclgan_wgrad_plan {
+    aclgan_tmap_spec mop[2][ACLGAN_MAX_AVARIANTS]; /* [plane][variant] rank-4 (c, x, y, z); box = 64 ch x 64 pixels */
+    aclgan_tmap_spec nop[2][ACLGAN_MAX_AVARIANTS];
+    int32_t planes, nseg;        /* 1/1 or 2/3: (m_hi,n_hi), (m_hi,n_lo), (m_lo,n_hi) */
+    int32_t n_mvariants, n_nvariants;
+    int32_t m_chunks;            /* 64-channel chunks of the M operand per tile (1 | 2); UMMA M is always 128 */
+    int32_t n_chunks;            /* 64-channel chunks of the N operand per tile (1..4);  UMMA N = 64 * n_chunks */
+    int32_t m_tiles, n_tiles;
+    int32_t box_x, box_y, box_z; /* pixel box (product 64) */
+    int32_t blocks_x, blocks_y, blocks_z; /* pixel blocks covering the reduction grid */
+    int32_t ksplit;              /* CTAs per (tap, m_tile, n_tile), each reducing a contiguous range of pixel blocks */
+    int32_t num_taps;
+    int32_t m_dx[ACLGAN_MAX_TAPS], m_dy[ACLGAN_MAX_TAPS], m_var[ACLGAN_MAX_TAPS];
+    int32_t n_dx[ACLGAN_MAX_TAPS], n_dy[ACLGAN_MAX_TAPS], n_var[ACLGAN_MAX_TAPS];
+    int32_t tap_out[ACLGAN_MAX_TAPS]; /* tap slot in dw */
+    uint64_t dw;                 /* fp32, element (m, tap, n) at m*dw_sm + tap*dw_st + n */
+    int64_t dw_sm, dw_st;
+    int32_t M, Nn;               /* valid rows / columns */
+} aclgan_wgrad_plan;
+
+/* ---- padded NHWC activation handle ---- */
+typedef struct aclgan_act {
+    uint64_t data[2]; /* plane pointers */
+    int32_t planes;   /* 1 | 2 */
+    int32_t n, h, w;  /* logical extent */
+    int32_t c;        /* stored channels per pixel (multiple of 8) */
+    int32_t pad;      /* stored border width */
+} aclgan_act;
+
+/* ---- convolution descriptors ---- */
+typedef struct aclgan_conv_desc {
+    int32_t cin, cout;   /* logical channels (reference nn.Conv2d in/out channels, networks.py:363) */
+    int32_t k;           /* square kernel size */
+    int32_t stride;      /* 1 | 2 */
+    int32_t pad;         /* reflect padding applied by the block (networks.py:318-325); stored in the input plane */
+    int32_t window;      /* ACLGAN_WINDOW_*: small-C side handled as a 64-wide pixel window */
+} aclgan_conv_desc;
+
+int aclgan_version(void);
+const char* aclgan_build_info(void);
+
+/* plan builders: pure host code, usable without a GPU (unit-tested by CPU emulation) */
+int aclgan_plan_conv_fwd(const aclgan_conv_desc* cd, const aclgan_act* x, const uint64_t w[2],
+                         const aclgan_out_spec* out, aclgan_igemm_plan* plan);
+int aclgan_plan_conv_dgrad(const aclgan_conv_desc* cd, const aclgan_act* dy, const uint64_t wt[2], int phase,
+                           const aclgan_out_spec* out, aclgan_igemm_plan* plan);
+int aclgan_plan_conv_wgrad(const aclgan_conv_desc* cd, const aclgan_act* dy, const aclgan_act* x, uint64_t dw,
+                           aclgan_wgrad_plan* plan);
+/* packed-weight geometry (elements): rows x k_total of the forward (K-major over cin) and
+ * transposed (K-major over cout) packings the plans above expect */
+int aclgan_packed_weight_shape(const aclgan_conv_desc* cd, int transposed, int64_t* rows, int64_t* k_total);
+/* index of logical weight element W[co][ci][kh][kw] inside the packed buffers; -1 if not stored */
+int64_t aclgan_packed_weight_index(const aclgan_conv_desc* cd, int transposed, int co, int ci, int kh, int kw);
+/* the fp32 weight-gradient buffer written by the wgrad plan has exactly the layout of one of the two packings:
+ * returns 0 (forward packing) or 1 (transposed packing) */
+int aclgan_wgrad_layout(const aclgan_conv_desc* cd);
+
+/* launches (networks.py:363,366 Conv2d forward; autograd of it for dgrad / wgrad) */
+int aclgan_igemm_launch(const aclgan_igemm_plan* plan, void* stream);
+int aclgan_wgrad_launch(const aclgan_wgrad_plan* plan, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACLGAN_B200_H */

@@ -1,0 +1,185 @@
+"""CPU validation of the host-side plan builders (csrc/plans.cu) by emulating their TMA/MMA/epilogue contract."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import aclgan_native as N
+import emul
+
+
+def make_act(mem, x_nchw, pad, cs, planes=1, slack=64, mode="reflect"):
+    """NCHW float -> padded NHWC bf16 plane(s) with `cs` stored channels (+ zeroed slack behind)."""
+    n, c, h, w = x_nchw.shape
+    xp = F.pad(x_nchw, (pad,) * 4, mode=mode) if pad > 0 else x_nchw
+    buf = torch.zeros(planes, n * (h + 2 * pad) * (w + 2 * pad) * cs + slack, dtype=torch.bfloat16)
+    v = torch.zeros(n, h + 2 * pad, w + 2 * pad, cs)
+    v[..., :c] = xp.permute(0, 2, 3, 1)
+    hi = v.bfloat16()
+    buf[0, :v.numel()] = hi.reshape(-1)
+    if planes == 2:
+        buf[1, :v.numel()] = (v - hi.float()).bfloat16().reshape(-1)
+    act = N.Act()
+    for p in range(planes):
+        act.data[p] = mem.add(buf[p])
+    act.planes, act.n, act.h, act.w, act.c, act.pad = planes, n, h, w, cs, pad
+    recon = buf[:, :v.numel()].float().sum(0).reshape(n, h + 2 * pad, w + 2 * pad, cs)[..., :c].permute(0, 3, 1, 2)
+    return act, buf, recon.double()      # recon = what the tensor cores will effectively see (already padded)
+
+
+def out_spec(mem, n, h, w, c, kind=N.OUT_F32, pad=0, act=N.ACT_NONE, bias=None, mirror=0):
+    hp, wp = h + 2 * pad, w + 2 * pad
+    dt = torch.float32 if kind in (N.OUT_F32, N.OUT_F32_ATOMIC) else torch.bfloat16
+    planes = 2 if kind == N.OUT_SPLIT else 1
+    buf = torch.zeros(planes, n, hp, wp, c, dtype=dt)
+    o = N.OutSpec()
+    for p in range(planes):
+        o.ptr[p] = mem.add(buf[p])
+    o.kind, o.act, o.slope, o.mirror = kind, act, 0.2, mirror
+    o.off = (pad * wp + pad) * c
+    o.sn, o.sy, o.sx, o.sc = hp * wp * c, wp * c, c, 1
+    o.N, o.H, o.W, o.C = n, h, w, c
+    if bias is not None:
+        o.bias = mem.add(bias)
+    return o, buf
+
+
+FWD_CASES = [
+    # cin, cout, k, stride, pad, window, n, h, w, planes
+    (64, 64, 3, 1, 1, 0, 2, 8, 8, 1),
+    (64, 128, 4, 2, 1, 0, 2, 16, 16, 1),
+    (128, 64, 5, 1, 2, 0, 1, 8, 16, 1),
+    (64, 32, 3, 1, 1, 0, 3, 4, 4, 2),
+    (3, 64, 7, 1, 3, 1, 1, 8, 16, 1),
+    (6, 16, 4, 2, 1, 1, 2, 8, 8, 1),
+    (64, 4, 7, 1, 3, 0, 1, 8, 8, 1),
+    (64, 48, 4, 2, 1, 0, 1, 2, 2, 1),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,s,pad,window,n,h,w,planes", FWD_CASES)
+def test_conv_fwd_plan(cin, cout, k, s, pad, window, n, h, w, planes):
+    L = N.lib()
+    torch.manual_seed(0)
+    mem = emul.Memory()
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, k, k) * 0.1
+    bias = torch.randn(cout)
+    desc = N.ConvDesc(cin, cout, k, s, pad, window)
+    cs = (16 if s == 2 else 8) if window else ((cin + 63) // 64) * 64
+    act, abuf, xeff = make_act(mem, x, pad, cs, planes)
+    wp_hi = emul.pack_weight(desc, wt, False)
+    wts = [wp_hi]
+    weff = wt.bfloat16().double()
+    if planes == 2:
+        wts.append(emul.pack_weight(desc, wt - wt.bfloat16().float(), False))
+        weff = weff + (wt - wt.bfloat16().float()).bfloat16().double()
+    wptr = (C.c_uint64 * 2)(*[mem.add(t) for t in wts] + [0] * (2 - len(wts)))
+    ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+    o, obuf = out_spec(mem, n, ho, wo, cout, N.OUT_F32, pad=1, act=N.ACT_LRELU, bias=bias, mirror=1)
+    plan = N.IgemmPlan()
+    N.check(L.aclgan_plan_conv_fwd(C.byref(desc), C.byref(act), wptr, C.byref(o), C.byref(plan)), "plan fwd")
+    emul.run_igemm(mem, plan)
+    ref = F.conv2d(xeff, weff, bias.double(), stride=s)
+    ref = F.leaky_relu(ref, 0.2)
+    ref = F.pad(ref, (1, 1, 1, 1), mode="reflect") if min(ho, wo) > 1 else None
+    got = obuf[0].permute(0, 3, 1, 2).double()
+    if ref is None:
+        ref = F.leaky_relu(F.conv2d(xeff, weff, bias.double(), stride=s), 0.2)
+        got = got[:, :, 1:-1, 1:-1]
+    tol = 1e-6 if planes == 1 else 2e-4
+    assert torch.allclose(got, ref, rtol=tol, atol=tol), float((got - ref).abs().max())
+
+
+DGRAD_CASES = [
+    # cin, cout, k, stride, pad, n, ho, wo, planes
+    (64, 64, 3, 1, 1, 2, 6, 6, 1),
+    (64, 128, 4, 2, 1, 1, 4, 4, 1),
+    (128, 64, 5, 1, 2, 1, 4, 8, 1),
+    (3, 64, 7, 1, 3, 1, 4, 4, 1),
+    (64, 64, 4, 2, 1, 2, 2, 2, 2),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,s,pad,n,ho,wo,planes", DGRAD_CASES)
+def test_conv_dgrad_plan(cin, cout, k, s, pad, n, ho, wo, planes):
+    L = N.lib()
+    torch.manual_seed(1)
+    mem = emul.Memory()
+    dy = torch.randn(n, cout, ho, wo)
+    wt = torch.randn(cout, cin, k, k) * 0.1
+    desc = N.ConvDesc(cin, cout, k, s, pad, 0)
+    pz = k - 1 if s == 1 else k // 2 - 1
+    cs = ((cout + 63) // 64) * 64
+    act, abuf, dyeff = make_act(mem, dy, pz, cs, planes, mode="constant")
+    dyeff = dyeff[:, :, pz:pz + ho, pz:pz + wo] if pz > 0 else dyeff
+    wts = [emul.pack_weight(desc, wt, True)]
+    weff = wt.bfloat16().double()
+    if planes == 2:
+        wts.append(emul.pack_weight(desc, wt - wt.bfloat16().float(), True))
+        weff = weff + (wt - wt.bfloat16().float()).bfloat16().double()
+    wptr = (C.c_uint64 * 2)(*[mem.add(t) for t in wts] + [0] * (2 - len(wts)))
+    hp = (ho - 1) * s + k
+    wp = (wo - 1) * s + k
+    cin_s = ((cin + 15) // 16) * 16
+    obuf = torch.zeros(n, hp, wp, cin_s, dtype=torch.float32)
+    optr = mem.add(obuf)
+    for phase in range(1 if s == 1 else 4):
+        o = N.OutSpec()
+        o.ptr[0] = optr
+        o.kind, o.act, o.mirror = N.OUT_F32, N.ACT_NONE, 0
+        pa, pb = phase >> 1, phase & 1
+        o.off = (pa * wp + pb) * cin_s if s == 2 else 0
+        o.sn, o.sy, o.sx, o.sc = hp * wp * cin_s, s * wp * cin_s, s * cin_s, 1
+        o.N, o.H, o.W, o.C = n, hp // s, wp // s, cin_s
+        plan = N.IgemmPlan()
+        N.check(L.aclgan_plan_conv_dgrad(C.byref(desc), C.byref(act), wptr, phase, C.byref(o), C.byref(plan)), "plan dgrad")
+        emul.run_igemm(mem, plan)
+    ref = F.conv_transpose2d(dyeff, weff, stride=s)            # gradient w.r.t. the padded input
+    got = obuf.permute(0, 3, 1, 2).double()[:, :cin]
+    tol = 1e-6 if planes == 1 else 2e-4
+    assert got.shape == ref.shape
+    assert torch.allclose(got, ref, rtol=tol, atol=tol), float((got - ref).abs().max())
+    assert float(obuf[..., cin:].abs().max()) == 0 if cin_s > cin else True
+
+
+WGRAD_CASES = [
+    # cin, cout, k, stride, pad, window, n, h, w, planes
+    (64, 64, 3, 1, 1, 0, 2, 8, 8, 1),
+    (64, 128, 4, 2, 1, 0, 2, 16, 16, 1),
+    (128, 64, 5, 1, 2, 0, 1, 8, 16, 1),       # swapped roles (cout < 128, cout < cin)
+    (256, 128, 3, 1, 1, 0, 1, 4, 4, 2),
+    (3, 64, 7, 1, 3, 1, 1, 8, 16, 1),
+    (6, 64, 4, 2, 1, 1, 2, 8, 8, 1),
+    (64, 4, 7, 1, 3, 2, 1, 8, 8, 1),
+    (128, 64, 4, 2, 1, 0, 3, 4, 4, 1),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,s,pad,window,n,h,w,planes", WGRAD_CASES)
+def test_conv_wgrad_plan(cin, cout, k, s, pad, window, n, h, w, planes):
+    L = N.lib()
+    torch.manual_seed(2)
+    mem = emul.Memory()
+    desc = N.ConvDesc(cin, cout, k, s, pad, window)
+    ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+    x = torch.randn(n, cin, h, w)
+    dy = torch.randn(n, cout, ho, wo)
+    cs_x = (16 if s == 2 else 8) if window == 1 else ((cin + 63) // 64) * 64
+    cs_y = 8 if window == 2 else ((cout + 63) // 64) * 64
+    pz = (k - 1) if (s == 1) else (k // 2 - 1)
+    xact, _, xeff = make_act(mem, x, pad, cs_x, planes)
+    yact, _, yeff = make_act(mem, dy, pz, cs_y, planes, mode="constant")
+    yeff = yeff[:, :, pz:pz + ho, pz:pz + wo]
+    layout = L.aclgan_wgrad_layout(C.byref(desc))
+    rows, kt = C.c_int64(), C.c_int64()
+    L.aclgan_packed_weight_shape(C.byref(desc), layout, C.byref(rows), C.byref(kt))
+    dw = torch.zeros(rows.value * kt.value, dtype=torch.float64)
+    plan = N.WgradPlan()
+    N.check(L.aclgan_plan_conv_wgrad(C.byref(desc), C.byref(yact), C.byref(xact), mem.add(dw), C.byref(plan)), "plan wgrad")
+    emul.run_wgrad(mem, plan)
+    got = emul.unpack_wgrad(desc, dw, (cout, cin, k, k))
+    ref = torch.nn.grad.conv2d_weight(xeff, (cout, cin, k, k), yeff, stride=s)
+    tol = 1e-6 if planes == 1 else 3e-4
+    assert torch.allclose(got, ref, rtol=tol, atol=tol * float(ref.abs().max())), float((got - ref).abs().max())

@@ -143,6 +143,132 @@ int aclgan_wgrad_layout(const aclgan_conv_desc* cd);
 int aclgan_igemm_launch(const aclgan_igemm_plan* plan, void* stream);
 int aclgan_wgrad_launch(const aclgan_wgrad_plan* plan, void* stream);
 
+
+/* ================= element-wise / reduction kernels around the convolutions ================= */
+
+enum { ACLGAN_NORM_NONE = 0, ACLGAN_NORM_IN = 1, ACLGAN_NORM_ADAIN = 2, ACLGAN_NORM_LN = 3 };
+enum { ACLGAN_MASK_NONE = 0, ACLGAN_MASK_FROM_Z = 1, ACLGAN_MASK_FROM_OUT = 2 };
+
+/* dense NHWC tensor (raw conv output / gradient), bf16 (kind 0) or fp32 (kind 1) */
+typedef struct aclgan_tensor4 {
+    uint64_t ptr;
+    int32_t kind;
+    int32_t n, h, w, c;
+} aclgan_tensor4;
+
+/* NCHW fp32 image(s) -> reflect-padded NHWC planes with 8|16 stored channels (reference: images.cuda(),
+ * train.py:67, nn.ReflectionPad2d of the first Conv2dBlock networks.py:319, torch.cat of the dis_2 pair
+ * trainer.py:132-133,279-280) */
+typedef struct aclgan_pack_img_args {
+    uint64_t src0, src1;   /* fp32 NCHW; src1 optional (second image of a concatenated pair) */
+    int32_t c0, c1;        /* channels taken from src0 / src1 */
+    int32_t n, h, w;
+    aclgan_act dst;        /* dst.c in {8,16}, dst.pad = reflect width */
+} aclgan_pack_img_args;
+int aclgan_pack_img(const aclgan_pack_img_args* a, void* stream);
+
+/* per-(n,c) sum and sum of squares of a raw conv output, accumulated in fp64 (first half of
+ * nn.InstanceNorm2d / F.batch_norm / LayerNorm statistics: networks.py:333,499-501,525-529) */
+int aclgan_norm_stats(const aclgan_tensor4* y, uint64_t sums /* double [n][c][2], zeroed by the caller */, void* stream);
+
+/* statistics -> per-(n,c) scale / shift (+ saved mean / inverse deviation for the backward pass).
+ *   IN    : scale = rstd, shift = -mean*rstd                       (biased var, eps inside sqrt)
+ *   ADAIN : scale = rstd*w[n,c], shift = b[n,c] - mean*scale       (networks.py:497-503)
+ *   LN    : per sample over C*H*W, UNBIASED std, eps outside: scale = g[c]/(std+eps)  (networks.py:525-535) */
+typedef struct aclgan_norm_finalize_args {
+    int32_t mode, n, c, hw;  /* c = stored channels */
+    int32_t c_valid;         /* logical channels (<= c); stored padding channels get scale = shift = 0 */
+    float eps;
+    uint64_t sums;          /* double [n][c][2] */
+    uint64_t w, b;          /* ADAIN: fp32 [n][c_valid]; LN: fp32 [c_valid] gamma / beta; IN: unused */
+    uint64_t scale, shift;  /* out fp32 [n][c] */
+    uint64_t mean, inv;     /* out fp32 [n][c] (LN: broadcast per sample) */
+    uint64_t sigma;         /* out fp32 [n] (LN only: the unbiased std) */
+} aclgan_norm_finalize_args;
+int aclgan_norm_finalize(const aclgan_norm_finalize_args* a, void* stream);
+
+/* out = act(y*scale + shift) (+ residual), written as the NEXT conv's reflect-padded (optionally 2x nearest
+ * upsampled) input plane(s)  (networks.py:367-370 norm+activation, :309 residual add, :256 nn.Upsample,
+ * :319 ReflectionPad2d of the consumer) */
+typedef struct aclgan_apply_args {
+    aclgan_tensor4 y;
+    uint64_t scale, shift;  /* fp32 [n][c], or 0 for identity */
+    int32_t act;
+    float slope;
+    int32_t has_res;
+    aclgan_act res;         /* residual source plane (same n,h,w,c), any pad */
+    int32_t upsample;       /* 1 | 2 */
+    aclgan_act dst;         /* n, h*upsample, w*upsample, c; pad = consumer's reflect width */
+} aclgan_apply_args;
+int aclgan_norm_apply(const aclgan_apply_args* a, void* stream);
+
+/* backward of  pad/upsample -> activation -> norm  for one block.
+ * g = fold(gp) (+ gr): gradient w.r.t. the block's logical output, gathered from the gradient of the padded
+ * (and upsampled) plane; dz = g * act'(z);  norm blocks: dy = ca*dz + cb*yhat + cc with yhat = (y-mean)*inv.
+ * `reduce` produces T1 = sum dz, T2 = sum dz*yhat per (n,c) in fp64; `apply` writes dy as zero-bordered plane(s). */
+typedef struct aclgan_block_bwd_args {
+    uint64_t gp;            /* gradient of the padded plane [n][u*h+2p][u*w+2p][c] or 0 */
+    int32_t g_kind;         /* 0 bf16, 1 fp32 (gp and gr) */
+    int32_t gp_pad, upsample;
+    uint64_t gr;            /* dense [n][h][w][c] additional gradient (residual branch) or 0 */
+    int32_t n, h, w, c;
+    int32_t mask_mode;      /* ACLGAN_MASK_* */
+    float slope;
+    aclgan_tensor4 y;       /* raw conv output (MASK_FROM_Z / norm blocks) */
+    uint64_t scale, shift;  /* fp32 [n][c] used in the forward pass */
+    aclgan_act out;         /* forward output plane (MASK_FROM_OUT) */
+    int32_t norm;           /* 0 | 1 */
+    uint64_t mean, inv;     /* fp32 [n][c] */
+    uint64_t sums;          /* double [n][c][2]: T1, T2 (written by reduce) */
+    uint64_t ca, cb, cc;    /* fp32 [n][c] (read by apply when norm) */
+    aclgan_act dy;          /* apply output, dy.pad = zero border */
+} aclgan_block_bwd_args;
+int aclgan_block_bwd_reduce(const aclgan_block_bwd_args* a, void* stream);
+int aclgan_block_bwd_apply(const aclgan_block_bwd_args* a, void* stream);
+
+/* T1/T2 -> (ca, cb, cc) and the parameter gradients of the norm layer */
+typedef struct aclgan_norm_bwd_finalize_args {
+    int32_t mode, n, c, hw;
+    int32_t c_valid;
+    uint64_t sums;          /* double [n][c][2] */
+    uint64_t inv, sigma;    /* forward saves */
+    uint64_t w;             /* ADAIN: fp32 [n][c] weight; LN: fp32 [c] gamma */
+    uint64_t ca, cb, cc;    /* out fp32 [n][c] */
+    uint64_t dw, db;        /* out: ADAIN fp32 [n][c] (assigned); LN fp32 [c] (accumulated: +=) ; IN unused */
+} aclgan_norm_bwd_finalize_args;
+int aclgan_norm_bwd_finalize(const aclgan_norm_bwd_finalize_args* a, void* stream);
+
+/* gradient of an NCHW fp32 image (optionally through tanh: d * (1 - out^2)) -> zero-bordered 8-channel planes
+ * feeding the final conv's dgrad / wgrad; also accumulates the bias gradient (sum over n,h,w) */
+typedef struct aclgan_img_grad_pack_args {
+    uint64_t dimg, out_img; /* fp32 NCHW [n][c][h][w]; out_img = tanh output or 0 */
+    int32_t n, c, h, w;
+    aclgan_act dy;          /* dy.c = 8 */
+    uint64_t dbias;         /* fp32 [c], accumulated */
+} aclgan_img_grad_pack_args;
+int aclgan_img_grad_pack(const aclgan_img_grad_pack_args* a, void* stream);
+
+/* first-layer dgrad output (fp32 [n][h+2p][w+2p][cs], gradient of the padded image plane) -> NCHW fp32 image
+ * gradient with the reflect padding folded back (adjoint of networks.py:319) */
+typedef struct aclgan_img_grad_unpack_args {
+    uint64_t src;
+    int32_t n, c, h, w, cs, pad;
+    int32_t c_off;          /* first stored channel taken from src (second image of a concatenated pair) */
+    uint64_t dst;           /* fp32 NCHW [n][c][h][w] */
+    int32_t accumulate;
+} aclgan_img_grad_unpack_args;
+int aclgan_img_grad_unpack(const aclgan_img_grad_unpack_args* a, void* stream);
+
+/* OIHW fp32 master weight -> packed bf16 plane(s); the packed index is affine in (co,ci,kh,kw) */
+typedef struct aclgan_pack_weight_args {
+    uint64_t w;
+    int32_t co, ci, kh, kw;
+    int64_t base, s_co, s_ci, s_kh, s_kw;
+    uint64_t dst[2];
+    int32_t planes;
+} aclgan_pack_weight_args;
+int aclgan_pack_weight(const aclgan_pack_weight_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

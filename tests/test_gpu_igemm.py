@@ -51,7 +51,7 @@ def test_conv_fwd(cin, cout, k, s, pad, window, n, h, w, planes):
         got = got[:, :, 1:-1, 1:-1]
     err = G.rel_err(got, ref)
     # operands are exactly representable; only the fp32 accumulation order differs (x3 also drops lo*lo)
-    assert err < (2e-6 if planes == 1 else 3e-5), err
+    assert err < (2e-5 if planes == 1 else 5e-5), err  # fp32 accumulation over K up to 6400
 
 
 def test_conv_fwd_bf16_store_and_split():
@@ -116,7 +116,7 @@ def test_conv_dgrad(cin, cout, k, s, pad, n, ho, wo, planes):
     ref = F.conv_transpose2d(dyeff, weff.cuda(), stride=s)
     got = obuf.permute(0, 3, 1, 2).double()[:, :cin]
     err = G.rel_err(got, ref)
-    assert err < (2e-6 if planes == 1 else 3e-5), err
+    assert err < (2e-5 if planes == 1 else 5e-5), err  # fp32 accumulation over K up to 6400
 
 
 def test_conv_fwd_throughput_report(capsys):

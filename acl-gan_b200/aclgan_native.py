@@ -29,7 +29,7 @@ class OutSpec(C.Structure):
     _fields_ = [("ptr", C.c_uint64 * 2), ("kind", C.c_int32), ("act", C.c_int32), ("slope", C.c_float),
                 ("mirror", C.c_int32), ("off", C.c_int64), ("sn", C.c_int64), ("sy", C.c_int64),
                 ("sx", C.c_int64), ("sc", C.c_int64), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("C", C.c_int32), ("bias", C.c_uint64), ("stats", C.c_uint64)]
+                ("C", C.c_int32), ("bias", C.c_uint64), ("bias_n", C.c_int32), ("stats", C.c_uint64)]
 
 
 class IgemmPlan(C.Structure):
@@ -67,6 +67,72 @@ class Act(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [("cin", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32), ("stride", C.c_int32),
                 ("pad", C.c_int32), ("window", C.c_int32)]
+
+
+NORM_NONE, NORM_IN, NORM_ADAIN, NORM_LN = 0, 1, 2, 3
+MASK_NONE, MASK_FROM_Z, MASK_FROM_OUT = 0, 1, 2
+WINDOW_NONE, WINDOW_IN, WINDOW_OUT = 0, 1, 2
+
+
+class Tensor4(C.Structure):
+    _fields_ = [("ptr", C.c_uint64), ("kind", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("c", C.c_int32)]
+
+
+class PackImgArgs(C.Structure):
+    _fields_ = [("src0", C.c_uint64), ("src1", C.c_uint64), ("c0", C.c_int32), ("c1", C.c_int32),
+                ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("dst", Act)]
+
+
+class NormFinalizeArgs(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("n", C.c_int32), ("c", C.c_int32), ("hw", C.c_int32),
+                ("c_valid", C.c_int32), ("eps", C.c_float), ("sums", C.c_uint64), ("w", C.c_uint64),
+                ("b", C.c_uint64), ("scale", C.c_uint64), ("shift", C.c_uint64), ("mean", C.c_uint64),
+                ("inv", C.c_uint64), ("sigma", C.c_uint64)]
+
+
+class ApplyArgs(C.Structure):
+    _fields_ = [("y", Tensor4), ("scale", C.c_uint64), ("shift", C.c_uint64), ("act", C.c_int32),
+                ("slope", C.c_float), ("has_res", C.c_int32), ("res", Act), ("upsample", C.c_int32), ("dst", Act)]
+
+
+class BlockBwdArgs(C.Structure):
+    _fields_ = [("gp", C.c_uint64), ("g_kind", C.c_int32), ("gp_pad", C.c_int32), ("upsample", C.c_int32),
+                ("gr", C.c_uint64), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+                ("mask_mode", C.c_int32), ("slope", C.c_float), ("y", Tensor4), ("scale", C.c_uint64),
+                ("shift", C.c_uint64), ("out", Act), ("norm", C.c_int32), ("mean", C.c_uint64),
+                ("inv", C.c_uint64), ("sums", C.c_uint64), ("ca", C.c_uint64), ("cb", C.c_uint64),
+                ("cc", C.c_uint64), ("dy", Act)]
+
+
+class NormBwdFinalizeArgs(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("n", C.c_int32), ("c", C.c_int32), ("hw", C.c_int32),
+                ("c_valid", C.c_int32), ("sums", C.c_uint64), ("inv", C.c_uint64), ("sigma", C.c_uint64),
+                ("w", C.c_uint64), ("ca", C.c_uint64), ("cb", C.c_uint64), ("cc", C.c_uint64),
+                ("dw", C.c_uint64), ("db", C.c_uint64)]
+
+
+class ImgGradPackArgs(C.Structure):
+    _fields_ = [("dimg", C.c_uint64), ("out_img", C.c_uint64), ("n", C.c_int32), ("c", C.c_int32),
+                ("h", C.c_int32), ("w", C.c_int32), ("dy", Act), ("dbias", C.c_uint64)]
+
+
+class ImgGradUnpackArgs(C.Structure):
+    _fields_ = [("src", C.c_uint64), ("n", C.c_int32), ("c", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("cs", C.c_int32), ("pad", C.c_int32), ("c_off", C.c_int32), ("dst", C.c_uint64),
+                ("accumulate", C.c_int32)]
+
+
+class PackWeightArgs(C.Structure):
+    _fields_ = [("w", C.c_uint64), ("co", C.c_int32), ("ci", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+                ("base", C.c_int64), ("s_co", C.c_int64), ("s_ci", C.c_int64), ("s_kh", C.c_int64),
+                ("s_kw", C.c_int64), ("dst", C.c_uint64 * 2), ("planes", C.c_int32)]
+
+
+class AdamTensor(C.Structure):
+    _fields_ = [("p", C.c_uint64), ("m", C.c_uint64), ("v", C.c_uint64), ("g", C.c_uint64),
+                ("d", C.c_int32 * 4), ("gs", C.c_int64 * 4), ("goff", C.c_int64),
+                ("pk", (C.c_uint64 * 2) * 2), ("aff", (C.c_int64 * 5) * 2), ("planes", C.c_int32), ("pad_", C.c_int32)]
 
 
 class NativeError(RuntimeError):
@@ -136,9 +202,27 @@ def _declare(L):
                                          C.POINTER(WgradPlan)]
     L.aclgan_wgrad_layout.argtypes = [C.POINTER(ConvDesc)]
     L.aclgan_wgrad_launch.argtypes = [C.POINTER(WgradPlan), C.c_void_p]
+    L.aclgan_pack_img.argtypes = [C.POINTER(PackImgArgs), C.c_void_p]
+    L.aclgan_norm_stats.argtypes = [C.POINTER(Tensor4), C.c_uint64, C.c_void_p]
+    L.aclgan_norm_finalize.argtypes = [C.POINTER(NormFinalizeArgs), C.c_void_p]
+    L.aclgan_norm_apply.argtypes = [C.POINTER(ApplyArgs), C.c_void_p]
+    L.aclgan_block_bwd_reduce.argtypes = [C.POINTER(BlockBwdArgs), C.c_void_p]
+    L.aclgan_block_bwd_apply.argtypes = [C.POINTER(BlockBwdArgs), C.c_void_p]
+    L.aclgan_norm_bwd_finalize.argtypes = [C.POINTER(NormBwdFinalizeArgs), C.c_void_p]
+    L.aclgan_img_grad_pack.argtypes = [C.POINTER(ImgGradPackArgs), C.c_void_p]
+    L.aclgan_img_grad_unpack.argtypes = [C.POINTER(ImgGradUnpackArgs), C.c_void_p]
+    L.aclgan_pack_weight.argtypes = [C.POINTER(PackWeightArgs), C.c_void_p]
+    L.aclgan_adam_step.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_void_p]
+    L.aclgan_adam_advance.argtypes = [C.c_uint64, C.c_void_p]
+
+
+launch_count = 0
 
 
 def check(rc, what):
+    global launch_count
+    if not what.startswith("plan"):
+        launch_count += 1
     if rc != 0:
         raise NativeError("%s failed with status %d" % (what, rc))
 

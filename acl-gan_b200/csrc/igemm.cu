@@ -131,7 +131,7 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmKParams& P, const uint
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         float t = __uint_as_float(raw[i]);
-        if (bias != nullptr && i < cnt) t += __ldg(bias + ch0 + i);
+        if (bias != nullptr && ch0 + i < o.bias_n) t += __ldg(bias + ch0 + i);
         v[i] = apply_act(t, o.act, o.slope);
     }
     if (o.stats != 0) {

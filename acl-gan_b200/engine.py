@@ -1,0 +1,499 @@
+"""Execution engine of the B200-native ACL-GAN step: activation planes, per-conv packed state, the fused
+block operators (forward + hand-scheduled backward on a tape) that networks.py / trainer.py compose.
+
+Nothing here falls back to eager PyTorch convolutions or to the CPU: every heavy operator is a launch of
+libaclgan_b200.so through the C ABI (include/aclgan_b200.h).  PyTorch provides device memory, streams and the
+tiny glue on [N, C]-sized vectors.
+
+Reference behaviour being reproduced (file:line under /root/reference): Conv2dBlock.forward networks.py:365-371,
+ResBlock.forward :306-310, nn.Upsample :256, AdaptiveInstanceNorm2d.forward :490-503, LayerNorm.forward
+:520-536, and autograd's backward of all of them under loss.backward() (trainer.py:169,292).
+"""
+import ctypes as C
+import math
+
+import torch
+
+import aclgan_native as N
+
+
+def _sp():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else 0)
+
+
+def round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class Precision:
+    """bf16: one bf16 plane, bf16 raw conv outputs and gradients (throughput mode).
+    fp32x3: hi/lo bf16 planes (3 tensor-core passes ~ fp32 products), fp32 raw outputs and gradients (parity mode)."""
+
+    def __init__(self, name):
+        assert name in ("bf16", "fp32x3"), name
+        self.name = name
+        self.planes = 1 if name == "bf16" else 2
+        self.kind = 0 if name == "bf16" else 1          # dense tensor kind: 0 bf16, 1 fp32
+        self.dtype = torch.bfloat16 if name == "bf16" else torch.float32
+
+
+class Tape:
+    """Hand-scheduled reverse pass: forward operators push closures, backward() runs them in reverse."""
+
+    def __init__(self, enabled=True):
+        self.ops = []
+        self.enabled = enabled
+
+    def push(self, fn):
+        if self.enabled:
+            self.ops.append(fn)
+
+    def backward(self):
+        while self.ops:
+            self.ops.pop()()
+
+
+class ActT:
+    """Reflect-padded NHWC activation plane(s): buf [planes, numel + slack] bf16."""
+
+    def __init__(self, eng, n, h, w, c_valid, pad, cs=None, zero=False):
+        self.eng = eng
+        self.n, self.h, self.w, self.c_valid, self.pad = n, h, w, c_valid, pad
+        self.c = cs if cs is not None else round_up(c_valid, 64)
+        self.planes = eng.prec.planes
+        self.numel = n * (h + 2 * pad) * (w + 2 * pad) * self.c
+        alloc = torch.zeros if (zero or self.c < 64 or self.c != c_valid) else torch.empty
+        self.buf = alloc((self.planes, self.numel + 64), dtype=torch.bfloat16, device=eng.device)
+        if alloc is torch.empty:
+            self.buf[:, self.numel:].zero_()
+        self.gp = None            # gradient of the padded plane [n, h+2p, w+2p, c] (engine gradient dtype)
+        self.gr = None            # dense gradient [n, h, w, c] (residual branches / heads)
+        self.requires_grad = False
+
+    def struct(self):
+        a = N.Act()
+        for p in range(self.planes):
+            a.data[p] = self.buf[p].data_ptr()
+        a.planes, a.n, a.h, a.w, a.c, a.pad = self.planes, self.n, self.h, self.w, self.c, self.pad
+        return a
+
+    def add_gp(self, g):
+        self.gp = g if self.gp is None else self.gp.add_(g)
+
+    def add_gr(self, g):
+        self.gr = g if self.gr is None else self.gr.add_(g)
+
+    def value_nchw(self):
+        """fp32 NCHW copy of the logical (un-padded, valid-channel) content - for tests / API boundaries."""
+        p = self.pad
+        v = self.buf[:, :self.numel].float().sum(0).view(self.n, self.h + 2 * p, self.w + 2 * p, self.c)
+        v = v[:, p:p + self.h, p:p + self.w, :self.c_valid]
+        return v.permute(0, 3, 1, 2).contiguous()
+
+
+class ImgT:
+    """NCHW fp32 image tensor with an optional gradient accumulator (images cross the API boundary in the
+    reference's own layout: trainer.py passes B x 3 x H x W fp32 tensors)."""
+
+    def __init__(self, t, requires_grad=False):
+        self.t = t.contiguous()
+        self.requires_grad = requires_grad
+        self.grad = None
+
+    def add_grad(self, g):
+        self.grad = g if self.grad is None else self.grad.add_(g)
+
+
+class GradArena:
+    """One flat fp32 buffer per optimizer group (generators / discriminators) holding every gradient of the
+    group: a single memset per step and a single NCCL all-reduce."""
+
+    def __init__(self, device):
+        self.device = device
+        self.sizes = []
+        self.flat = None
+
+    def reserve(self, numel):
+        off = sum(self.sizes)
+        self.sizes.append(round_up(numel, 4))       # keep 16 B alignment for float4 atomics
+        return off
+
+    def finalize(self):
+        self.flat = torch.zeros(max(4, sum(self.sizes)), dtype=torch.float32, device=self.device)
+
+    def view(self, off, numel):
+        return self.flat[off:off + numel]
+
+    def zero_(self):
+        self.flat.zero_()
+
+
+def _affine_index(desc, transposed, shape):
+    """coefficients of the (affine) packed-weight index function of the C library"""
+    L = N.lib()
+    co, ci, kh, kw = shape
+
+    def idx(a, b, c, d):
+        return L.aclgan_packed_weight_index(C.byref(desc), int(transposed), a, b, c, d)
+
+    base = idx(0, 0, 0, 0)
+    return (base, idx(1, 0, 0, 0) - base if co > 1 else 0, idx(0, 1, 0, 0) - base if ci > 1 else 0,
+            idx(0, 0, 1, 0) - base if kh > 1 else 0, idx(0, 0, 0, 1) - base if kw > 1 else 0)
+
+
+class ConvLayer:
+    """Engine-side state of one nn.Conv2d parameter pair: packed bf16 weights (forward / transposed, hi[/lo])
+    derived from the fp32 OIHW master parameter, and the slice of the gradient arena its wgrad kernel fills."""
+
+    def __init__(self, eng, arena, weight, bias, stride, pad, window=N.WINDOW_NONE):
+        self.eng = eng
+        self.weight, self.bias = weight, bias
+        co, ci, k, _ = weight.shape
+        self.cout, self.cin, self.k, self.stride, self.pad, self.window = co, ci, k, stride, pad, window
+        self.desc = N.ConvDesc(ci, co, k, stride, pad, window)
+        L = N.lib()
+        self.packed = {}
+        self.aff = {}
+        for tr in (0, 1):
+            rows, kt = C.c_int64(), C.c_int64()
+            L.aclgan_packed_weight_shape(C.byref(self.desc), tr, C.byref(rows), C.byref(kt))
+            self.packed[tr] = torch.zeros((eng.prec.planes, rows.value * kt.value), dtype=torch.bfloat16,
+                                          device=eng.device)
+            self.aff[tr] = _affine_index(self.desc, tr, weight.shape)
+            setattr(self, "shape%d" % tr, (rows.value, kt.value))
+        self.layout = L.aclgan_wgrad_layout(C.byref(self.desc))
+        rows, kt = getattr(self, "shape%d" % self.layout)
+        self.arena = arena
+        self.dw_off = arena.reserve(rows * kt)
+        self.dw_numel = rows * kt
+        self.db_off = arena.reserve(co)
+        self.dirty = True
+
+    # -- packed weights -------------------------------------------------------------------------------
+    def repack(self):
+        L = N.lib()
+        w = self.weight.detach()
+        co, ci, kh, kw = w.shape
+        for tr in (0, 1):
+            a = N.PackWeightArgs()
+            a.w = w.data_ptr()
+            a.co, a.ci, a.kh, a.kw = co, ci, kh, kw
+            a.base, a.s_co, a.s_ci, a.s_kh, a.s_kw = self.aff[tr]
+            for p in range(self.eng.prec.planes):
+                a.dst[p] = self.packed[tr][p].data_ptr()
+            a.planes = self.eng.prec.planes
+            N.check(L.aclgan_pack_weight(C.byref(a), _sp()), "pack_weight")
+        self.dirty = False
+
+    def wptr(self, tr):
+        if self.dirty:
+            self.repack()
+        t = self.packed[tr]
+        return (C.c_uint64 * 2)(t[0].data_ptr(), t[1].data_ptr() if t.shape[0] > 1 else 0)
+
+    # -- gradients ------------------------------------------------------------------------------------
+    def dw(self):
+        return self.arena.view(self.dw_off, self.dw_numel)
+
+    def db(self):
+        return self.arena.view(self.db_off, self.cout)
+
+    def grad_views(self):
+        """(weight grad in OIHW shape, bias grad) as views of the arena (a small copy for the one layout whose
+        kw stride is negative)."""
+        base, s_co, s_ci, s_kh, s_kw = self.aff[self.layout]
+        co, ci, kh, kw = self.weight.shape
+        dw = self.dw()
+        if s_kw >= 0:
+            g = torch.as_strided(dw, (co, ci, kh, kw), (s_co, s_ci, s_kh, s_kw), base)
+        else:
+            g = torch.as_strided(dw, (co, ci, kh, kw), (s_co, s_ci, s_kh, -s_kw), base + (kw - 1) * s_kw).flip(3)
+        return g, self.db()
+
+
+class Engine:
+    def __init__(self, precision="bf16", device="cuda"):
+        self.prec = Precision(precision) if isinstance(precision, str) else precision
+        self.device = torch.device(device)
+        self._check_device()
+        N.lib()
+        self.eps = 1e-5
+
+    def _check_device(self):
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise N.NativeError("aclgan_b200 has no CPU path: a CUDA device is required")
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def new_dense(self, n, h, w, c, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f((n, h, w, c), dtype=self.prec.dtype, device=self.device)
+
+    def t4(self, t):
+        n, h, w, c = t.shape
+        return N.Tensor4(t.data_ptr(), self.prec.kind, n, h, w, c)
+
+    # ------------------------------------------------------------------------------------------ image I/O
+    def pack_image(self, tape, img0, pad, cs, img1=None):
+        """NCHW fp32 image (optionally the channel concat of two images) -> reflect-padded plane."""
+        t0 = img0.t
+        n, c0, h, w = t0.shape
+        c1 = img1.t.shape[1] if img1 is not None else 0
+        out = ActT(self, n, h, w, c0 + c1, pad, cs=cs, zero=True)
+        a = N.PackImgArgs()
+        a.src0 = t0.data_ptr()
+        a.src1 = img1.t.data_ptr() if img1 is not None else 0
+        a.c0, a.c1, a.n, a.h, a.w = c0, c1, n, h, w
+        a.dst = out.struct()
+        N.check(N.lib().aclgan_pack_img(C.byref(a), _sp()), "pack_img")
+        out.requires_grad = img0.requires_grad or (img1 is not None and img1.requires_grad)
+        if out.requires_grad:
+            def bwd():
+                if out.gp is None:
+                    return
+                for img, off in ((img0, 0), (img1, c0)):
+                    if img is None or not img.requires_grad:
+                        continue
+                    u = N.ImgGradUnpackArgs()
+                    g = torch.empty_like(img.t)
+                    u.src = out.gp.data_ptr()
+                    u.n, u.c, u.h, u.w = n, img.t.shape[1], h, w
+                    u.cs, u.pad, u.c_off = out.gp.shape[-1], pad, off
+                    u.dst, u.accumulate = g.data_ptr(), 0
+                    N.check(N.lib().aclgan_img_grad_unpack(C.byref(u), _sp()), "img_grad_unpack")
+                    img.add_grad(g)
+                out.gp = None
+            tape.push(bwd)
+        return out
+
+    # ------------------------------------------------------------------------------------------ conv pieces
+    def _out_plane(self, dst, act, bias, slope=0.2):
+        """OutSpec that makes a conv epilogue write straight into plane `dst` (interior + reflect halo)."""
+        o = N.OutSpec()
+        hp, wp = dst.h + 2 * dst.pad, dst.w + 2 * dst.pad
+        for p in range(dst.planes):
+            o.ptr[p] = dst.buf[p].data_ptr()
+        o.kind = N.OUT_BF16 if dst.planes == 1 else N.OUT_SPLIT
+        o.act, o.slope, o.mirror = act, slope, dst.pad
+        o.off = (dst.pad * wp + dst.pad) * dst.c
+        o.sn, o.sy, o.sx, o.sc = hp * wp * dst.c, wp * dst.c, dst.c, 1
+        o.N, o.H, o.W, o.C = dst.n, dst.h, dst.w, dst.c
+        o.bias = bias.data_ptr() if bias is not None else 0
+        o.bias_n = bias.numel() if bias is not None else 0
+        return o
+
+    def _out_dense(self, t, bias=None, act=N.ACT_NONE):
+        n, h, w, c = t.shape
+        o = N.OutSpec()
+        o.ptr[0] = t.data_ptr()
+        o.kind = N.OUT_BF16 if t.dtype == torch.bfloat16 else N.OUT_F32
+        o.act, o.slope, o.mirror, o.off = act, 0.2, 0, 0
+        o.sn, o.sy, o.sx, o.sc = h * w * c, w * c, c, 1
+        o.N, o.H, o.W, o.C = n, h, w, c
+        o.bias = bias.data_ptr() if bias is not None else 0
+        o.bias_n = bias.numel() if bias is not None else 0
+        return o
+
+    def conv_fwd_launch(self, layer, x, ospec):
+        plan = N.IgemmPlan()
+        xs = x.struct()
+        N.check(N.lib().aclgan_plan_conv_fwd(C.byref(layer.desc), C.byref(xs), layer.wptr(0), C.byref(ospec),
+                                             C.byref(plan)), "plan_conv_fwd")
+        N.check(N.lib().aclgan_igemm_launch(C.byref(plan), _sp()), "igemm_launch(fwd)")
+
+    def conv_out_hw(self, layer, x):
+        hp, wp = x.h + 2 * x.pad, x.w + 2 * x.pad
+        return (hp - layer.k) // layer.stride + 1, (wp - layer.k) // layer.stride + 1
+
+    def conv_dgrad(self, layer, dy, x):
+        """gradient w.r.t. the padded input plane of `layer`: dense [n, hp, wp, cs] in the gradient dtype."""
+        hp, wp = x.h + 2 * x.pad, x.w + 2 * x.pad
+        cs = x.c if x.c >= 64 else 16           # image planes: 3|6 channels -> one 16-wide UMMA column block
+        if x.c < 64:
+            g = torch.zeros((x.n, hp, wp, cs), dtype=torch.float32, device=self.device)
+        else:
+            g = self.new_dense(x.n, hp, wp, cs, zero=(cs != round_up(layer.cin, 16)))
+        dys = dy.struct()
+        s = layer.stride
+        for phase in range(1 if s == 1 else 4):
+            o = self._out_dense(g)
+            pa, pb = phase >> 1, phase & 1
+            if s == 2:
+                o.off = (pa * wp + pb) * cs
+                o.sy, o.sx = 2 * wp * cs, 2 * cs
+                o.H, o.W = hp // 2, wp // 2
+            plan = N.IgemmPlan()
+            N.check(N.lib().aclgan_plan_conv_dgrad(C.byref(layer.desc), C.byref(dys), layer.wptr(1), phase,
+                                                   C.byref(o), C.byref(plan)), "plan_conv_dgrad")
+            N.check(N.lib().aclgan_igemm_launch(C.byref(plan), _sp()), "igemm_launch(dgrad)")
+        return g
+
+    def conv_wgrad(self, layer, dy, x):
+        plan = N.WgradPlan()
+        dys, xs = dy.struct(), x.struct()
+        N.check(N.lib().aclgan_plan_conv_wgrad(C.byref(layer.desc), C.byref(dys), C.byref(xs),
+                                               layer.dw().data_ptr(), C.byref(plan)), "plan_conv_wgrad")
+        N.check(N.lib().aclgan_wgrad_launch(C.byref(plan), _sp()), "wgrad_launch")
+
+    def dy_pad(self, layer):
+        if layer.window == N.WINDOW_OUT or layer.stride == 1:
+            return layer.k - 1
+        return layer.k // 2 - 1
+
+    # ------------------------------------------------------------------------------------------ conv block
+    def conv_block(self, tape, layer, x, norm=N.NORM_NONE, act=N.ACT_NONE, out_pad=0, upsample=1, res=None,
+                   adain=None, ln=None, train_w=True):
+        """pad -> conv -> norm -> activation (-> + residual) -> [2x nearest upsample] -> reflect pad of the consumer.
+        adain = (weight [n,c], bias [n,c], grad holder dict) ; ln = (gamma, beta, dgamma view, dbeta view)."""
+        L = N.lib()
+        ho, wo = self.conv_out_hw(layer, x)
+        n, cout = x.n, layer.cout
+        slope = 0.2
+        if norm == N.NORM_NONE:
+            assert upsample == 1 and res is None
+            out = ActT(self, n, ho, wo, cout, out_pad)
+            self.conv_fwd_launch(layer, x, self._out_plane(out, act, layer.bias, slope))
+            saved = None
+        else:
+            cs = round_up(cout, 64)
+            y = self.new_dense(n, ho, wo, cs, zero=(cs != cout))
+            self.conv_fwd_launch(layer, x, self._out_dense(y, layer.bias))
+            sums = torch.zeros((n, cs, 2), dtype=torch.float64, device=self.device)
+            y4 = self.t4(y)
+            N.check(L.aclgan_norm_stats(C.byref(y4), sums.data_ptr(), _sp()), "norm_stats")
+            coef = torch.empty((4, n, cs), dtype=torch.float32, device=self.device)   # scale, shift, mean, inv
+            sigma = torch.empty((n,), dtype=torch.float32, device=self.device)
+            f = N.NormFinalizeArgs()
+            f.mode, f.n, f.c, f.hw, f.c_valid, f.eps = norm, n, cs, ho * wo, cout, self.eps
+            f.sums = sums.data_ptr()
+            if norm == N.NORM_ADAIN:
+                f.w, f.b = adain[0].data_ptr(), adain[1].data_ptr()
+            elif norm == N.NORM_LN:
+                f.w, f.b = ln[0].data_ptr(), ln[1].data_ptr()
+            f.scale, f.shift, f.mean, f.inv = (coef[i].data_ptr() for i in range(4))
+            f.sigma = sigma.data_ptr()
+            N.check(L.aclgan_norm_finalize(C.byref(f), _sp()), "norm_finalize")
+            out = ActT(self, n, ho * upsample, wo * upsample, cout, out_pad)
+            a = N.ApplyArgs()
+            a.y, a.scale, a.shift, a.act, a.slope = y4, coef[0].data_ptr(), coef[1].data_ptr(), act, slope
+            a.has_res = 1 if res is not None else 0
+            if res is not None:
+                a.res = res.struct()
+            a.upsample, a.dst = upsample, out.struct()
+            N.check(L.aclgan_norm_apply(C.byref(a), _sp()), "norm_apply")
+            saved = (y, coef, sigma)
+        need_x_grad = x.requires_grad
+        out.requires_grad = need_x_grad or train_w or (res is not None and res.requires_grad) or adain is not None
+        if not tape.enabled or not out.requires_grad:
+            return out
+
+        def bwd():
+            gp, gr = out.gp, out.gr
+            out.gp = out.gr = None
+            if gp is None and gr is None:
+                return
+            if res is not None and res.requires_grad:
+                # gradient of the residual branch = gradient of the block output (dense, un-padded)
+                res.add_gr(self._fold_only(gp, gr, out, upsample))
+            b = N.BlockBwdArgs()
+            b.gp = gp.data_ptr() if gp is not None else 0
+            b.gr = gr.data_ptr() if gr is not None else 0
+            b.g_kind, b.gp_pad, b.upsample = self.prec.kind, out.pad, upsample
+            cs = round_up(cout, 64)
+            b.n, b.h, b.w, b.c = n, ho, wo, cs
+            b.slope = 0.0 if act == N.ACT_RELU else slope
+            dy = ActT(self, n, ho, wo, cout, self.dy_pad(layer))
+            b.dy = dy.struct()
+            sums = torch.zeros((n, cs, 2), dtype=torch.float64, device=self.device)
+            b.sums = sums.data_ptr()
+            if norm == N.NORM_NONE:
+                b.norm = 0
+                b.mask_mode = N.MASK_NONE if act == N.ACT_NONE else N.MASK_FROM_OUT
+                b.out = out.struct()
+                if train_w:
+                    N.check(L.aclgan_block_bwd_reduce(C.byref(b), _sp()), "block_bwd_reduce")
+                    layer.db().add_(sums[:, :cout, 0].sum(0).float())
+            else:
+                y, coef, sigma = saved
+                b.norm = 1
+                b.mask_mode = N.MASK_NONE if act == N.ACT_NONE else N.MASK_FROM_Z
+                b.y = self.t4(y)
+                b.scale, b.shift, b.mean, b.inv = (coef[i].data_ptr() for i in range(4))
+                N.check(L.aclgan_block_bwd_reduce(C.byref(b), _sp()), "block_bwd_reduce")
+                cf = torch.empty((3, n, cs), dtype=torch.float32, device=self.device)
+                f = N.NormBwdFinalizeArgs()
+                f.mode, f.n, f.c, f.hw, f.c_valid = norm, n, cs, ho * wo, cout
+                f.sums, f.inv, f.sigma = sums.data_ptr(), coef[3].data_ptr(), sigma.data_ptr()
+                if norm == N.NORM_ADAIN:
+                    dwb = torch.empty((2, n, cout), dtype=torch.float32, device=self.device)
+                    f.w, f.dw, f.db = adain[0].data_ptr(), dwb[0].data_ptr(), dwb[1].data_ptr()
+                    adain[2](dwb[0], dwb[1])
+                elif norm == N.NORM_LN:
+                    f.w, f.dw, f.db = ln[0].data_ptr(), ln[2].data_ptr(), ln[3].data_ptr()
+                f.ca, f.cb, f.cc = (cf[i].data_ptr() for i in range(3))
+                N.check(L.aclgan_norm_bwd_finalize(C.byref(f), _sp()), "norm_bwd_finalize")
+                b.ca, b.cb, b.cc = (cf[i].data_ptr() for i in range(3))
+            N.check(L.aclgan_block_bwd_apply(C.byref(b), _sp()), "block_bwd_apply")
+            if train_w:
+                self.conv_wgrad(layer, dy, x)
+            if need_x_grad:
+                x.add_gp(self.conv_dgrad(layer, dy, x))
+
+        tape.push(bwd)
+        return out
+
+    def _fold_only(self, gp, gr, out, upsample):
+        """dense gradient of the logical block output (fold of the padded / upsampled plane gradient)"""
+        if gp is None:
+            return gr.clone()
+        b = N.BlockBwdArgs()
+        cs = gp.shape[-1]
+        h, w = out.h // upsample, out.w // upsample
+        b.gp, b.gr = gp.data_ptr(), (gr.data_ptr() if gr is not None else 0)
+        b.g_kind, b.gp_pad, b.upsample = self.prec.kind, out.pad, upsample
+        b.n, b.h, b.w, b.c = out.n, h, w, cs
+        b.mask_mode, b.norm = N.MASK_NONE, 0
+        # block_bwd_apply writes bf16 plane(s); a dense gradient in the engine dtype is wanted here, so the fold
+        # goes through the plane writer and is read back as hi(+lo)
+        tmp = ActT(self, out.n, h, w, out.c_valid, 0)
+        b.dy = tmp.struct()
+        N.check(N.lib().aclgan_block_bwd_apply(C.byref(b), _sp()), "block_bwd_apply(fold)")
+        v = tmp.buf[:, :tmp.numel].float().sum(0) if self.prec.planes == 2 else tmp.buf[0, :tmp.numel]
+        return v.view(out.n, h, w, cs).to(self.prec.dtype)
+
+    # ------------------------------------------------------------------------------------------ final conv
+    def conv_to_image(self, tape, layer, x, act=N.ACT_TANH, train_w=True):
+        """last decoder block: conv -> tanh -> NCHW fp32 image (networks.py:260)"""
+        ho, wo = self.conv_out_hw(layer, x)
+        n, cout = x.n, layer.cout
+        img = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=self.device)
+        o = N.OutSpec()
+        o.ptr[0] = img.data_ptr()
+        o.kind, o.act, o.slope, o.mirror, o.off = N.OUT_F32, act, 0.2, 0, 0
+        o.sn, o.sy, o.sx, o.sc = cout * ho * wo, wo, 1, ho * wo
+        o.N, o.H, o.W, o.C = n, ho, wo, cout
+        o.bias = layer.bias.data_ptr()
+        o.bias_n = cout
+        self.conv_fwd_launch(layer, x, o)
+        out = ImgT(img, requires_grad=tape.enabled)
+        if not tape.enabled:
+            return out
+
+        def bwd():
+            if out.grad is None:
+                return
+            dy = ActT(self, n, ho, wo, cout, layer.k - 1, cs=8, zero=True)
+            a = N.ImgGradPackArgs()
+            a.dimg = out.grad.data_ptr()
+            a.out_img = img.data_ptr() if act == N.ACT_TANH else 0
+            a.n, a.c, a.h, a.w = n, cout, ho, wo
+            a.dy = dy.struct()
+            a.dbias = layer.db().data_ptr() if train_w else 0
+            N.check(N.lib().aclgan_img_grad_pack(C.byref(a), _sp()), "img_grad_pack")
+            out.grad = None
+            if train_w:
+                self.conv_wgrad(layer, dy, x)
+            if x.requires_grad:
+                x.add_gp(self.conv_dgrad(layer, dy, x))
+
+        tape.push(bwd)
+        return out

@@ -1,0 +1,629 @@
+"""Drop-in `networks` module of the B200-native ACL-GAN implementation.
+
+Same public classes, constructor signatures, child-module names and `state_dict` keys as the reference's
+networks.py (AdaINGen / MsImageDis / the block classes - SURVEY.md 8b), so checkpoints, `weights_init`
+(utils.py:274-294) and the optimizer parameter order interchange.  The modules own the fp32 OIHW master
+parameters; all arithmetic is done by `engine.Engine` through the CUDA extension - there is no eager /
+CPU forward: calling a network without a CUDA device raises.
+
+Two call levels:
+  * reference-compatible tensor API (`encode`, `decode`, `forward`, `calc_*_loss`): NCHW fp32 in / out,
+    forward values only (no autograd graph is attached to the results);
+  * engine API (`enc(...)`, `dec(...)`, `dis(...)`) used by trainer.py, which records the hand-scheduled
+    backward pass on an `engine.Tape`.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+import aclgan_native as N
+import engine as E
+
+_ACT = {"relu": N.ACT_RELU, "lrelu": N.ACT_LRELU, "tanh": N.ACT_TANH, "none": N.ACT_NONE}
+_NORM = {"none": N.NORM_NONE, "in": N.NORM_IN, "adain": N.NORM_ADAIN, "ln": N.NORM_LN}
+
+_default_engine = {}
+
+
+def get_engine(precision=None):
+    """process-wide engine per precision ('bf16' throughput mode, 'fp32x3' parity mode)"""
+    import os
+    precision = precision or os.environ.get("ACLGAN_PRECISION", "bf16")
+    if precision not in _default_engine:
+        _default_engine[precision] = E.Engine(precision)
+    return _default_engine[precision]
+
+
+# ======================================================================================================
+# normalisation layers (parameter / buffer holders; the arithmetic lives in csrc/elementwise.cu)
+# ======================================================================================================
+class AdaptiveInstanceNorm2d(nn.Module):
+    """reference networks.py:477-506; weight / bias are assigned per forward by AdaINGen.decode"""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.weight = None
+        self.bias = None
+        self.register_buffer("running_mean", torch.zeros(num_features))   # never updated (networks.py:487-494)
+        self.register_buffer("running_var", torch.ones(num_features))
+
+    def __repr__(self):
+        return "%s(%d)" % (self.__class__.__name__, self.num_features)
+
+
+class LayerNorm(nn.Module):
+    """reference networks.py:509-536 (per-sample mean / unbiased std, eps outside, per-channel affine)"""
+
+    def __init__(self, num_features, eps=1e-5, affine=True):
+        super().__init__()
+        self.num_features, self.affine, self.eps = num_features, affine, eps
+        if affine:
+            self.gamma = nn.Parameter(torch.Tensor(num_features).uniform_())
+            self.beta = nn.Parameter(torch.zeros(num_features))
+
+
+def l2normalize(v, eps=1e-12):
+    return v / (v.norm() + eps)
+
+
+class SpectralNorm(nn.Module):
+    """option surface only (norm='sn' is not reachable from any shipped config)"""
+
+    def __init__(self, module, name="weight", power_iterations=1):
+        super().__init__()
+        raise NotImplementedError("spectral norm ('sn') is outside the B200 hot path")
+
+
+# ======================================================================================================
+# blocks
+# ======================================================================================================
+class Conv2dBlock(nn.Module):
+    """pad -> conv -> norm -> activation (reference networks.py:312-371)"""
+
+    def __init__(self, input_dim, output_dim, kernel_size, stride, padding=0, norm="none", activation="relu",
+                 pad_type="zero"):
+        super().__init__()
+        self.use_bias = True
+        if pad_type == "reflect":
+            self.pad = nn.ReflectionPad2d(padding)
+        elif pad_type in ("replicate", "zero"):
+            raise NotImplementedError("pad_type %r: only 'reflect' is implemented on the B200 path" % pad_type)
+        else:
+            assert 0, "Unsupported padding type: {}".format(pad_type)
+        if norm == "in":
+            self.norm = nn.InstanceNorm2d(output_dim)
+        elif norm == "ln":
+            self.norm = LayerNorm(output_dim)
+        elif norm == "adain":
+            self.norm = AdaptiveInstanceNorm2d(output_dim)
+        elif norm == "none":
+            self.norm = None
+        elif norm in ("bn", "sn"):
+            raise NotImplementedError("norm %r is outside the B200 hot path" % norm)
+        else:
+            assert 0, "Unsupported normalization: {}".format(norm)
+        if activation in ("relu", "lrelu", "tanh"):
+            self.activation = {"relu": nn.ReLU(inplace=True), "lrelu": nn.LeakyReLU(0.2, inplace=True),
+                               "tanh": nn.Tanh()}[activation]
+        elif activation == "none":
+            self.activation = None
+        elif activation in ("prelu", "selu"):
+            raise NotImplementedError("activation %r is outside the B200 hot path" % activation)
+        else:
+            assert 0, "Unsupported activation: {}".format(activation)
+        self.conv = nn.Conv2d(input_dim, output_dim, kernel_size, stride, bias=self.use_bias)
+        self.spec = dict(cin=input_dim, cout=output_dim, k=kernel_size, stride=stride, pad=padding,
+                         norm=norm, act=activation)
+        self._layer = None
+
+    def layer(self, eng, arena, window=N.WINDOW_NONE):
+        if self._layer is None or self._layer.eng is not eng:
+            self._layer = E.ConvLayer(eng, arena, self.conv.weight, self.conv.bias, self.spec["stride"],
+                                      self.spec["pad"], window)
+        return self._layer
+
+    def forward(self, x):
+        raise NotImplementedError("Conv2dBlock is executed by its owning network through the CUDA engine")
+
+
+class ResBlock(nn.Module):
+    def __init__(self, dim, norm="in", activation="relu", pad_type="zero"):
+        super().__init__()
+        self.model = nn.Sequential(
+            Conv2dBlock(dim, dim, 3, 1, 1, norm=norm, activation=activation, pad_type=pad_type),
+            Conv2dBlock(dim, dim, 3, 1, 1, norm=norm, activation="none", pad_type=pad_type))
+
+
+class ResBlocks(nn.Module):
+    def __init__(self, num_blocks, dim, norm="in", activation="relu", pad_type="zero"):
+        super().__init__()
+        self.model = nn.Sequential(*[ResBlock(dim, norm=norm, activation=activation, pad_type=pad_type)
+                                     for _ in range(num_blocks)])
+
+
+class LinearBlock(nn.Module):
+    def __init__(self, input_dim, output_dim, norm="none", activation="relu"):
+        super().__init__()
+        if norm != "none":
+            raise NotImplementedError("LinearBlock norm %r is outside the B200 hot path" % norm)
+        self.fc = nn.Linear(input_dim, output_dim, bias=True)
+        self.norm = None
+        if activation == "relu":
+            self.activation = nn.ReLU(inplace=True)
+        elif activation == "none":
+            self.activation = None
+        else:
+            raise NotImplementedError("LinearBlock activation %r" % activation)
+
+
+class MLP(nn.Module):
+    """style code -> AdaIN parameters (reference networks.py:280-292)"""
+
+    def __init__(self, input_dim, output_dim, dim, n_blk, norm="none", activ="relu"):
+        super().__init__()
+        blocks = [LinearBlock(input_dim, dim, norm=norm, activation=activ)]
+        blocks += [LinearBlock(dim, dim, norm=norm, activation=activ) for _ in range(n_blk - 2)]
+        blocks += [LinearBlock(dim, output_dim, norm="none", activation="none")]
+        self.model = nn.Sequential(*blocks)
+
+
+class StyleEncoder(nn.Module):
+    def __init__(self, n_downsample, input_dim, dim, style_dim, norm, activ, pad_type):
+        super().__init__()
+        m = [Conv2dBlock(input_dim, dim, 7, 1, 3, norm=norm, activation=activ, pad_type=pad_type)]
+        for _ in range(2):
+            m.append(Conv2dBlock(dim, 2 * dim, 4, 2, 1, norm=norm, activation=activ, pad_type=pad_type))
+            dim *= 2
+        for _ in range(n_downsample - 2):
+            m.append(Conv2dBlock(dim, dim, 4, 2, 1, norm=norm, activation=activ, pad_type=pad_type))
+        m.append(nn.AdaptiveAvgPool2d(1))
+        m.append(nn.Conv2d(dim, style_dim, 1, 1, 0))
+        self.model = nn.Sequential(*m)
+        self.output_dim = dim
+
+
+class ContentEncoder(nn.Module):
+    def __init__(self, n_downsample, n_res, input_dim, dim, norm, activ, pad_type):
+        super().__init__()
+        m = [Conv2dBlock(input_dim, dim, 7, 1, 3, norm=norm, activation=activ, pad_type=pad_type)]
+        for _ in range(n_downsample):
+            m.append(Conv2dBlock(dim, 2 * dim, 4, 2, 1, norm=norm, activation=activ, pad_type=pad_type))
+            dim *= 2
+        m.append(ResBlocks(n_res, dim, norm=norm, activation=activ, pad_type=pad_type))
+        self.model = nn.Sequential(*m)
+        self.output_dim = dim
+
+
+class Decoder(nn.Module):
+    def __init__(self, n_upsample, n_res, dim, output_dim, res_norm="adain", activ="relu", pad_type="zero"):
+        super().__init__()
+        m = [ResBlocks(n_res, dim, res_norm, activ, pad_type=pad_type)]
+        for _ in range(n_upsample):
+            m += [nn.Upsample(scale_factor=2),
+                  Conv2dBlock(dim, dim // 2, 5, 1, 2, norm="ln", activation=activ, pad_type=pad_type)]
+            dim //= 2
+        m.append(Conv2dBlock(dim, output_dim, 7, 1, 3, norm="none", activation="tanh", pad_type=pad_type))
+        self.model = nn.Sequential(*m)
+
+
+class _EngineNet(nn.Module):
+    """shared plumbing: lazily binds the parameters to an engine + gradient arena"""
+
+    def __init__(self):
+        super().__init__()
+        self._eng = None
+        self._arena = None
+        self._bound = False
+        self._own_arena = False
+        self.train_weights = True
+        self.register_load_state_dict_post_hook(lambda module, keys: module.mark_dirty())
+
+    def bind(self, eng, arena=None):
+        self._eng = eng
+        self._own_arena = arena is None
+        self._arena = arena if arena is not None else E.GradArena(eng.device)
+        self._bound = False
+
+    def _ensure_bound(self):
+        if self._eng is None:
+            self.bind(get_engine())
+        if not self._bound:
+            for p in self.parameters():
+                if p.device.type != "cuda":
+                    raise N.NativeError("aclgan_b200: parameters must live on a CUDA device (no CPU path)")
+            self._build_layers()
+            self._bound = True
+            if self._own_arena:
+                self._arena.finalize()
+                self.attach_grads()
+
+    def conv_layers(self):
+        return [m._layer for m in self.modules() if isinstance(m, Conv2dBlock) and m._layer is not None]
+
+    def mark_dirty(self):
+        for l in self.conv_layers():
+            l.dirty = True
+
+    def attach_grads(self):
+        """points every parameter's .grad at its slice of the arena (conv weights: strided OIHW views)"""
+        for blk in self.modules():
+            if isinstance(blk, Conv2dBlock) and blk._layer is not None:
+                gw, gb = blk._layer.grad_views()
+                blk.conv.weight.grad = gw
+                blk.conv.bias.grad = gb
+        for p, (off, numel) in getattr(self, "_dense_grads", []):
+            p.grad = self._arena.view(off, numel).view(p.shape)
+
+    def _reserve_dense(self, p):
+        if not hasattr(self, "_dense_grads"):
+            self._dense_grads = []
+        off = self._arena.reserve(p.numel())
+        self._dense_grads.append((p, (off, p.numel())))
+        return off
+
+    def _grad_of(self, p):
+        for q, (off, numel) in self._dense_grads:
+            if q is p:
+                return self._arena.view(off, numel).view(p.shape)
+        raise KeyError
+
+
+# ======================================================================================================
+# Generator
+# ======================================================================================================
+class AdaINGen(_EngineNet):
+    """AdaIN auto-encoder (reference networks.py:112-171)"""
+
+    def __init__(self, input_dim, params):
+        super().__init__()
+        dim, style_dim = params["dim"], params["style_dim"]
+        n_down, n_res = params["n_downsample"], params["n_res"]
+        activ, pad_type = params["activ"], params["pad_type"]
+        self.enc_style = StyleEncoder(4, input_dim, dim, style_dim, norm="none", activ=activ, pad_type=pad_type)
+        self.enc_content = ContentEncoder(n_down, n_res, input_dim, dim, "in", activ, pad_type=pad_type)
+        self.dec = Decoder(n_down, n_res, self.enc_content.output_dim, params["output_dim"], res_norm="adain",
+                           activ=activ, pad_type=pad_type)
+        self.mlp = MLP(style_dim, self.get_num_adain_params(self.dec), params["mlp_dim"], 3, norm="none", activ=activ)
+        self.activ = activ
+
+    # ---- reference-compatible helpers ---------------------------------------------------------------
+    def get_num_adain_params(self, model):
+        return sum(2 * m.num_features for m in model.modules() if isinstance(m, AdaptiveInstanceNorm2d))
+
+    def assign_adain_params(self, adain_params, model):
+        """networks.py:154-163: per AdaIN module (modules() order) first C columns -> bias, next C -> weight"""
+        for m in model.modules():
+            if isinstance(m, AdaptiveInstanceNorm2d):
+                c = m.num_features
+                m.bias = adain_params[:, :c].contiguous().view(-1)
+                m.weight = adain_params[:, c:2 * c].contiguous().view(-1)
+                if adain_params.size(1) > 2 * c:
+                    adain_params = adain_params[:, 2 * c:]
+
+    # ---- engine binding -----------------------------------------------------------------------------
+    def _build_layers(self):
+        eng, ar = self._eng, self._arena
+        # registration order == optimizer order is irrelevant for the arena; windows mark the small-C layers
+        for i, blk in enumerate(self.enc_style.model):
+            if isinstance(blk, Conv2dBlock):
+                blk.layer(eng, ar, N.WINDOW_IN if i == 0 else N.WINDOW_NONE)
+        for i, blk in enumerate(self.enc_content.model):
+            if isinstance(blk, Conv2dBlock):
+                blk.layer(eng, ar, N.WINDOW_IN if i == 0 else N.WINDOW_NONE)
+        for rb in self.enc_content.model[-1].model:
+            for blk in rb.model:
+                blk.layer(eng, ar)
+        dec = list(self.dec.model)
+        for rb in dec[0].model:
+            for blk in rb.model:
+                blk.layer(eng, ar)
+        for blk in dec[1:-1]:
+            if isinstance(blk, Conv2dBlock):
+                blk.layer(eng, ar)
+                self._reserve_dense(blk.norm.gamma)
+                self._reserve_dense(blk.norm.beta)
+        dec[-1].layer(eng, ar, N.WINDOW_OUT if dec[-1].spec["cout"] <= 8 else N.WINDOW_NONE)
+        head = self.enc_style.model[-1]
+        for p in (head.weight, head.bias):
+            self._reserve_dense(p)
+        for lb in self.mlp.model:
+            self._reserve_dense(lb.fc.weight)
+            self._reserve_dense(lb.fc.bias)
+
+    # ---- engine API ---------------------------------------------------------------------------------
+    def enc_content_fwd(self, tape, img):
+        """ContentEncoder (networks.py:230-245) on an ImgT -> content plane (pad 1: it feeds 3x3 convs)"""
+        self._ensure_bound()
+        eng, tw = self._eng, self.train_weights and tape.enabled
+        act = _ACT[self.activ]
+        m = list(self.enc_content.model)
+        x = eng.pack_image(tape, img, 3, 8)
+        convs = m[:-1]
+        for i, blk in enumerate(convs):
+            nxt_pad = convs[i + 1].spec["pad"] if i + 1 < len(convs) else 1
+            x = eng.conv_block(tape, blk._layer, x, norm=N.NORM_IN, act=act, out_pad=nxt_pad, train_w=tw)
+        for rb in m[-1].model:
+            h = eng.conv_block(tape, rb.model[0]._layer, x, norm=N.NORM_IN, act=act, out_pad=1, train_w=tw)
+            x = eng.conv_block(tape, rb.model[1]._layer, h, norm=N.NORM_IN, act=N.ACT_NONE, out_pad=1, res=x,
+                               train_w=tw)
+        return x
+
+    def enc_style_fwd(self, tape, img):
+        """StyleEncoder (networks.py:212-228) -> E.ImgT holding the [N, style_dim] code"""
+        self._ensure_bound()
+        eng, tw = self._eng, self.train_weights and tape.enabled
+        act = _ACT[self.activ]
+        m = list(self.enc_style.model)
+        convs = [b for b in m if isinstance(b, Conv2dBlock)]
+        x = eng.pack_image(tape, img, 3, 8)
+        for i, blk in enumerate(convs):
+            nxt_pad = convs[i + 1].spec["pad"] if i + 1 < len(convs) else 0
+            x = eng.conv_block(tape, blk._layer, x, norm=N.NORM_NONE, act=act, out_pad=nxt_pad, train_w=tw)
+        head = m[-1]
+        c = x.c_valid
+        xf = x.buf[:, :x.numel].float().sum(0).view(x.n, x.h * x.w, x.c)[:, :, :c]
+        pooled = xf.mean(1)                                              # AdaptiveAvgPool2d(1)
+        w2 = head.weight.detach().view(head.weight.shape[0], c)
+        style = E.ImgT(torch.addmm(head.bias.detach(), pooled, w2.t()), requires_grad=tape.enabled)
+        if tape.enabled:
+            def bwd():
+                if style.grad is None:
+                    return
+                ds = style.grad
+                style.grad = None
+                if tw:
+                    self._grad_of(head.weight).view(-1, c).add_(ds.t() @ pooled)
+                    self._grad_of(head.bias).add_(ds.sum(0))
+                dp = (ds @ w2) / float(x.h * x.w)                        # [n, c]
+                g = torch.zeros((x.n, x.h, x.w, x.c), dtype=eng.prec.dtype, device=eng.device)
+                g[..., :c] = dp.view(x.n, 1, 1, c).to(eng.prec.dtype)
+                x.add_gr(g)
+            tape.push(bwd)
+        return style
+
+    def mlp_fwd(self, tape, style):
+        """MLP (networks.py:280-292) on an E.ImgT [N, style_dim] -> E.ImgT [N, n_adain]"""
+        self._ensure_bound()
+        tw = self.train_weights and tape.enabled
+        fcs = [lb.fc for lb in self.mlp.model]
+        hs = [style.t.reshape(style.t.shape[0], -1)]
+        for i, fc in enumerate(fcs):
+            z = torch.addmm(fc.bias.detach(), hs[-1], fc.weight.detach().t())
+            hs.append(torch.relu(z) if i + 1 < len(fcs) else z)
+        out = E.ImgT(hs[-1], requires_grad=tape.enabled)
+        if tape.enabled:
+            def bwd():
+                if out.grad is None:
+                    return
+                g = out.grad
+                out.grad = None
+                for i in reversed(range(len(fcs))):
+                    if i + 1 < len(fcs):
+                        g = g * (hs[i + 1] > 0).to(g.dtype)
+                    if tw:
+                        self._grad_of(fcs[i].weight).add_(g.t() @ hs[i])
+                        self._grad_of(fcs[i].bias).add_(g.sum(0))
+                    g = g @ fcs[i].weight.detach()
+                if style.requires_grad:
+                    style.add_grad(g.view_as(style.t))
+            tape.push(bwd)
+        return out
+
+    def dec_fwd(self, tape, content, style):
+        """AdaINGen.decode + Decoder.forward (networks.py:147-152, 247-264) -> E.ImgT image"""
+        self._ensure_bound()
+        eng, tw = self._eng, self.train_weights and tape.enabled
+        act = _ACT[self.activ]
+        ap = self.mlp_fwd(tape, style)
+        m = list(self.dec.model)
+        c = content.c_valid
+        n = content.n
+        d_ap = None
+        if tape.enabled:
+            d_ap = torch.zeros_like(ap.t)
+
+            def bwd_ap():
+                ap.add_grad(d_ap)
+            tape.push(bwd_ap)
+        x = content
+        i_adain = 0
+        for rb in m[0].model:
+            for j, blk in enumerate(rb.model):
+                blkp = ap.t[:, i_adain * 2 * c:(i_adain + 1) * 2 * c]
+                bias = blkp[:, :c].contiguous()
+                weight = blkp[:, c:2 * c].contiguous()
+                if d_ap is not None:
+                    def sink(dw, db, k=i_adain):
+                        d_ap[:, k * 2 * c:k * 2 * c + c] = db
+                        d_ap[:, k * 2 * c + c:(k + 1) * 2 * c] = dw
+                else:
+                    sink = None
+                i_adain += 1
+                last_rb = rb is m[0].model[-1] and j == 1
+                if j == 0:
+                    h = eng.conv_block(tape, blk._layer, x, norm=N.NORM_ADAIN, act=act, out_pad=1,
+                                       adain=(weight, bias, sink), train_w=tw)
+                else:
+                    up = 2 if (last_rb and len(m) > 2) else 1
+                    nxt = m[2].spec["pad"] if (last_rb and len(m) > 2) else (m[-1].spec["pad"] if last_rb else 1)
+                    x = eng.conv_block(tape, blk._layer, h, norm=N.NORM_ADAIN, act=N.ACT_NONE, out_pad=nxt,
+                                       upsample=up, res=x, adain=(weight, bias, sink), train_w=tw)
+        ups = [b for b in m[1:-1] if isinstance(b, Conv2dBlock)]
+        for i, blk in enumerate(ups):
+            last = i + 1 == len(ups)
+            nxt = m[-1].spec["pad"] if last else ups[i + 1].spec["pad"]
+            ln = (blk.norm.gamma.detach(), blk.norm.beta.detach(),
+                  self._grad_of(blk.norm.gamma), self._grad_of(blk.norm.beta))
+            x = eng.conv_block(tape, blk._layer, x, norm=N.NORM_LN, act=act, out_pad=nxt,
+                               upsample=1 if last else 2, ln=ln, train_w=tw)
+        return eng.conv_to_image(tape, m[-1]._layer, x, act=N.ACT_TANH, train_w=tw)
+
+    # ---- reference-compatible tensor API (forward values only) ---------------------------------------
+    def _content_from_tensor(self, content):
+        eng = self._eng
+        n, c, h, w = content.shape
+        a = E.ActT(eng, n, h, w, c, 1)
+        v = F.pad(content.float(), (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1)
+        full = torch.zeros((n, h + 2, w + 2, a.c), dtype=torch.float32, device=eng.device)
+        full[..., :c] = v
+        hi = full.bfloat16()
+        a.buf[0, :a.numel] = hi.reshape(-1)
+        if a.planes == 2:
+            a.buf[1, :a.numel] = (full - hi.float()).bfloat16().reshape(-1)
+        return a
+
+    def encode(self, images):
+        self._ensure_bound()
+        tape = E.Tape(enabled=False)
+        img = E.ImgT(images.detach().float())
+        style = self.enc_style_fwd(tape, img)
+        content = self.enc_content_fwd(tape, img)
+        return content.value_nchw(), style.t.view(style.t.shape[0], -1, 1, 1)
+
+    def decode(self, content, style):
+        self._ensure_bound()
+        tape = E.Tape(enabled=False)
+        ap_style = E.ImgT(style.detach().float().reshape(style.shape[0], -1))
+        return self.dec_fwd(tape, self._content_from_tensor(content.detach()), ap_style).t
+
+    def forward(self, images):
+        content, style = self.encode(images)
+        return self.decode(content, style)
+
+
+class VAEGen(nn.Module):
+    """dead code in the reference (imported by trainer.py:4, never instantiated - SURVEY 2.1)"""
+
+    def __init__(self, input_dim, params):
+        super().__init__()
+        raise NotImplementedError("VAEGen is not part of the ACL-GAN hot path")
+
+
+class Vgg16(nn.Module):
+    """option surface only: vgg_w is 0 in every shipped config (trainer.py:55)"""
+
+    def __init__(self):
+        super().__init__()
+        raise NotImplementedError("the VGG perceptual loss is outside the B200 hot path")
+
+
+# ======================================================================================================
+# Discriminator
+# ======================================================================================================
+class MsImageDis(_EngineNet):
+    """multi-scale PatchGAN (reference networks.py:21-106)"""
+
+    def __init__(self, input_dim, params):
+        super().__init__()
+        self.n_layer, self.gan_type, self.dim = params["n_layer"], params["gan_type"], params["dim"]
+        self.norm, self.activ = params["norm"], params["activ"]
+        self.num_scales, self.pad_type = params["num_scales"], params["pad_type"]
+        self.input_dim = input_dim
+        self.downsample = nn.AvgPool2d(3, stride=2, padding=[1, 1], count_include_pad=False)
+        self.cnns = nn.ModuleList([self._make_net() for _ in range(self.num_scales)])
+        if self.norm != "none":
+            raise NotImplementedError("discriminator norm %r is outside the B200 hot path" % self.norm)
+
+    def _make_net(self):
+        dim = self.dim
+        layers = [Conv2dBlock(self.input_dim, dim, 4, 2, 1, norm="none", activation=self.activ, pad_type=self.pad_type)]
+        for _ in range(self.n_layer - 1):
+            layers.append(Conv2dBlock(dim, dim * 2, 4, 2, 1, norm=self.norm, activation=self.activ,
+                                      pad_type=self.pad_type))
+            dim *= 2
+        layers.append(nn.Conv2d(dim, 1, 1, 1, 0))
+        return nn.Sequential(*layers)
+
+    def _build_layers(self):
+        for net in self.cnns:
+            for i, blk in enumerate(net):
+                if isinstance(blk, Conv2dBlock):
+                    blk.layer(self._eng, self._arena, N.WINDOW_IN if i == 0 else N.WINDOW_NONE)
+                else:
+                    self._reserve_dense(blk.weight)
+                    self._reserve_dense(blk.bias)
+
+    # ---- engine API ---------------------------------------------------------------------------------
+    def dis(self, tape, img0, img1=None):
+        """forward over all scales; img1 = second image of a channel-concatenated pair (dis_2).
+        returns a list of E.ImgT logits [N,1,h,w]"""
+        self._ensure_bound()
+        eng, tw = self._eng, self.train_weights and tape.enabled
+        act = _ACT[self.activ]
+        outs = []
+        imgs = [img0, img1]
+        for s, net in enumerate(self.cnns):
+            x = eng.pack_image(tape, imgs[0], 1, 16, imgs[1])
+            blocks = [b for b in net if isinstance(b, Conv2dBlock)]
+            for i, blk in enumerate(blocks):
+                x = eng.conv_block(tape, blk._layer, x, norm=N.NORM_NONE, act=act,
+                                   out_pad=1 if i + 1 < len(blocks) else 0, train_w=tw)
+            outs.append(self._head(tape, net[-1], x, tw))
+            if s + 1 < len(self.cnns):
+                imgs = [self._pool(tape, im) if im is not None else None for im in imgs]
+        return outs
+
+    def _pool(self, tape, img):
+        """AvgPool2d(3, 2, padding 1, count_include_pad=False) on the NCHW image (networks.py:33,53)"""
+        t = F.avg_pool2d(img.t, 3, stride=2, padding=1, count_include_pad=False)
+        out = E.ImgT(t, requires_grad=img.requires_grad)
+        if tape.enabled and img.requires_grad:
+            def bwd():
+                if out.grad is None:
+                    return
+                g = torch.ops.aten.avg_pool2d_backward(out.grad, img.t, [3, 3], [2, 2], [1, 1], False, False, None)
+                out.grad = None
+                img.add_grad(g)
+            tape.push(bwd)
+        return out
+
+    def _head(self, tape, conv, x, tw):
+        """1x1 conv dim*8 -> 1 (networks.py:45): per-pixel dot product on the un-padded plane"""
+        eng = self._eng
+        c = x.c_valid
+        xf = x.buf[:, :x.numel].float().sum(0).view(x.n, x.h, x.w, x.c)[..., :c]
+        wv = conv.weight.detach().view(c)
+        logit = E.ImgT((xf @ wv + conv.bias.detach()).view(x.n, 1, x.h, x.w), requires_grad=tape.enabled)
+        if tape.enabled:
+            def bwd():
+                if logit.grad is None:
+                    return
+                d = logit.grad.view(x.n, x.h, x.w)
+                logit.grad = None
+                if tw:
+                    self._grad_of(conv.weight).view(c).add_(torch.einsum("nhw,nhwc->c", d, xf))
+                    self._grad_of(conv.bias).add_(d.sum().view(1))
+                if x.requires_grad:
+                    g = torch.zeros((x.n, x.h, x.w, x.c), dtype=eng.prec.dtype, device=eng.device)
+                    g[..., :c] = (d.unsqueeze(-1) * wv).to(eng.prec.dtype)
+                    x.add_gr(g)
+            tape.push(bwd)
+        return logit
+
+    # ---- reference-compatible tensor API (forward values only) ---------------------------------------
+    def forward(self, x):
+        tape = E.Tape(enabled=False)
+        return [o.t for o in self.dis(tape, E.ImgT(x.detach().float()))]
+
+    @staticmethod
+    def _lsgan(outs, target):
+        return sum(torch.mean((o - target) ** 2) for o in outs)
+
+    def _check_gan(self):
+        if self.gan_type == "nsgan":
+            raise NotImplementedError("gan_type 'nsgan' is outside the B200 hot path")
+        if self.gan_type != "lsgan":
+            assert 0, "Unsupported GAN type: {}".format(self.gan_type)
+
+    def calc_dis_loss(self, input_fake, input_real):
+        self._check_gan()
+        return self._lsgan(self.forward(input_fake), 0.0) + self._lsgan(self.forward(input_real), 1.0)
+
+    def calc_gen_loss(self, input_fake):
+        self._check_gan()
+        return self._lsgan(self.forward(input_fake), 1.0)
+
+    def calc_gen_d2_loss(self, input_fake, input_real):
+        self._check_gan()
+        return self._lsgan(self.forward(input_fake), 1.0) + self._lsgan(self.forward(input_real), 0.0)

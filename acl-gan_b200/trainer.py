@@ -1,0 +1,353 @@
+"""Drop-in `trainer` module: `aclgan_Trainer` with the reference's surface (trainer.py:14-332 of the reference:
+same child modules / attribute names / loss_* attributes / checkpoint files), running the adversarial-
+consistency cycle on the CUDA engine with a hand-scheduled backward pass instead of autograd.
+
+Differences that do not change any result (SURVEY.md 8a "work the reference performs that does not affect
+any result"): dis_update runs the generators without recording a backward pass (the reference back-propagates
+into them and zeroes those grads at trainer.py:91), gen_update computes no discriminator weight gradients
+(zeroed at :248), style encoders whose output is unused are skipped, dis_A(x_a) is evaluated once with
+weight 1 instead of twice with weight 1/2.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+import aclgan_native as N
+import engine as E
+from networks import AdaINGen, MsImageDis, get_engine
+from utils import get_model_list, get_scheduler, weights_init
+
+
+class aclgan_Trainer(nn.Module):
+    def __init__(self, hyperparameters):
+        super().__init__()
+        hp = hyperparameters
+        lr = hp["lr"]
+        # construction order == reference (trainer.py:19-25): it fixes the RNG stream and the state_dict
+        self.gen_AB = AdaINGen(hp["input_dim_a"], hp["gen"])
+        self.gen_BA = AdaINGen(hp["input_dim_a"], hp["gen"])
+        self.dis_A = MsImageDis(hp["input_dim_a"], hp["dis"])
+        self.dis_B = MsImageDis(hp["input_dim_a"], hp["dis"])
+        self.dis_2 = MsImageDis(hp["input_dim_b"], hp["dis"])
+        self.instancenorm = nn.InstanceNorm2d(512, affine=False)
+        self.style_dim = hp["gen"]["style_dim"]
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        display_size = int(hp["display_size"])
+        self.z_1 = torch.randn(display_size, self.style_dim, 1, 1).to(dev)
+        self.z_2 = torch.randn(display_size, self.style_dim, 1, 1).to(dev)
+        self.z_3 = torch.randn(display_size, self.style_dim, 1, 1).to(dev)
+
+        beta1, beta2 = hp["beta1"], hp["beta2"]
+        dis_params = list(self.dis_A.parameters()) + list(self.dis_B.parameters()) + list(self.dis_2.parameters())
+        gen_params = list(self.gen_AB.parameters()) + list(self.gen_BA.parameters())
+        self.dis_opt = torch.optim.Adam([p for p in dis_params if p.requires_grad], lr=lr, betas=(beta1, beta2),
+                                        weight_decay=hp["weight_decay"])
+        self.gen_opt = torch.optim.Adam([p for p in gen_params if p.requires_grad], lr=lr, betas=(beta1, beta2),
+                                        weight_decay=hp["weight_decay"])
+        self.dis_scheduler = get_scheduler(self.dis_opt, hp)
+        self.gen_scheduler = get_scheduler(self.gen_opt, hp)
+        self.alpha = hp["alpha"]
+        self.focus_lam = hp["focus_loss"]
+
+        self.apply(weights_init(hp["init"]))
+        self.dis_A.apply(weights_init("gaussian"))
+        self.dis_B.apply(weights_init("gaussian"))
+        self.dis_2.apply(weights_init("gaussian"))
+
+        if hp.get("vgg_w", 0) > 0:
+            raise NotImplementedError("vgg_w > 0: the VGG perceptual loss is outside the B200 hot path")
+        self.precision = hp.get("precision", os.environ.get("ACLGAN_PRECISION", "bf16"))
+        self._ready = False
+        self._noise = None          # optional injected style noise (tests / graph replay): list of 3 tensors
+
+    # ------------------------------------------------------------------------------------------ engine
+    def _setup(self):
+        if self._ready:
+            return
+        eng = get_engine(self.precision)
+        self.eng = eng
+        self.gen_arena = E.GradArena(eng.device)
+        self.dis_arena = E.GradArena(eng.device)
+        for net in (self.gen_AB, self.gen_BA):
+            net.bind(eng, self.gen_arena)
+        for net in (self.dis_A, self.dis_B, self.dis_2):
+            net.bind(eng, self.dis_arena)
+        for net in self._nets():
+            net._ensure_bound()
+        self.gen_arena.finalize()
+        self.dis_arena.finalize()
+        for net in self._nets():
+            net.attach_grads()
+        self._ready = True
+
+    def _nets(self):
+        return (self.gen_AB, self.gen_BA, self.dis_A, self.dis_B, self.dis_2)
+
+    def _draw_noise(self, n):
+        """three CPU randn draws moved to the device, exactly as trainer.py:99-101 / 254-256"""
+        if self._noise is not None:
+            zs, self._noise = self._noise, None
+            return [E.ImgT(z.to(self.eng.device).float().reshape(n, self.style_dim)) for z in zs]
+        return [E.ImgT(torch.randn(n, self.style_dim, 1, 1).to(self.eng.device).reshape(n, self.style_dim))
+                for _ in range(3)]
+
+    def _allreduce(self, arena):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(arena.flat)
+            arena.flat.div_(dist.get_world_size())
+
+    # ------------------------------------------------------------------------------------------ pieces
+    def recon_criterion(self, input, target):
+        return torch.mean(torch.abs(input - target))
+
+    def focus_translation(self, x_fg, x_bg, x_focus):
+        x_map = ((x_focus + 1) / 2).repeat(1, 3, 1, 1)
+        return x_fg * x_map + x_bg * (1 - x_map)
+
+    def _blend(self, tape, out, bg):
+        """decoder output [N,4,H,W] -> focus-blended RGB (trainer.py:85-88,108-111); returns (image, raw mask)"""
+        fg, f = out.t[:, :3], out.t[:, 3:4]
+        m = (f + 1) / 2
+        res = E.ImgT(fg * m + bg.t * (1 - m), requires_grad=out.requires_grad or bg.requires_grad)
+        if tape.enabled and res.requires_grad:
+            def bwd():
+                if res.grad is None:
+                    return
+                d = res.grad
+                res.grad = None
+                if out.requires_grad:
+                    do = torch.cat((d * m, (d * (fg - bg.t)).sum(1, keepdim=True) * 0.5), 1)
+                    out.add_grad(do)
+                if bg.requires_grad:
+                    bg.add_grad(d * (1 - m))
+            tape.push(bwd)
+        return res
+
+    def _rgb(self, tape, out):
+        """first three channels of a decoder output as an image node (the .split(3, 1)[0] of trainer.py:113-114)"""
+        if out.t.shape[1] == 3:
+            return out
+        res = E.ImgT(out.t[:, :3], requires_grad=out.requires_grad)
+        if tape.enabled and res.requires_grad:
+            def bwd():
+                if res.grad is None:
+                    return
+                do = torch.zeros_like(out.t)
+                do[:, :3] = res.grad
+                res.grad = None
+                out.add_grad(do)
+            tape.push(bwd)
+        return res
+
+    @staticmethod
+    def _lsgan(outs, target, weight):
+        """sum over scales of mean((o - t)^2) (networks.py:67,83,98); seeds d loss / d logits scaled by `weight`"""
+        total = 0
+        for o in outs:
+            diff = o.t - target
+            total = total + torch.mean(diff * diff)
+            if o.requires_grad and weight != 0:
+                o.add_grad(diff * (2.0 * weight / diff.numel()))
+        return total
+
+    def _cycle(self, tape, x_a, x_b, zs, need_recon):
+        """encode / decode cycle shared by both updates (trainer.py:103-133 and 258-280)"""
+        focus = self.focus_lam > 0
+        AB, BA = self.gen_AB, self.gen_BA
+        z_1, z_2, z_3 = zs
+        r = {}
+        c_1 = AB.enc_content_fwd(tape, x_a)
+        c_2 = BA.enc_content_fwd(tape, x_a)
+        o_b = AB.dec_fwd(tape, c_1, z_1)
+        o_a = BA.dec_fwd(tape, c_2, E.ImgT(self.alpha * z_2.t))
+        if need_recon:
+            s_2 = BA.enc_style_fwd(tape, x_a)
+            c_4 = AB.enc_content_fwd(tape, x_b)
+            s_4 = AB.enc_style_fwd(tape, x_b)
+            r["o_rec_a"] = BA.dec_fwd(tape, c_2, s_2)
+            r["o_rec_b"] = AB.dec_fwd(tape, c_4, s_4)
+        if focus:
+            x_B_fake = self._blend(tape, o_b, x_a)
+            x_A_fake = self._blend(tape, o_a, x_a)
+        else:
+            x_B_fake, x_A_fake = o_b, o_a
+        c_3 = BA.enc_content_fwd(tape, x_B_fake)
+        o_a2 = BA.dec_fwd(tape, c_3, z_3)
+        x_A2_fake = self._blend(tape, o_a2, x_B_fake) if focus else o_a2
+        r.update(o_b=o_b, o_a=o_a, o_a2=o_a2, x_B_fake=x_B_fake, x_A_fake=x_A_fake, x_A2_fake=x_A2_fake)
+        self._last_cycle = r        # handles only (tests / image dumps read them); freed by the next update
+        return r
+
+    # ------------------------------------------------------------------------------------------ updates
+    def gen_update(self, x_a, x_b, hyperparameters):
+        self._setup()
+        hp = hyperparameters
+        self.gen_arena.zero_()
+        for d in (self.dis_A, self.dis_B, self.dis_2):
+            d.train_weights = False                       # their weight grads are discarded (trainer.py:248)
+        tape = E.Tape()
+        n = x_a.size(0)
+        xa, xb = E.ImgT(x_a.detach().float()), E.ImgT(x_b.detach().float())
+        zs = self._draw_noise(n)
+        focus = hp["focus_loss"] > 0
+        r = self._cycle(tape, xa, xb, zs, need_recon=True)
+
+        gw, gcw = hp["gan_w"], hp["gan_cw"]
+        self.loss_gen_adv_A = (self._lsgan(self.dis_A.dis(tape, r["x_A_fake"]), 1.0, 0.5 * gw) +
+                               self._lsgan(self.dis_A.dis(tape, r["x_A2_fake"]), 1.0, 0.5 * gw)) * 0.5
+        self.loss_gen_adv_B = self._lsgan(self.dis_B.dis(tape, r["x_B_fake"]), 1.0, gw)
+        self.loss_gen_adv_2 = (self._lsgan(self.dis_2.dis(tape, xa, r["x_A_fake"]), 1.0, gcw) +
+                               self._lsgan(self.dis_2.dis(tape, xa, r["x_A2_fake"]), 0.0, gcw))
+        total = gw * self.loss_gen_adv_A + gw * self.loss_gen_adv_B + gcw * self.loss_gen_adv_2
+
+        if focus:
+            # trainer.py:146-161 (sums over the WHOLE batch; normalised by H*W*B*3)
+            delta, up, lo, eps = hp["focus_delta"], hp["focus_upper"], hp["focus_lower"], hp["focus_epsilon"]
+            norm = float(x_a.size(2) * x_a.size(3) * x_a.size(0) * 3)
+            acc = 0
+            for tag, out in (("B", r["o_b"]), ("A", r["o_a"]), ("A2", r["o_a2"])):
+                m = (out.t[:, 3:4] + 1) / 2
+                s1 = torch.relu(torch.sum(m - up))
+                s2 = torch.relu(torch.sum(lo - m))
+                size = s1 ** 2 * delta + s2 ** 2 * delta
+                dev = m - 0.5
+                den = torch.abs(dev) + eps
+                digit = torch.sum(1 / den)
+                setattr(self, "loss_gen_focus_%s_size" % tag, size)
+                setattr(self, "loss_gen_focus_%s_digit" % tag, digit)
+                acc = acc + size + digit
+                dm = (2 * delta) * (s1 - s2) - torch.sign(dev) / (den * den)       # d(size + digit) / dm
+                do = torch.zeros_like(out.t)
+                do[:, 3:4] = dm * (0.5 * hp["focus_loss"] / norm)
+                out.add_grad(do)
+            total = total + hp["focus_loss"] * acc / x_a.size(2) / x_a.size(3) / x_a.size(0) / 3
+
+        rec_a, rec_b = self._rgb(tape, r["o_rec_a"]), self._rgb(tape, r["o_rec_b"])
+        da, db = rec_a.t - xa.t, rec_b.t - xb.t
+        self.loss_idt_A = torch.mean(torch.abs(da))
+        self.loss_idt_B = torch.mean(torch.abs(db))
+        rw = hp["recon_x_w"]
+        rec_a.add_grad(torch.sign(da) * (rw / da.numel()))
+        rec_b.add_grad(torch.sign(db) * (rw / db.numel()))
+        self.loss_gen_total = total + rw * self.loss_idt_A + rw * self.loss_idt_B
+
+        tape.backward()
+        for d in (self.dis_A, self.dis_B, self.dis_2):
+            d.train_weights = True
+        self._allreduce(self.gen_arena)
+        self.gen_opt.step()
+        self.gen_AB.mark_dirty()
+        self.gen_BA.mark_dirty()
+
+    def dis_update(self, x_a, x_b, hyperparameters):
+        self._setup()
+        hp = hyperparameters
+        self.dis_arena.zero_()
+        n = x_a.size(0)
+        xa, xb = E.ImgT(x_a.detach().float()), E.ImgT(x_b.detach().float())
+        zs = self._draw_noise(n)
+        # the generators only produce the fakes here: no backward pass is recorded for them (trainer.py:91)
+        r = self._cycle(E.Tape(enabled=False), xa, xb, zs, need_recon=False)
+        fake_a, fake_a2, fake_b = (E.ImgT(r[k].t) for k in ("x_A_fake", "x_A2_fake", "x_B_fake"))
+
+        tape = E.Tape()
+        gw, gcw = hp["gan_w"], hp["gan_cw"]
+        real_a = self._lsgan(self.dis_A.dis(tape, xa), 1.0, gw)           # counted twice with weight 1/2 in the reference
+        self.loss_dis_A = (self._lsgan(self.dis_A.dis(tape, fake_a), 0.0, 0.5 * gw) +
+                           self._lsgan(self.dis_A.dis(tape, fake_a2), 0.0, 0.5 * gw) + 2.0 * real_a) * 0.5
+        self.loss_dis_B = (self._lsgan(self.dis_B.dis(tape, fake_b), 0.0, gw) +
+                           self._lsgan(self.dis_B.dis(tape, xb), 1.0, gw))
+        self.loss_dis_2 = (self._lsgan(self.dis_2.dis(tape, xa, fake_a), 0.0, gcw) +
+                           self._lsgan(self.dis_2.dis(tape, xa, fake_a2), 1.0, gcw))
+        self.loss_dis_total = gw * self.loss_dis_A + gw * self.loss_dis_B + gcw * self.loss_dis_2
+        tape.backward()
+        self._allreduce(self.dis_arena)
+        self.dis_opt.step()
+        for d in (self.dis_A, self.dis_B, self.dis_2):
+            d.mark_dirty()
+
+    # ------------------------------------------------------------------------------------------ inference
+    def forward(self, x_a, x_b):
+        raise NotImplementedError("aclgan_Trainer.forward is dead code in the reference (crashes with the shipped "
+                                  "4-channel decoder, SURVEY 2.1); use sample() / gen_*.encode / decode")
+
+    def sample(self, x_a, x_b):
+        """trainer.py:179-245: per-image translations with the fixed display noise"""
+        self._setup()
+        self.eval()
+        focus = self.focus_lam > 0
+        cols = {k: [] for k in ("x_A", "x_B", "x_A_fake", "x_B_fake", "x_A2_fake", "x_A_recon", "x_B_recon",
+                                "mask_A", "mask_B", "mask_A2", "mask_recon")}
+        with torch.no_grad():
+            for i in range(x_a.size(0)):
+                a, b = x_a[i].unsqueeze(0), x_b[i].unsqueeze(0)
+                cols["x_A"].append(a)
+                cols["x_B"].append(b)
+                c_1, s_1 = self.gen_BA.encode(a)
+                o = self.gen_BA.decode(c_1, self.z_1[i].unsqueeze(0))
+                rec = self.gen_BA.decode(c_1, s_1)
+                c_2, _ = self.gen_AB.encode(a)
+                ob = self.gen_AB.decode(c_2, self.z_2[i].unsqueeze(0))
+                if focus:
+                    cols["x_A_fake"].append(self.focus_translation(o[:, :3], a, o[:, 3:4]))
+                    cols["mask_A"].append(o[:, 3:4])
+                    cols["x_A_recon"].append(rec[:, :3])
+                    cols["mask_recon"].append(rec[:, 3:4])
+                    xb_img = self.focus_translation(ob[:, :3], a, ob[:, 3:4])
+                    cols["mask_B"].append(ob[:, 3:4])
+                else:
+                    cols["x_A_fake"].append(o)
+                    cols["x_A_recon"].append(rec)
+                    xb_img = ob
+                cols["x_B_fake"].append(xb_img)
+                c_3, _ = self.gen_BA.encode(xb_img)
+                o2 = self.gen_BA.decode(c_3, self.z_3[i].unsqueeze(0))
+                if focus:
+                    cols["x_A2_fake"].append(self.focus_translation(o2[:, :3], xb_img, o2[:, 3:4]))
+                    cols["mask_A2"].append(o2[:, 3:4])
+                else:
+                    cols["x_A2_fake"].append(o2)
+                    c_4, s_4 = self.gen_AB.encode(b)
+                    cols["x_B_recon"].append(self.gen_AB.decode(c_4, s_4))
+        cat = {k: torch.cat(v) for k, v in cols.items() if v}
+        self.train()
+        if focus:
+            return (cat["x_A"], cat["x_A_fake"], cat["mask_A"], cat["x_B_fake"], cat["mask_B"], cat["x_A2_fake"],
+                    cat["mask_A2"], cat["x_A_recon"], cat["mask_recon"])
+        return (cat["x_A"], cat["x_A_fake"], cat["x_B_fake"], cat["x_A2_fake"], cat["x_A_recon"], cat["x_B"],
+                cat["x_B_recon"])
+
+    # ------------------------------------------------------------------------------------------ schedule / io
+    def update_learning_rate(self):
+        if self.dis_scheduler is not None:
+            self.dis_scheduler.step()
+        if self.gen_scheduler is not None:
+            self.gen_scheduler.step()
+
+    def resume(self, checkpoint_dir, hyperparameters):
+        last = get_model_list(checkpoint_dir, "gen")
+        sd = torch.load(last)
+        self.gen_AB.load_state_dict(sd["AB"])
+        self.gen_BA.load_state_dict(sd["BA"])
+        iterations = int(last[-11:-3])
+        sd = torch.load(get_model_list(checkpoint_dir, "dis"))
+        self.dis_A.load_state_dict(sd["A"])
+        self.dis_B.load_state_dict(sd["B"])
+        self.dis_2.load_state_dict(sd["2"])
+        sd = torch.load(os.path.join(checkpoint_dir, "optimizer.pt"))
+        self.dis_opt.load_state_dict(sd["dis"])
+        self.gen_opt.load_state_dict(sd["gen"])
+        self.dis_scheduler = get_scheduler(self.dis_opt, hyperparameters, iterations)
+        self.gen_scheduler = get_scheduler(self.gen_opt, hyperparameters, iterations)
+        print("Resume from iteration %d" % iterations)
+        return iterations
+
+    def save(self, snapshot_dir, iterations):
+        gen_name = os.path.join(snapshot_dir, "gen_%08d.pt" % (iterations + 1))
+        dis_name = os.path.join(snapshot_dir, "dis_%08d.pt" % (iterations + 1))
+        opt_name = os.path.join(snapshot_dir, "optimizer.pt")
+        torch.save({"AB": self.gen_AB.state_dict(), "BA": self.gen_BA.state_dict()}, gen_name)
+        torch.save({"A": self.dis_A.state_dict(), "B": self.dis_B.state_dict(), "2": self.dis_2.state_dict()}, dis_name)
+        torch.save({"gen": self.gen_opt.state_dict(), "dis": self.dis_opt.state_dict()}, opt_name)

@@ -1,0 +1,195 @@
+"""Drop-in `utils` module (host-side helpers the reference's train.py / test.py import).
+
+Same function names and call signatures as the reference's utils.py; the bodies are written
+for this repo: `get_config` uses the safe YAML loader (the reference's bare `yaml.load` fails on PyYAML >= 6,
+utils.py:105), image / HTML writers and the data-loader factory keep the reference's file naming so the output
+folders look the same.  None of this is on the GPU hot path.
+"""
+import math
+import os
+import time
+
+import torch
+import torch.nn.init as init
+import yaml
+from torch.optim import lr_scheduler
+
+
+# ------------------------------------------------------------------------------------------ config
+def get_config(config):
+    with open(config, "r") as stream:
+        return yaml.safe_load(stream)
+
+
+# ------------------------------------------------------------------------------------------ init / schedule
+def weights_init(init_type="gaussian"):
+    """utils.py:274-294: re-draws every Conv*/Linear* weight, zeroes biases; draws in module order"""
+    draw = {
+        "gaussian": lambda w: init.normal_(w, 0.0, 0.02),
+        "xavier": lambda w: init.xavier_normal_(w, gain=math.sqrt(2)),
+        "kaiming": lambda w: init.kaiming_normal_(w, a=0, mode="fan_in"),
+        "orthogonal": lambda w: init.orthogonal_(w, gain=math.sqrt(2)),
+        "default": lambda w: w,
+    }
+    assert init_type in draw, "Unsupported initialization: {}".format(init_type)
+
+    def init_fun(m):
+        name = m.__class__.__name__
+        if (name.startswith("Conv") or name.startswith("Linear")) and hasattr(m, "weight"):
+            draw[init_type](m.weight.data)
+            if getattr(m, "bias", None) is not None:
+                init.constant_(m.bias.data, 0.0)
+
+    return init_fun
+
+
+def get_scheduler(optimizer, hyperparameters, iterations=-1):
+    policy = hyperparameters.get("lr_policy", "constant")
+    if policy == "constant":
+        return None
+    if policy == "step":
+        if iterations >= 0:
+            for grp in optimizer.param_groups:       # StepLR(last_epoch != -1) expects initial_lr
+                grp.setdefault("initial_lr", hyperparameters["lr"])
+        return lr_scheduler.StepLR(optimizer, step_size=hyperparameters["step_size"],
+                                   gamma=hyperparameters["gamma"], last_epoch=iterations)
+    raise NotImplementedError("learning rate policy [%s] is not implemented" % policy)
+
+
+def get_model_list(dirname, key):
+    """latest checkpoint whose file name contains `key` (lexicographic order == iteration order)"""
+    if not os.path.exists(dirname):
+        return None
+    names = sorted(os.path.join(dirname, f) for f in os.listdir(dirname)
+                   if os.path.isfile(os.path.join(dirname, f)) and key in f and ".pt" in f)
+    return names[-1] if names else None
+
+
+def pytorch03_to_pytorch04(state_dict_base, trainer_name):
+    """strips the InstanceNorm running-stat keys very old checkpoints carry (utils.py:309-330)"""
+    def clean(sd):
+        return {k: v for k, v in sd.items()
+                if not (k.endswith(("running_mean", "running_var", "num_batches_tracked")) and
+                        k.startswith(("enc_content.model", "enc.model")))}
+    return {k: clean(v) for k, v in state_dict_base.items()}
+
+
+def vgg_preprocess(batch):
+    raise NotImplementedError("VGG perceptual loss is outside the B200 hot path (vgg_w = 0 in all configs)")
+
+
+def load_vgg16(model_dir):
+    raise NotImplementedError("VGG perceptual loss is outside the B200 hot path (vgg_w = 0 in all configs)")
+
+
+# ------------------------------------------------------------------------------------------ logging
+class Timer:
+    def __init__(self, msg):
+        self.msg, self.start_time = msg, None
+
+    def __enter__(self):
+        self.start_time = time.time()
+
+    def __exit__(self, exc_type, exc_value, exc_tb):
+        print(self.msg % (time.time() - self.start_time))
+
+
+def write_loss(iterations, trainer, train_writer):
+    for name in dir(trainer):
+        if name.startswith("__") or callable(getattr(trainer, name)):
+            continue
+        if "loss" in name or "grad" in name or "nwd" in name:
+            train_writer.add_scalar(name, getattr(trainer, name), iterations + 1)
+
+
+def prepare_sub_folder(output_directory):
+    image_directory = os.path.join(output_directory, "images")
+    checkpoint_directory = os.path.join(output_directory, "checkpoints")
+    for d in (image_directory, checkpoint_directory):
+        if not os.path.exists(d):
+            print("Creating directory: {}".format(d))
+            os.makedirs(d)
+    return checkpoint_directory, image_directory
+
+
+def _grid(image_outputs, display_image_num, file_name):
+    import torchvision.utils as vutils
+    tensors = [im.expand(-1, 3, -1, -1) for im in image_outputs]
+    data = torch.cat([t[:display_image_num] for t in tensors], 0)
+    grid = vutils.make_grid(data.data, nrow=display_image_num, padding=0, normalize=True)
+    vutils.save_image(grid, file_name, nrow=1)
+
+
+def write_2images(image_outputs, display_image_num, image_directory, postfix):
+    n = len(image_outputs)
+    _grid(image_outputs[0:n // 2], display_image_num, "%s/gen_a2b_%s.jpg" % (image_directory, postfix))
+    _grid(image_outputs[n // 2:n], display_image_num, "%s/gen_b2a_%s.jpg" % (image_directory, postfix))
+
+
+def write_html(filename, iterations, image_save_iterations, image_directory, all_size=1536):
+    rows = []
+
+    def row(path):
+        rows.append('<h3>%s</h3><a href="%s"><img src="%s" style="width:%dpx"></a><br>' % (
+            os.path.basename(path), path, path, all_size))
+
+    row("%s/gen_a2b_train_current.jpg" % image_directory)
+    row("%s/gen_b2a_train_current.jpg" % image_directory)
+    for j in range(iterations, image_save_iterations - 1, -1):
+        if j % image_save_iterations == 0:
+            for tag in ("a2b_test", "b2a_test", "a2b_train", "b2a_train"):
+                row("%s/gen_%s_%08d.jpg" % (image_directory, tag, j))
+    with open(filename, "w") as f:
+        f.write('<html><head><title>Experiment = %s</title><meta http-equiv="refresh" content="30"></head><body>%s'
+                "</body></html>" % (os.path.basename(filename), "\n".join(rows)))
+
+
+# ------------------------------------------------------------------------------------------ data
+def get_data_loader_folder(input_folder, batch_size, train, new_size=None, height=256, width=256, num_workers=4,
+                           crop=True):
+    from torch.utils.data import DataLoader
+    from torchvision import transforms
+    from data import ImageFolder
+    tf = [transforms.ToTensor(), transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))]
+    if crop:
+        tf = [transforms.RandomCrop((height, width))] + tf
+    if new_size is not None:
+        tf = [transforms.Resize(new_size)] + tf
+    if train:
+        tf = [transforms.RandomHorizontalFlip()] + tf
+    dataset = ImageFolder(input_folder, transform=transforms.Compose(tf))
+    return DataLoader(dataset=dataset, batch_size=batch_size, shuffle=train, drop_last=True,
+                      num_workers=num_workers, pin_memory=True)
+
+
+def get_data_loader_list(root, file_list, batch_size, train, new_size=None, height=256, width=256, num_workers=4,
+                         crop=True):
+    from torch.utils.data import DataLoader
+    from torchvision import transforms
+    from data import ImageFilelist
+    tf = [transforms.ToTensor(), transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))]
+    if crop:
+        tf = [transforms.RandomCrop((height, width))] + tf
+    if new_size is not None:
+        tf = [transforms.Resize(new_size)] + tf
+    if train:
+        tf = [transforms.RandomHorizontalFlip()] + tf
+    dataset = ImageFilelist(root, file_list, transform=transforms.Compose(tf))
+    return DataLoader(dataset=dataset, batch_size=batch_size, shuffle=train, drop_last=True,
+                      num_workers=num_workers, pin_memory=True)
+
+
+def get_all_data_loaders(conf):
+    bs, nw = conf["batch_size"], conf["num_workers"]
+    size_a = conf.get("new_size", conf.get("new_size_a"))
+    size_b = conf.get("new_size", conf.get("new_size_b"))
+    h, w = conf["crop_image_height"], conf["crop_image_width"]
+    if "data_root" in conf:
+        root = conf["data_root"]
+        mk = lambda sub, train, size: get_data_loader_folder(os.path.join(root, sub), bs, train, size, h, w, nw, True)
+        return mk("trainA", True, size_a), mk("trainB", True, size_b), mk("testA", False, size_a), mk("testB", False, size_b)
+    mk = lambda folder, lst, train, size: get_data_loader_list(conf[folder], conf[lst], bs, train, size, h, w, nw, True)
+    return (mk("data_folder_train_a", "data_list_train_a", True, size_a),
+            mk("data_folder_train_b", "data_list_train_b", True, size_b),
+            mk("data_folder_test_a", "data_list_test_a", False, size_a),
+            mk("data_folder_test_b", "data_list_test_b", False, size_b))

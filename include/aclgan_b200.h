@@ -53,7 +53,8 @@ typedef struct aclgan_out_spec {
     int64_t off;            /* element offset of logical pixel (n=0, y=0, x=0), channel 0 */
     int64_t sn, sy, sx, sc; /* element strides */
     int32_t N, H, W, C;     /* valid logical extent: rows outside are not stored; channels >= C dropped */
-    uint64_t bias;          /* fp32 [C] or 0 */
+    uint64_t bias;          /* fp32 [bias_n] or 0 */
+    int32_t bias_n;         /* channels >= bias_n get no bias (stored padding channels) */
     uint64_t stats;         /* fp32 [N][C][2] (sum, sum of squares) accumulated with atomics, or 0 */
 } aclgan_out_spec;
 
@@ -268,6 +269,26 @@ typedef struct aclgan_pack_weight_args {
     int32_t planes;
 } aclgan_pack_weight_args;
 int aclgan_pack_weight(const aclgan_pack_weight_args* a, void* stream);
+
+
+/* ---- fused multi-tensor Adam (torch.optim.Adam semantics with L2 weight decay: reference trainer.py:39-42,170,293)
+ *      + re-derivation of the packed bf16 weight planes in the same pass.  One table entry per parameter tensor. */
+typedef struct aclgan_adam_tensor {
+    uint64_t p, m, v;        /* fp32 contiguous: parameter (OIHW / dense), exp_avg, exp_avg_sq */
+    uint64_t g;              /* fp32 gradient base pointer */
+    int32_t d[4];            /* logical dims (co, ci, kh, kw); lower-rank tensors are left-padded with 1 */
+    int64_t gs[4];           /* gradient element strides per dim (the arena keeps conv grads in packed layout) */
+    int64_t goff;            /* gradient element offset */
+    uint64_t pk[2][2];       /* [packing: forward, transposed][plane] bf16 destinations or 0 */
+    int64_t aff[2][5];       /* [packing] base, s_co, s_ci, s_kh, s_kw */
+    int32_t planes;
+    int32_t pad_;
+} aclgan_adam_tensor;
+
+/* hyper (device, fp32[8]): lr, beta1, beta2, eps, weight_decay, grad_scale, step (advanced on device), unused.
+ * chunks (device, int32[2*n_chunks]): (tensor id, first element / 1024) per CTA. */
+int aclgan_adam_step(uint64_t table, uint64_t chunks, int32_t n_chunks, uint64_t hyper, void* stream);
+int aclgan_adam_advance(uint64_t hyper, void* stream);
 
 #ifdef __cplusplus
 }

@@ -117,7 +117,8 @@ def run_igemm(mem, plan):
                             continue
                         v = acc[r, :cnt].clone()
                         if bias is not None:
-                            v = v + bias[ch0:ch0 + cnt]
+                            nb = max(0, min(cnt, o.bias_n - ch0))
+                            v[:nb] = v[:nb] + bias[ch0:ch0 + nb]
                         v = _act(v, o.act, o.slope)
                         for yy in _mirror(y, o.H, o.mirror):
                             for xx in _mirror(x, o.W, o.mirror):

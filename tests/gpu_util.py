@@ -64,6 +64,7 @@ def out_spec(n, h, w, c, kind=N.OUT_F32, pad=0, act=N.ACT_NONE, bias=None, mirro
     o.N, o.H, o.W, o.C = n, h, w, c
     if bias is not None:
         o.bias = bias.data_ptr()
+        o.bias_n = bias.numel()
     return o, buf
 
 

@@ -1,0 +1,100 @@
+"""Host-logic test without a GPU: runs the whole dis_update / gen_update orchestration (engine.py, networks.py,
+trainer.py) on CPU tensors with the kernel LAUNCHES replaced by no-ops.  The plan builders (pure host C++) run
+for real, so every convolution geometry of both updates is validated; numerical results are meaningless here
+(the -m gpu tests check those)."""
+import ctypes as C
+import copy
+import os
+
+import pytest
+import torch
+import yaml
+
+import aclgan_native as N
+import engine as E
+import networks
+import trainer as T
+
+LAUNCHERS = ["aclgan_igemm_launch", "aclgan_wgrad_launch", "aclgan_pack_img", "aclgan_norm_stats",
+             "aclgan_norm_finalize", "aclgan_norm_apply", "aclgan_block_bwd_reduce", "aclgan_block_bwd_apply",
+             "aclgan_norm_bwd_finalize", "aclgan_img_grad_pack", "aclgan_img_grad_unpack", "aclgan_pack_weight"]
+
+
+class _Stub:
+    def __init__(self, real, counts):
+        self._real, self.counts = real, counts
+
+    def __getattr__(self, name):
+        if name in LAUNCHERS:
+            def f(*a, **k):
+                self.counts[name] = self.counts.get(name, 0) + 1
+                return 0
+            return f
+        return getattr(self._real, name)
+
+
+@pytest.fixture
+def dry(monkeypatch):
+    counts = {}
+    real = N.lib()
+    monkeypatch.setattr(N, "_lib", _Stub(real, counts))
+    monkeypatch.setattr(E.Engine, "_check_device", lambda self: None)
+    monkeypatch.setattr(networks, "_default_engine", {})
+    orig = E.Engine.__init__
+    monkeypatch.setattr(E.Engine, "__init__", lambda self, precision="bf16", device="cpu": orig(self, precision, "cpu"))
+    monkeypatch.setattr(networks._EngineNet, "_ensure_bound", _ensure_bound_cpu)
+    yield counts
+    N._lib = real
+
+
+def _ensure_bound_cpu(self):
+    if self._eng is None:
+        self.bind(networks.get_engine())
+    if not self._bound:
+        self._build_layers()
+        self._bound = True
+        if self._own_arena:
+            self._arena.finalize()
+            self.attach_grads()
+
+
+def _cfg(name="male2female.yaml", tiny=True):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = yaml.safe_load(open(os.path.join(root, "acl-gan_b200", "configs", name)))
+    if tiny:
+        cfg["gen"].update(dim=16, mlp_dim=32, n_res=2)
+        cfg["dis"].update(dim=16)
+        cfg["display_size"] = 2
+    return cfg
+
+
+@pytest.mark.parametrize("cfgname,precision", [("male2female.yaml", "bf16"), ("male2female.yaml", "fp32x3"),
+                                               ("selfie2anime.yaml", "bf16")])
+def test_updates_dryrun(dry, cfgname, precision):
+    cfg = _cfg(cfgname)
+    cfg["precision"] = precision
+    torch.manual_seed(0)
+    tr = T.aclgan_Trainer(copy.deepcopy(cfg))
+    x_a = torch.rand(2, 3, 64, 64) * 2 - 1
+    x_b = torch.rand(2, 3, 64, 64) * 2 - 1
+    tr.dis_update(x_a, x_b, cfg)
+    n_dis = dict(dry)
+    tr.gen_update(x_a, x_b, cfg)
+    assert n_dis["aclgan_igemm_launch"] > 50 and n_dis["aclgan_wgrad_launch"] == 7 * 3 * 4
+    assert dry["aclgan_wgrad_launch"] > n_dis["aclgan_wgrad_launch"]
+    for name in ("loss_dis_total", "loss_gen_total", "loss_idt_A", "loss_gen_adv_2"):
+        assert getattr(tr, name).dim() == 0
+    for p in list(tr.gen_AB.parameters()) + list(tr.dis_2.parameters()):
+        assert p.grad is not None and p.grad.shape == p.shape
+    out = tr.sample(x_a, x_b)
+    assert len(out) == (9 if cfg["focus_loss"] > 0 else 7)
+
+
+def test_full_width_plans_dryrun(dry):
+    """all layer geometries of the real (dim 64) networks at 64x64"""
+    cfg = _cfg(tiny=False)
+    torch.manual_seed(0)
+    tr = T.aclgan_Trainer(copy.deepcopy(cfg))
+    x = torch.rand(1, 3, 64, 64) * 2 - 1
+    tr.dis_update(x, x, cfg)
+    tr.gen_update(x, x, cfg)

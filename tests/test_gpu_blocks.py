@@ -1,0 +1,206 @@
+"""-m gpu: fused conv blocks (conv + norm + act + residual + upsample + reflect pad), forward and backward,
+against a plain torch fp64 restatement on the same operands (tolerances: fp32x3 parity mode 2e-4 / bf16 mode 3e-2)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import aclgan_native as N
+import engine as E
+
+pytestmark = pytest.mark.gpu
+
+
+def plane_from_nchw(eng, x, pad):
+    n, c, h, w = x.shape
+    a = E.ActT(eng, n, h, w, c, pad)
+    v = F.pad(x.float(), (pad,) * 4, mode="reflect").permute(0, 2, 3, 1) if pad else x.float().permute(0, 2, 3, 1)
+    full = torch.zeros((n, h + 2 * pad, w + 2 * pad, a.c), device=x.device)
+    full[..., :c] = v
+    hi = full.bfloat16()
+    a.buf[0, :a.numel] = hi.reshape(-1)
+    if a.planes == 2:
+        a.buf[1, :a.numel] = (full - hi.float()).bfloat16().reshape(-1)
+    return a
+
+
+def ref_block(x, w, b, stride, pad, norm, act, res, upsample, out_pad, adain, ln):
+    y = F.conv2d(F.pad(x, (pad,) * 4, mode="reflect"), w, b, stride=stride)
+    if norm == N.NORM_IN or norm == N.NORM_ADAIN:
+        mu = y.mean((2, 3), keepdim=True)
+        var = y.var((2, 3), unbiased=False, keepdim=True)
+        y = (y - mu) / torch.sqrt(var + 1e-5)
+        if norm == N.NORM_ADAIN:
+            y = y * adain[0][:, :, None, None] + adain[1][:, :, None, None]
+    elif norm == N.NORM_LN:
+        flat = y.reshape(y.shape[0], -1)
+        mu = flat.mean(1).view(-1, 1, 1, 1)
+        sd = flat.std(1).view(-1, 1, 1, 1)
+        y = (y - mu) / (sd + 1e-5) * ln[0].view(1, -1, 1, 1) + ln[1].view(1, -1, 1, 1)
+    if act == N.ACT_RELU:
+        y = torch.relu(y)
+    elif act == N.ACT_LRELU:
+        y = F.leaky_relu(y, 0.2)
+    if res is not None:
+        y = y + res
+    if upsample == 2:
+        y = F.interpolate(y, scale_factor=2, mode="nearest")
+    return F.pad(y, (out_pad,) * 4, mode="reflect") if out_pad else y
+
+
+CASES = [
+    # cin, cout, k, stride, pad, norm, act, res, upsample, out_pad, n, h
+    (64, 64, 3, 1, 1, N.NORM_IN, N.ACT_RELU, False, 1, 1, 2, 16),
+    (64, 64, 3, 1, 1, N.NORM_ADAIN, N.ACT_NONE, True, 2, 2, 2, 8),
+    (64, 128, 4, 2, 1, N.NORM_IN, N.ACT_RELU, False, 1, 1, 2, 16),
+    (128, 64, 5, 1, 2, N.NORM_LN, N.ACT_RELU, False, 2, 2, 2, 8),
+    (128, 64, 5, 1, 2, N.NORM_LN, N.ACT_RELU, False, 1, 3, 1, 8),
+    (64, 128, 4, 2, 1, N.NORM_NONE, N.ACT_LRELU, False, 1, 1, 2, 16),
+    (64, 64, 4, 2, 1, N.NORM_NONE, N.ACT_RELU, False, 1, 0, 2, 8),
+    (32, 16, 3, 1, 1, N.NORM_ADAIN, N.ACT_RELU, False, 1, 1, 2, 8),      # channel counts below one 64-chunk
+]
+
+
+@pytest.mark.parametrize("precision", ["fp32x3", "bf16"])
+@pytest.mark.parametrize("cin,cout,k,stride,pad,norm,act,use_res,upsample,out_pad,n,h", CASES)
+def test_conv_block(precision, cin, cout, k, stride, pad, norm, act, use_res, upsample, out_pad, n, h):
+    eng = E.Engine(precision)
+    tol = 2e-4 if precision == "fp32x3" else 4e-2
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = torch.randn(n, cin, h, h, device=dev)
+    w = torch.nn.Parameter(torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5)
+    b = torch.nn.Parameter(torch.randn(cout, device=dev) * 0.1)
+    ho = (h + 2 * pad - k) // stride + 1
+    res = torch.randn(n, cout, ho, ho, device=dev) if use_res else None
+    adain_w = torch.rand(n, cout, device=dev) + 0.5
+    adain_b = torch.randn(n, cout, device=dev)
+    gamma, beta = torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev)
+
+    arena = E.GradArena(eng.device)
+    layer = E.ConvLayer(eng, arena, w, b, stride, pad)
+    ln_off = (arena.reserve(cout), arena.reserve(cout))
+    arena.finalize()
+    xa = plane_from_nchw(eng, x, pad)
+    xa.requires_grad = True
+    ra = plane_from_nchw(eng, res, 1) if use_res else None
+    if ra is not None:
+        ra.requires_grad = True
+    got_adain = {}
+    adain = (adain_w, adain_b, lambda dw, db: got_adain.update(dw=dw, db=db)) if norm == N.NORM_ADAIN else None
+    ln = (gamma, beta, arena.view(ln_off[0], cout), arena.view(ln_off[1], cout)) if norm == N.NORM_LN else None
+    tape = E.Tape()
+    out = eng.conv_block(tape, layer, xa, norm=norm, act=act, out_pad=out_pad, upsample=upsample, res=ra,
+                         adain=adain, ln=ln)
+    torch.cuda.synchronize()
+
+    # ---- reference in fp64 on the operands the kernels actually see (bf16 / hi+lo rounded)
+    def eff(t, planes):
+        hi = t.detach().float().bfloat16()
+        return (hi.double() + ((t.detach().float() - hi.float()).bfloat16().double() if planes == 2 else 0))
+    P = eng.prec.planes
+    x64 = eff(x, P).requires_grad_(True)
+    w64 = eff(w, P).requires_grad_(True)
+    b64 = b.detach().double().requires_grad_(True)
+    r64 = eff(res, P).requires_grad_(True) if use_res else None
+    aw, ab = adain_w.double().requires_grad_(True), adain_b.double().requires_grad_(True)
+    g64, be64 = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    ref = ref_block(x64, w64, b64, stride, pad, norm, act, r64, upsample, out_pad, (aw, ab), (g64, be64))
+
+    p = out.pad
+    full = out.buf[:, :out.numel].float().sum(0).view(n, out.h + 2 * p, out.w + 2 * p, out.c)
+    got = full[..., :cout].permute(0, 3, 1, 2).double()
+    err = float((got - ref).norm() / ref.norm())
+    assert err < tol, ("forward", err)
+    if out.c > cout:
+        assert float(full[..., cout:].abs().max()) == 0.0
+
+    # ---- backward: random gradient on the padded output plane
+    G = torch.randn_like(ref)
+    gp = torch.zeros((n, out.h + 2 * p, out.w + 2 * p, out.c), device=dev, dtype=eng.prec.dtype)
+    gp[..., :cout] = G.permute(0, 2, 3, 1).to(eng.prec.dtype)
+    Geff = gp[..., :cout].double().permute(0, 3, 1, 2)
+    out.gp = gp
+    tape.backward()
+    torch.cuda.synchronize()
+    (ref * Geff).sum().backward()
+
+    def rel(a, bb):
+        return float((a.double() - bb).norm() / (bb.norm() + 1e-30))
+    # gradient w.r.t. the input: fold my padded-plane gradient with the adjoint of reflect padding
+    gx = xa.gp[..., :cin].double().permute(0, 3, 1, 2).requires_grad_(False)
+    probe = torch.zeros_like(x64).requires_grad_(True)
+    (F.pad(probe, (pad,) * 4, mode="reflect") * gx).sum().backward()
+    btol = tol * 3
+    assert rel(probe.grad, x64.grad) < btol, ("dgrad", rel(probe.grad, x64.grad))
+    gw, gb = layer.grad_views()
+    assert rel(gw, w64.grad) < btol, ("wgrad", rel(gw, w64.grad))
+    if norm == N.NORM_NONE:
+        assert rel(gb, b64.grad) < btol, ("bgrad", rel(gb, b64.grad))
+    if use_res:
+        assert rel(ra.gr[..., :cout].permute(0, 3, 1, 2), r64.grad) < btol, "res grad"
+    if norm == N.NORM_ADAIN:
+        assert rel(got_adain["dw"], aw.grad) < btol and rel(got_adain["db"], ab.grad) < btol, "adain grads"
+    if norm == N.NORM_LN:
+        assert rel(ln[2], g64.grad) < btol and rel(ln[3], be64.grad) < btol, "ln grads"
+
+
+@pytest.mark.parametrize("precision", ["fp32x3", "bf16"])
+def test_image_io_and_final_conv(precision):
+    """image pack (+concat) -> window conv ; 64 -> 4 tanh conv to an NCHW image ; both with backward"""
+    eng = E.Engine(precision)
+    tol = 2e-4 if precision == "fp32x3" else 4e-2
+    torch.manual_seed(1)
+    dev = "cuda"
+    n, h = 2, 16
+    P = eng.prec.planes
+
+    def eff(t):
+        hi = t.detach().float().bfloat16()
+        return hi.double() + ((t.detach().float() - hi.float()).bfloat16().double() if P == 2 else 0)
+
+    # ---- first conv of a discriminator on a concatenated pair (6 channels, 4x4 stride 2)
+    a_img = torch.rand(n, 3, h, h, device=dev) * 2 - 1
+    b_img = torch.rand(n, 3, h, h, device=dev) * 2 - 1
+    w = torch.nn.Parameter(torch.randn(64, 6, 4, 4, device=dev) * 0.1)
+    b = torch.nn.Parameter(torch.randn(64, device=dev) * 0.1)
+    arena = E.GradArena(eng.device)
+    layer = E.ConvLayer(eng, arena, w, b, 2, 1, N.WINDOW_IN)
+    w2 = torch.nn.Parameter(torch.randn(4, 64, 7, 7, device=dev) * 0.02)
+    b2 = torch.nn.Parameter(torch.randn(4, device=dev) * 0.1)
+    layer2 = E.ConvLayer(eng, arena, w2, b2, 1, 3, N.WINDOW_OUT)
+    arena.finalize()
+    tape = E.Tape()
+    ia, ib = E.ImgT(a_img), E.ImgT(b_img, requires_grad=True)
+    xp = eng.pack_image(tape, ia, 1, 16, ib)
+    out = eng.conv_block(tape, layer, xp, norm=N.NORM_NONE, act=N.ACT_LRELU, out_pad=3)
+    img = eng.conv_to_image(tape, layer2, out)
+    torch.cuda.synchronize()
+
+    a64, b64i = eff(a_img), eff(b_img).requires_grad_(True)
+    w64, bb64 = eff(w).requires_grad_(True), b.detach().double().requires_grad_(True)
+    w264, b264 = eff(w2).requires_grad_(True), b2.detach().double().requires_grad_(True)
+    y = F.leaky_relu(F.conv2d(F.pad(torch.cat((a64, b64i), 1), (1,) * 4, mode="reflect"), w64, bb64, stride=2), 0.2)
+    y_seen = y
+    if P == 1:
+        y_seen = y + (y.detach().float().bfloat16().double() - y.detach())      # the next conv reads the bf16 plane
+    ref = torch.tanh(F.conv2d(F.pad(y_seen, (3,) * 4, mode="reflect"), w264, b264))
+    err = float((img.t.double() - ref).norm() / ref.norm())
+    assert err < tol, ("forward", err)
+
+    G = torch.randn_like(ref)
+    img.add_grad(G.float())
+    tape.backward()
+    torch.cuda.synchronize()
+    (ref * G.float().double()).sum().backward()
+
+    def rel(a, bb):
+        return float((a.double() - bb).norm() / (bb.norm() + 1e-30))
+    btol = tol * 3
+    gw2, gb2 = layer2.grad_views()
+    assert rel(gw2, w264.grad) < btol, ("wgrad window-out", rel(gw2, w264.grad))
+    assert rel(gb2, b264.grad) < btol, "bias grad final"
+    gw, gb = layer.grad_views()
+    assert rel(gw, w64.grad) < btol, ("wgrad window-in", rel(gw, w64.grad))
+    assert rel(gb, bb64.grad) < btol, "bias grad"
+    assert ia.grad is None
+    assert rel(ib.grad, b64i.grad) < btol, ("image grad", rel(ib.grad, b64i.grad))

@@ -1,0 +1,164 @@
+"""-m gpu: whole dis_update / gen_update through the drop-in trainer vs (a) the golden fixtures generated from the
+UNMODIFIED reference and (b) the CPU oracle run live on this box with identical weights / inputs / noise.
+
+Parity contract: forward tensors and loss scalars <= 1e-3 rel (fp32x3 parity mode); gradients are
+judged against the fp64 run with the reference's own fp32-vs-fp64 noise floor as allowance:
+err(new, fp64) <= max(1e-3, 2 * err(ref_fp32, fp64)); post-step parameters <= 1e-3 rel.  The bf16 throughput mode is
+reported against the same numbers with a 5e-2 bar on losses/images."""
+import copy
+import os
+
+import pytest
+import torch
+
+import aclgan_oracle as O
+import trainer as T
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(golden_dir, case, tag):
+    return torch.load(os.path.join(golden_dir, "%s_%s.pt" % (case, tag)), weights_only=False)
+
+
+def _inputs(g):
+    torch.manual_seed(1)
+    b, s = g["batch"], g["size"]
+    x_a = torch.rand(b, 3, s, s) * 2 - 1
+    x_b = torch.rand(b, 3, s, s) * 2 - 1
+    torch.manual_seed(2)
+    zs = [torch.randn(b, 8, 1, 1) for _ in range(6)]
+    return x_a, x_b, zs
+
+
+def _sig(t):
+    t = t.detach().double().reshape(-1)
+    return torch.stack([t.sum(), t.abs().sum(), (t * t).sum()])
+
+
+def _build(g, precision):
+    cfg = copy.deepcopy(g["cfg"])
+    cfg["precision"] = precision
+    torch.manual_seed(0)
+    tr = T.aclgan_Trainer(cfg)
+    for n, sig in g["init_sig"].items():
+        mine = torch.stack([_sig(v) for v in getattr(tr, n).state_dict().values()]).sum(0)
+        if not torch.allclose(mine, sig, rtol=1e-9, atol=1e-9):
+            pytest.skip("CPU RNG stream of this host differs from the fixture host (%s)" % n)
+    tr.cuda()
+    return tr, cfg
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("case,precision", [("tiny", "fp32x3"), ("p0", "fp32x3"), ("p0nf", "fp32x3"), ("tiny", "bf16"),
+                                            ("p0", "bf16")])
+def test_step_vs_golden(golden_dir, case, precision):
+    g32, g64 = _load(golden_dir, case, "fp32"), _load(golden_dir, case, "fp64")
+    tr, cfg = _build(g32, precision)
+    x_a, x_b, zs = _inputs(g32)
+    xa, xb = x_a.cuda(), x_b.cuda()
+    ltol = 1e-3 if precision == "fp32x3" else 5e-2
+    report = []
+
+    tr._noise = zs[:3]
+    tr.dis_update(xa, xb, cfg)
+    torch.cuda.synchronize()
+    for k, v in g32["dis_losses"].items():
+        e = abs(float(getattr(tr, k)) - float(v)) / abs(float(v))
+        report.append((k, e))
+        assert e < ltol, (k, float(getattr(tr, k)), float(v))
+    for k in ("x_B_fake", "x_A_fake", "x_A2_fake"):
+        e = _rel(tr._last_cycle[k].t, g32["dis_forward"][k])
+        report.append(("dis " + k, e))
+        assert e < ltol, (k, e)
+    if precision == "fp32x3":
+        gg32, gg64 = g32["dis_grads"], g64["dis_grads"]
+        for i, key in enumerate(gg64["keys"]):
+            n, k = key.split(".", 1)
+            gr = dict(getattr(tr, n).named_parameters())[k].grad.double().cpu().reshape(-1)
+            ref64, ref32 = float(gg64["norm"][i]), float(gg32["norm"][i])
+            allow = max(1e-3, 2 * abs(ref32 - ref64) / ref64)
+            assert abs(float(gr.norm()) - ref64) / ref64 < allow, ("dis grad norm", key, float(gr.norm()), ref64)
+            hd = gg64["head"][i][:min(8, gr.numel())]
+            assert float((gr[:hd.numel()] - hd).norm()) <= allow * max(float(hd.norm()), 1e-3 * ref64) + 1e-12, ("head", key)
+        ps = g32["dis_params_after"]
+        for i, key in enumerate(ps["keys"]):
+            n, k = key.split(".", 1)
+            p = dict(getattr(tr, n).named_parameters())[k]
+            assert abs(float((p.double() ** 2).sum()) - float(ps["sig"][i][2])) <= 1e-3 * float(ps["sig"][i][2]) + 1e-12, key
+
+    tr._noise = zs[3:]
+    tr.gen_update(xa, xb, cfg)
+    torch.cuda.synchronize()
+    for k, v in g32["gen_losses"].items():
+        e = abs(float(getattr(tr, k)) - float(v)) / max(abs(float(v)), 1e-12)
+        report.append((k, e))
+        assert e < (ltol if "focus" not in k else 5 * ltol), (k, float(getattr(tr, k)), float(v))
+    r = tr._last_cycle
+    for k in ("x_B_fake", "x_A_fake", "x_A2_fake"):
+        e = _rel(r[k].t, g32["gen_forward"][k])
+        report.append(("gen " + k, e))
+        assert e < ltol, (k, e)
+    assert _rel(r["o_rec_a"].t[:, :3], g32["gen_forward"]["x_A_recon"]) < ltol
+    if precision == "fp32x3":
+        gg32, gg64 = g32["gen_grads"], g64["gen_grads"]
+        worst = 0.0
+        for i, key in enumerate(gg64["keys"]):
+            n, k = key.split(".", 1)
+            ref64, ref32 = float(gg64["norm"][i]), float(gg32["norm"][i])
+            if ref64 < 1e-6:
+                continue        # conv biases in front of IN / AdaIN: exactly-zero true gradient
+            gr = dict(getattr(tr, n).named_parameters())[k].grad.double().cpu().reshape(-1)
+            allow = max(1e-3, 2 * abs(ref32 - ref64) / ref64)
+            e = abs(float(gr.norm()) - ref64) / ref64
+            worst = max(worst, e / allow)
+            assert e < allow, ("gen grad norm", key, float(gr.norm()), ref64, ref32)
+        report.append(("gen grad worst/allow", worst))
+    print("\n[step parity %s %s] " % (case, precision) + "  ".join("%s=%.2e" % kv for kv in report))
+
+
+@pytest.mark.parametrize("precision", ["fp32x3"])
+def test_gradients_vs_live_oracle(golden_dir, precision):
+    """full gradient tensors of the tiny networks vs the CPU oracle in fp64, with the oracle's own fp32 noise floor"""
+    g32 = _load(golden_dir, "tiny", "fp32")
+    tr, cfg = _build(g32, precision)
+    x_a, x_b, zs = _inputs(g32)
+    sds = {n: {k: v.detach().cpu().clone() for k, v in getattr(tr, n).state_dict().items()} for n in O.OracleTrainer.NETS}
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        ot = O.OracleTrainer(copy.deepcopy(g32["cfg"]), dtype=dt, construct=False)
+        ot.load_state_dicts(sds)
+        ot.dis_update(x_a.to(dt), x_b.to(dt), [z.to(dt) for z in zs[:3]], step=False)
+        gd = {(n, k): v.grad.clone() for n in ("dis_A", "dis_B", "dis_2") for k, v in ot.nets[n].items() if v.grad is not None}
+        ot.gen_update(x_a.to(dt), x_b.to(dt), [z.to(dt) for z in zs[3:]], step=False)
+        gg = {(n, k): v.grad.clone() for n in ("gen_AB", "gen_BA") for k, v in ot.nets[n].items() if v.grad is not None}
+        res[dt] = (gd, gg)
+    # same weights for both updates: grads only (no optimizer interference) -> lr 0 keeps the parameters fixed
+    for opt in (tr.dis_opt, tr.gen_opt):
+        for grp in opt.param_groups:
+            grp["lr"] = 0.0
+            grp["weight_decay"] = 0.0
+    tr._noise = zs[:3]
+    tr.dis_update(x_a.cuda(), x_b.cuda(), cfg)
+    mine_d = {(n, k): p.grad.detach().double().cpu().clone() for n in ("dis_A", "dis_B", "dis_2")
+              for k, p in getattr(tr, n).named_parameters()}
+    tr._noise = zs[3:]
+    tr.gen_update(x_a.cuda(), x_b.cuda(), cfg)
+    mine_g = {(n, k): p.grad.detach().double().cpu().clone() for n in ("gen_AB", "gen_BA")
+              for k, p in getattr(tr, n).named_parameters()}
+    worst = []
+    for mine, idx in ((mine_d, 0), (mine_g, 1)):
+        for key, g64 in res[torch.float64][idx].items():
+            nrm = float(g64.norm())
+            if nrm < 1e-7:
+                continue
+            e_new = float((mine[key] - g64).norm()) / nrm
+            e_ref = float((res[torch.float32][idx][key].double() - g64).norm()) / nrm
+            worst.append((e_new / max(1e-3, 2 * e_ref), key, e_new, e_ref))
+    worst.sort(reverse=True)
+    print("\n[grad parity vs live oracle] worst 5:", [(k, "%.2e" % a, "%.2e" % b) for _, k, a, b in worst[:5]])
+    assert worst[0][0] < 1.0, worst[:5]

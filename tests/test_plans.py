@@ -42,6 +42,7 @@ def out_spec(mem, n, h, w, c, kind=N.OUT_F32, pad=0, act=N.ACT_NONE, bias=None, 
     o.N, o.H, o.W, o.C = n, h, w, c
     if bias is not None:
         o.bias = mem.add(bias)
+        o.bias_n = bias.numel()
     return o, buf
 
 

@@ -198,6 +198,11 @@ class ConvLayer:
     def db(self):
         return self.arena.view(self.db_off, self.cout)
 
+    def grad_layout(self):
+        """(element offset in the arena, (s_co, s_ci, s_kh, s_kw)) of the OIHW gradient inside the packed-layout buffer"""
+        base, s_co, s_ci, s_kh, s_kw = self.aff[self.layout]
+        return self.dw_off + base, (s_co, s_ci, s_kh, s_kw)
+
     def grad_views(self):
         """(weight grad in OIHW shape, bias grad) as views of the arena (a small copy for the one layout whose
         kw stride is negative)."""

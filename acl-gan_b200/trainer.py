@@ -58,6 +58,10 @@ class aclgan_Trainer(nn.Module):
         if hp.get("vgg_w", 0) > 0:
             raise NotImplementedError("vgg_w > 0: the VGG perceptual loss is outside the B200 hot path")
         self.precision = hp.get("precision", os.environ.get("ACLGAN_PRECISION", "bf16"))
+        self._hp = hp
+        self.use_graphs = bool(int(hp.get("cuda_graphs", os.environ.get("ACLGAN_CUDA_GRAPHS", "1"))))
+        self._graphs = {}
+        self._launches = {}
         self._ready = False
         self._noise = None          # optional injected style noise (tests / graph replay): list of 3 tensors
 
@@ -79,10 +83,97 @@ class aclgan_Trainer(nn.Module):
         self.dis_arena.finalize()
         for net in self._nets():
             net.attach_grads()
+        self._adam_gen = self._adam_group(self.gen_opt, (self.gen_AB, self.gen_BA), self.gen_arena)
+        self._adam_dis = self._adam_group(self.dis_opt, (self.dis_A, self.dis_B, self.dis_2), self.dis_arena)
         self._ready = True
 
     def _nets(self):
         return (self.gen_AB, self.gen_BA, self.dis_A, self.dis_B, self.dis_2)
+
+    # ------------------------------------------------------------------------------------------ optimizer
+    def _adam_group(self, opt, nets, arena):
+        """device tables for the fused Adam kernel; the torch.optim.Adam object keeps owning the state tensors
+        (exp_avg / exp_avg_sq / step) so optimizer.pt stays interchangeable with the reference's"""
+        import ctypes as C
+        import networks as NW
+        dev = self.eng.device
+        layer_of = {}
+        for net in nets:
+            for blk in net.modules():
+                if isinstance(blk, NW.Conv2dBlock) and blk._layer is not None:
+                    layer_of[id(blk.conv.weight)] = blk._layer
+        params = opt.param_groups[0]["params"]
+        table = (N.AdamTensor * len(params))()
+        chunks = []
+        step0 = 0.0
+        for i, p in enumerate(params):
+            st = opt.state[p]
+            if "exp_avg" not in st:
+                st["step"] = torch.tensor(0.0)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            for k in ("exp_avg", "exp_avg_sq"):
+                if st[k].device != p.device or not st[k].is_contiguous():
+                    st[k] = st[k].to(p.device).contiguous()
+            step0 = max(step0, float(st["step"]))
+            t = table[i]
+            t.p, t.m, t.v = p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+            t.g = arena.flat.data_ptr()
+            shape = list(p.shape)
+            while len(shape) < 4:
+                shape = [1] + shape
+            lay = layer_of.get(id(p))
+            if lay is not None:
+                off, strides = lay.grad_layout()
+                t.goff = off
+                for j in range(4):
+                    t.gs[j] = strides[j]
+                for k in (0, 1):
+                    for pl in range(self.eng.prec.planes):
+                        t.pk[k][pl] = lay.packed[k][pl].data_ptr()
+                    for j in range(5):
+                        t.aff[k][j] = lay.aff[k][j]
+            else:
+                g = p.grad
+                assert g is not None and g.is_contiguous() and g.untyped_storage().data_ptr() == arena.flat.untyped_storage().data_ptr()
+                t.goff = g.storage_offset()
+                acc = 1
+                for j in reversed(range(4)):
+                    t.gs[j] = acc
+                    acc *= shape[j]
+            for j in range(4):
+                t.d[j] = shape[j]
+            t.planes = self.eng.prec.planes
+            for c in range((p.numel() + 1023) // 1024):
+                chunks += [i, c]
+        hp = self._hp
+        world = 1
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size()
+        hyper = torch.tensor([opt.param_groups[0]["lr"], hp["beta1"], hp["beta2"], 1e-8, hp["weight_decay"],
+                              1.0 / world, step0, 0.0], dtype=torch.float32, device=dev)
+        raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(dev)
+        return dict(table=raw, chunks=torch.tensor(chunks, dtype=torch.int32, device=dev), hyper=hyper,
+                    n_chunks=len(chunks) // 2, opt=opt, params=params, step=step0)
+
+    def _adam_step(self, grp):
+        L = N.lib()
+        sp = E._sp()
+        N.check(L.aclgan_adam_advance(grp["hyper"].data_ptr(), sp), "adam_advance")
+        N.check(L.aclgan_adam_step(grp["table"].data_ptr(), grp["chunks"].data_ptr(), grp["n_chunks"],
+                                   grp["hyper"].data_ptr(), sp), "adam_step")
+        grp["step"] += 1
+        grp["opt"]._opt_called = True
+
+    def _sync_opt_state(self):
+        """mirror the device-side step counters into the torch optimizer state (before state_dict())"""
+        if not self._ready:
+            return
+        for grp in (self._adam_gen, self._adam_dis):
+            n = float(grp["hyper"][6].item())
+            for p in grp["params"]:
+                grp["opt"].state[p]["step"] = torch.tensor(n)
 
     def _draw_noise(self, n):
         """three CPU randn draws moved to the device, exactly as trainer.py:99-101 / 254-256"""
@@ -93,10 +184,10 @@ class aclgan_Trainer(nn.Module):
                 for _ in range(3)]
 
     def _allreduce(self, arena):
+        """data parallel: sum the flat gradient buffer over ranks (NCCL); the 1/world scale is folded into Adam"""
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(arena.flat)
-            arena.flat.div_(dist.get_world_size())
 
     # ------------------------------------------------------------------------------------------ pieces
     def recon_criterion(self, input, target):
@@ -183,6 +274,14 @@ class aclgan_Trainer(nn.Module):
     # ------------------------------------------------------------------------------------------ updates
     def gen_update(self, x_a, x_b, hyperparameters):
         self._setup()
+        if self.use_graphs:
+            self._replay("gen", x_a, x_b, hyperparameters)
+        else:
+            self._gen_fwd_bwd(x_a, x_b, hyperparameters, self._draw_noise(x_a.size(0)))
+        self._allreduce(self.gen_arena)
+        self._adam_step(self._adam_gen)
+
+    def _gen_fwd_bwd(self, x_a, x_b, hyperparameters, zs):
         hp = hyperparameters
         self.gen_arena.zero_()
         for d in (self.dis_A, self.dis_B, self.dis_2):
@@ -190,7 +289,6 @@ class aclgan_Trainer(nn.Module):
         tape = E.Tape()
         n = x_a.size(0)
         xa, xb = E.ImgT(x_a.detach().float()), E.ImgT(x_b.detach().float())
-        zs = self._draw_noise(n)
         focus = hp["focus_loss"] > 0
         r = self._cycle(tape, xa, xb, zs, need_recon=True)
 
@@ -236,18 +334,21 @@ class aclgan_Trainer(nn.Module):
         tape.backward()
         for d in (self.dis_A, self.dis_B, self.dis_2):
             d.train_weights = True
-        self._allreduce(self.gen_arena)
-        self.gen_opt.step()
-        self.gen_AB.mark_dirty()
-        self.gen_BA.mark_dirty()
 
     def dis_update(self, x_a, x_b, hyperparameters):
         self._setup()
+        if self.use_graphs:
+            self._replay("dis", x_a, x_b, hyperparameters)
+        else:
+            self._dis_fwd_bwd(x_a, x_b, hyperparameters, self._draw_noise(x_a.size(0)))
+        self._allreduce(self.dis_arena)
+        self._adam_step(self._adam_dis)
+
+    def _dis_fwd_bwd(self, x_a, x_b, hyperparameters, zs):
         hp = hyperparameters
         self.dis_arena.zero_()
         n = x_a.size(0)
         xa, xb = E.ImgT(x_a.detach().float()), E.ImgT(x_b.detach().float())
-        zs = self._draw_noise(n)
         # the generators only produce the fakes here: no backward pass is recorded for them (trainer.py:91)
         r = self._cycle(E.Tape(enabled=False), xa, xb, zs, need_recon=False)
         fake_a, fake_a2, fake_b = (E.ImgT(r[k].t) for k in ("x_A_fake", "x_A2_fake", "x_B_fake"))
@@ -263,10 +364,76 @@ class aclgan_Trainer(nn.Module):
                            self._lsgan(self.dis_2.dis(tape, xa, fake_a2), 1.0, gcw))
         self.loss_dis_total = gw * self.loss_dis_A + gw * self.loss_dis_B + gcw * self.loss_dis_2
         tape.backward()
-        self._allreduce(self.dis_arena)
-        self.dis_opt.step()
-        for d in (self.dis_A, self.dis_B, self.dis_2):
-            d.mark_dirty()
+
+    @property
+    def launches_per_step_pair(self):
+        """kernels of libaclgan_b200.so launched per dis_update + gen_update (counted while capturing the graphs)"""
+        return sum(self._launches.values()) if len(self._launches) == 2 else None
+
+    # ------------------------------------------------------------------------------------------ CUDA graphs
+    def _replay(self, kind, x_a, x_b, hp):
+        """forward + backward of one update as a captured CUDA graph (the ~2500 kernel launches of an update would
+        otherwise be bound by host-side launch overhead).  Inputs / style noise are copied into static buffers; the
+        loss_* attributes are static 0-dim tensors the replay overwrites.  The gradient all-reduce and the Adam
+        kernel stay outside the graph."""
+        n = x_a.size(0)
+        key = (kind, tuple(x_a.shape), tuple(sorted((k, v) for k, v in hp.items() if isinstance(v, (int, float)))))
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._capture(kind, x_a, x_b, hp)
+            self._graphs[key] = ent
+        ent["xa"].copy_(x_a, non_blocking=True)
+        ent["xb"].copy_(x_b, non_blocking=True)
+        if self._noise is not None:
+            zs, self._noise = self._noise, None
+            ent["zpin"].copy_(torch.stack([z.reshape(n, self.style_dim).float().cpu() for z in zs]))
+        else:       # three CPU randn draws in the reference's order (trainer.py:99-101 / 254-256)
+            for i in range(3):
+                ent["zpin"][i].copy_(torch.randn(n, self.style_dim, 1, 1).view(n, self.style_dim))
+        ent["z"].copy_(ent["zpin"], non_blocking=True)
+        ent["graph"].replay()
+        for k, v in ent["losses"].items():
+            setattr(self, k, v)
+        self._last_cycle = ent["cycle"]
+
+    def _capture(self, kind, x_a, x_b, hp):
+        dev = self.eng.device
+        n = x_a.size(0)
+        ent = dict(xa=torch.empty(x_a.shape, dtype=torch.float32, device=dev),
+                   xb=torch.empty(x_b.shape, dtype=torch.float32, device=dev),
+                   z=torch.zeros((3, n, self.style_dim), dtype=torch.float32, device=dev),
+                   zpin=torch.zeros((3, n, self.style_dim), dtype=torch.float32).pin_memory())
+        ent["xa"].copy_(x_a)
+        ent["xb"].copy_(x_b)
+        impl = self._gen_fwd_bwd if kind == "gen" else self._dis_fwd_bwd
+
+        def run():
+            impl(ent["xa"], ent["xb"], hp, [E.ImgT(ent["z"][i]) for i in range(3)])
+
+        # warm-up off the capture stream (lazy initialisation of kernels / cuBLAS); forward + backward only,
+        # so no parameter, optimizer or RNG state is touched
+        for net in self._nets():
+            for l in net.conv_layers():
+                if l.dirty:
+                    l.repack()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        before = set(k for k in vars(self) if k.startswith("loss_"))
+        graph = torch.cuda.CUDAGraph()
+        n0 = N.launch_count
+        with torch.cuda.graph(graph):
+            run()
+        self._launches[kind] = N.launch_count - n0 + 2      # + the Adam kernels launched outside the graph
+        names = [k for k in vars(self) if k.startswith("loss_")]
+        prefix = "loss_gen" if kind == "gen" else "loss_dis"
+        ent["losses"] = {k: getattr(self, k) for k in names if k.startswith(prefix) or (kind == "gen" and k.startswith("loss_idt"))}
+        ent["cycle"] = self._last_cycle
+        ent["graph"] = graph
+        return ent
 
     # ------------------------------------------------------------------------------------------ inference
     def forward(self, x_a, x_b):
@@ -325,6 +492,9 @@ class aclgan_Trainer(nn.Module):
             self.dis_scheduler.step()
         if self.gen_scheduler is not None:
             self.gen_scheduler.step()
+        if self._ready:         # the fused Adam kernel reads lr from device memory (outside any captured graph)
+            self._adam_gen["hyper"][0:1].fill_(self.gen_opt.param_groups[0]["lr"])
+            self._adam_dis["hyper"][0:1].fill_(self.dis_opt.param_groups[0]["lr"])
 
     def resume(self, checkpoint_dir, hyperparameters):
         last = get_model_list(checkpoint_dir, "gen")
@@ -341,10 +511,12 @@ class aclgan_Trainer(nn.Module):
         self.gen_opt.load_state_dict(sd["gen"])
         self.dis_scheduler = get_scheduler(self.dis_opt, hyperparameters, iterations)
         self.gen_scheduler = get_scheduler(self.gen_opt, hyperparameters, iterations)
+        self._ready = False      # optimizer state tensors were replaced: rebuild the device tables lazily
         print("Resume from iteration %d" % iterations)
         return iterations
 
     def save(self, snapshot_dir, iterations):
+        self._sync_opt_state()
         gen_name = os.path.join(snapshot_dir, "gen_%08d.pt" % (iterations + 1))
         dis_name = os.path.join(snapshot_dir, "dis_%08d.pt" % (iterations + 1))
         opt_name = os.path.join(snapshot_dir, "optimizer.pt")

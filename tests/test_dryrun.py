@@ -17,7 +17,8 @@ import trainer as T
 
 LAUNCHERS = ["aclgan_igemm_launch", "aclgan_wgrad_launch", "aclgan_pack_img", "aclgan_norm_stats",
              "aclgan_norm_finalize", "aclgan_norm_apply", "aclgan_block_bwd_reduce", "aclgan_block_bwd_apply",
-             "aclgan_norm_bwd_finalize", "aclgan_img_grad_pack", "aclgan_img_grad_unpack", "aclgan_pack_weight"]
+             "aclgan_norm_bwd_finalize", "aclgan_img_grad_pack", "aclgan_img_grad_unpack", "aclgan_pack_weight",
+             "aclgan_adam_step", "aclgan_adam_advance"]
 
 
 class _Stub:
@@ -73,6 +74,7 @@ def _cfg(name="male2female.yaml", tiny=True):
 def test_updates_dryrun(dry, cfgname, precision):
     cfg = _cfg(cfgname)
     cfg["precision"] = precision
+    cfg["cuda_graphs"] = 0
     torch.manual_seed(0)
     tr = T.aclgan_Trainer(copy.deepcopy(cfg))
     x_a = torch.rand(2, 3, 64, 64) * 2 - 1
@@ -93,6 +95,7 @@ def test_updates_dryrun(dry, cfgname, precision):
 def test_full_width_plans_dryrun(dry):
     """all layer geometries of the real (dim 64) networks at 64x64"""
     cfg = _cfg(tiny=False)
+    cfg["cuda_graphs"] = 0
     torch.manual_seed(0)
     tr = T.aclgan_Trainer(copy.deepcopy(cfg))
     x = torch.rand(1, 3, 64, 64) * 2 - 1

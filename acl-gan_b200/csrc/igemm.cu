@@ -15,22 +15,25 @@
 // Replaces: nn.Conv2d forward inside Conv2dBlock.forward (reference networks.py:363,366) incl. the
 // ReflectionPad2d gather (networks.py:319) and, for no-norm blocks, bias + ReLU/LeakyReLU/tanh
 // (networks.py:345-353,370); the same kernel computes conv data gradients (autograd of networks.py:366).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace aclgan {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 4;
 constexpr int kTileM = 128;
 constexpr int kABytes = kTileM * 128;          // 128 rows x 64 bf16
 constexpr int kBBytesMax = 256 * 128;          // up to 256 rows x 64 bf16
-constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kPipeBytes = kMaxStages * (kABytes + kBBytesMax);   // 192 KB ring: 4 stages (M=128) or 3 stages (M=256)
+constexpr int kSmemBytes = kPipeBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kThreads = 256;
 
 struct alignas(64) IgemmKParams {
     CUtensorMap a[2][ACLGAN_MAX_AVARIANTS];
     CUtensorMap b[2];
     int planes, nseg, block_n, n_tiles;
+    int m_sub;   // 128-pixel tiles per CTA work item (1 | 2): with 2, every weight (B) stage feeds two A tiles
     int box_x, box_y, box_z, tiles_x, tiles_y, tiles_z;
     int cchunks, num_taps;
     int flat, flat_w, flat_img;
@@ -154,12 +157,19 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmKParams& P, const uint
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmKParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-    uint64_t* full_bar = bars;                  // [kStages]
-    uint64_t* empty_bar = bars + kStages;       // [kStages]
-    uint64_t* tfull_bar = bars + 2 * kStages;   // [2]
-    uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPipeBytes);
+    uint64_t* full_bar = bars;                     // [kMaxStages]
+    uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
+    uint64_t* tfull_bar = bars + 2 * kMaxStages;   // [2]
+    uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+    const int m_sub = P.m_sub;
+    const int stage_bytes = m_sub * kABytes + kBBytesMax;
+    const int num_stages = kPipeBytes / stage_bytes;           // 4 or 3
+    // TMEM: one accumulator set = m_sub x col_stride columns; two sets (double buffering) when they fit in 512
+    const int col_stride = P.block_n < 32 ? 32 : P.block_n;
+    const int set_cols = m_sub * col_stride;
+    const int acc_sets = (2 * set_cols <= 512) ? 2 : 1;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -171,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         }
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
@@ -191,9 +201,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     const int m_tiles = P.tiles_x * P.tiles_y * P.tiles_z;
-    const int total_tiles = m_tiles * P.n_tiles;
+    const int m_items = (m_tiles + m_sub - 1) / m_sub;
+    const int total_tiles = m_items * P.n_tiles;               // CTA work items
     const int k_iters = P.nseg * P.num_taps * P.cchunks;
-    const uint32_t stage_tx = kABytes + P.block_n * 128;
+    const uint32_t stage_tx = m_sub * kABytes + P.block_n * 128;
 
     if (warp == 0 && lane == 0) {
         // ---------------- TMA producer ----------------
@@ -201,27 +212,31 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % P.n_tiles;
-            int mt = tile / P.n_tiles;
-            const int tx = mt % P.tiles_x;
-            mt /= P.tiles_x;
-            const int ty = mt % P.tiles_y;
-            const int tz = mt / P.tiles_y;
-            const int x0 = tx * P.box_x, y0 = ty * P.box_y, z0 = tz * P.box_z;
+            const int mi = tile / P.n_tiles;
+            int x0[2], y0[2], z0[2];
+            for (int s = 0; s < m_sub; ++s) {
+                int mt = mi * m_sub + s;       // a tile index past the end decodes to z >= N: zero-filled, never stored
+                x0[s] = (mt % P.tiles_x) * P.box_x;
+                mt /= P.tiles_x;
+                y0[s] = (mt % P.tiles_y) * P.box_y;
+                z0[s] = (mt / P.tiles_y) * P.box_z;
+            }
             for (int seg = 0; seg < P.nseg; ++seg) {
                 const int pa = (seg == 2) ? 1 : 0;   // A plane: hi, hi, lo
                 const int pb = (seg == 1) ? 1 : 0;   // B plane: hi, lo, hi
                 for (int t = 0; t < P.num_taps; ++t) {
                     const CUtensorMap* am = &P.a[pa][P.tap_var[t]];
-                    const int ax = x0 + P.tap_dx[t], ay = y0 + P.tap_dy[t];
+                    const int dx = P.tap_dx[t], dy = P.tap_dy[t];
                     const int bk = P.tap_bk[t];
                     for (int cc = 0; cc < P.cchunks; ++cc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* sa = smem + stage * kStageBytes;
-                        uint8_t* sb = sa + kABytes;
+                        uint8_t* sa = smem + stage * stage_bytes;
+                        uint8_t* sb = sa + m_sub * kABytes;
                         mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-                        tma_load_4d(sa, am, &full_bar[stage], cc * 64, ax, ay, z0);
+                        for (int s = 0; s < m_sub; ++s)
+                            tma_load_4d(sa + s * kABytes, am, &full_bar[stage], cc * 64, x0[s] + dx, y0[s] + dy, z0[s]);
                         tma_load_2d(sb, &P.b[pb], &full_bar[stage], bk + cc * 64, nt * P.block_n);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -233,25 +248,27 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         uint32_t phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
+            const int acc = it % acc_sets;
+            const uint32_t acc_phase = (it / acc_sets) & 1;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * 256;
+            const uint32_t d_tmem = tmem_base + acc * set_cols;
             for (int k = 0; k < k_iters; ++k) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-                const uint32_t sb = sa + kABytes;
-                const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+                const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                const uint32_t sb = sa + m_sub * kABytes;
                 const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+                for (int s = 0; s < m_sub; ++s) {
+                    const uint64_t da = make_smem_desc_sw128(sa + s * kABytes, 16, 1024);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    // +32 bytes (= 16 bf16 of K) inside the 128B swizzle row -> +2 in the >>4 encoded address
-                    umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        // +32 bytes (= 16 bf16 of K) inside the 128B swizzle row -> +2 in the >>4 encoded address
+                        umma_bf16(d_tmem + s * col_stride, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(&empty_bar[stage]);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
             umma_commit(&tfull_bar[acc]);
         }
@@ -262,10 +279,15 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         const aclgan_out_spec& o = P.out;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
+            const int acc = it % acc_sets;
+            const uint32_t acc_phase = (it / acc_sets) & 1;
             const int nt = tile % P.n_tiles;
-            int mt = tile / P.n_tiles;
+            const int mi = tile / P.n_tiles;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+          for (int sub = 0; sub < m_sub; ++sub) {
+            int mt = mi * m_sub + sub;
+            const bool sub_ok = mt < m_tiles;      // odd tile count: the padding tile of the last work item
             const int tx = mt % P.tiles_x;
             mt /= P.tiles_x;
             const int ty = mt % P.tiles_y;
@@ -282,15 +304,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 y = ty * P.box_y + (row / P.box_x) % P.box_y;
                 z = tz * P.box_z + row / (P.box_x * P.box_y);
             }
-            const bool valid = (x < o.W) && (y < o.H) && (z < o.N);
+            const bool valid = sub_ok && (x < o.W) && (y < o.H) && (z < o.N);
             const int64_t pix0 = o.off + (int64_t)z * o.sn + (int64_t)y * o.sy + (int64_t)x * o.sx;
             int ys[3], xs[3];
             const int ny = mirror_coords(y, o.H, o.mirror, ys);
             const int nx = mirror_coords(x, o.W, o.mirror, xs);
 
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_row = tmem_base + acc * set_cols + sub * col_stride + ((uint32_t)(q * 32) << 16);
             const int n0 = nt * P.block_n;
             if (P.block_n >= 32) {
                 for (int c = 0; c < P.block_n; c += 32) {
@@ -305,6 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 tmem_ld_wait();
                 epilogue_chunk<16>(P, raw, n0, valid, pix0, ys, ny, xs, nx, y, x, z);
             }
+          }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -341,6 +362,15 @@ static int fill_kparams(const aclgan_igemm_plan* pl, IgemmKParams* kp) {
         kp->b[1] = kp->b[0];
     }
     kp->planes = pl->planes; kp->nseg = pl->nseg; kp->block_n = pl->block_n; kp->n_tiles = pl->n_tiles;
+    {
+        // two 128-pixel tiles per work item halve the weight-tile (B) traffic per FLOP; only worth it when
+        // enough work items remain to keep the SMs busy
+        const int m_tiles = pl->tiles_x * pl->tiles_y * pl->tiles_z;
+        const char* env = getenv("ACLGAN_IGEMM_MSUB");
+        int m_sub = (m_tiles * pl->n_tiles >= 2 * num_sms()) ? 2 : 1;
+        if (env != nullptr) m_sub = atoi(env) == 2 ? 2 : 1;
+        kp->m_sub = m_sub;
+    }
     kp->box_x = pl->box_x; kp->box_y = pl->box_y; kp->box_z = pl->box_z;
     kp->tiles_x = pl->tiles_x; kp->tiles_y = pl->tiles_y; kp->tiles_z = pl->tiles_z;
     kp->cchunks = pl->cchunks; kp->num_taps = pl->num_taps;
@@ -367,7 +397,7 @@ extern "C" int aclgan_igemm_launch(const aclgan_igemm_plan* plan, void* stream) 
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    const int total = plan->tiles_x * plan->tiles_y * plan->tiles_z * plan->n_tiles;
+    const int total = ((plan->tiles_x * plan->tiles_y * plan->tiles_z + kp.m_sub - 1) / kp.m_sub) * plan->n_tiles;
     if (total <= 0) return ACLGAN_OK;
     const int grid = total < num_sms() ? total : num_sms();
     igemm_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(kp);

@@ -209,10 +209,11 @@ class ConvLayer:
         base, s_co, s_ci, s_kh, s_kw = self.aff[self.layout]
         co, ci, kh, kw = self.weight.shape
         dw = self.dw()
+        off = dw.storage_offset() + base          # as_strided offsets are absolute within the arena storage
         if s_kw >= 0:
-            g = torch.as_strided(dw, (co, ci, kh, kw), (s_co, s_ci, s_kh, s_kw), base)
+            g = torch.as_strided(dw, (co, ci, kh, kw), (s_co, s_ci, s_kh, s_kw), off)
         else:
-            g = torch.as_strided(dw, (co, ci, kh, kw), (s_co, s_ci, s_kh, -s_kw), base + (kw - 1) * s_kw).flip(3)
+            g = torch.as_strided(dw, (co, ci, kh, kw), (s_co, s_ci, s_kh, -s_kw), off + (kw - 1) * s_kw).flip(3)
         return g, self.db()
 
 
@@ -431,11 +432,12 @@ class Engine:
                 if norm == N.NORM_ADAIN:
                     dwb = torch.empty((2, n, cout), dtype=torch.float32, device=self.device)
                     f.w, f.dw, f.db = adain[0].data_ptr(), dwb[0].data_ptr(), dwb[1].data_ptr()
-                    adain[2](dwb[0], dwb[1])
                 elif norm == N.NORM_LN:
                     f.w, f.dw, f.db = ln[0].data_ptr(), ln[2].data_ptr(), ln[3].data_ptr()
                 f.ca, f.cb, f.cc = (cf[i].data_ptr() for i in range(3))
                 N.check(L.aclgan_norm_bwd_finalize(C.byref(f), _sp()), "norm_bwd_finalize")
+                if norm == N.NORM_ADAIN:
+                    adain[2](dwb[0], dwb[1])        # after the launch: the sink may enqueue copies of dw / db
                 b.ca, b.cb, b.cc = (cf[i].data_ptr() for i in range(3))
             N.check(L.aclgan_block_bwd_apply(C.byref(b), _sp()), "block_bwd_apply")
             if train_w:

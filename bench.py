@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after warm-up run ONE step-pair between cudaProfilerStart/Stop and exit (for ncu "
+                         "--profile-from-start off launch lists); prints no bench line")
     return ap.parse_args()
 
 
@@ -239,6 +242,13 @@ def run_b200(args):
     for _ in range(max(3, args.warmup)):
         step_resident()
     barrier()
+    if args.profile_step:
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print("profiled one step-pair (%s kernels of libaclgan_b200.so per step-pair)" % tr.launches_per_step_pair)
+        return
     n0 = N.launch_count
     sampler = ClockSampler(local)
     if rank == 0:

@@ -26,8 +26,10 @@ FWD_CASES = [
 ]
 
 
+@pytest.mark.parametrize("msub", [1, 2])
 @pytest.mark.parametrize("cin,cout,k,s,pad,window,n,h,w,planes", FWD_CASES)
-def test_conv_fwd(cin, cout, k, s, pad, window, n, h, w, planes):
+def test_conv_fwd(monkeypatch, msub, cin, cout, k, s, pad, window, n, h, w, planes):
+    monkeypatch.setenv("ACLGAN_IGEMM_MSUB", str(msub))     # 128- vs 256-pixel work items of the igemm kernel
     L = N.lib()
     torch.manual_seed(0)
     x = torch.randn(n, cin, h, w, device="cuda")
@@ -85,8 +87,10 @@ DGRAD_CASES = [
 ]
 
 
+@pytest.mark.parametrize("msub", [1, 2])
 @pytest.mark.parametrize("cin,cout,k,s,pad,n,ho,wo,planes", DGRAD_CASES)
-def test_conv_dgrad(cin, cout, k, s, pad, n, ho, wo, planes):
+def test_conv_dgrad(monkeypatch, msub, cin, cout, k, s, pad, n, ho, wo, planes):
+    monkeypatch.setenv("ACLGAN_IGEMM_MSUB", str(msub))
     L = N.lib()
     torch.manual_seed(1)
     dy = torch.randn(n, cout, ho, wo, device="cuda")
@@ -119,8 +123,10 @@ def test_conv_dgrad(cin, cout, k, s, pad, n, ho, wo, planes):
     assert err < (2e-5 if planes == 1 else 5e-5), err  # fp32 accumulation over K up to 6400
 
 
-def test_conv_fwd_throughput_report(capsys):
+@pytest.mark.parametrize("msub", [1, 2])
+def test_conv_fwd_throughput_report(capsys, monkeypatch, msub):
     """not an assertion on speed - prints the achieved TFLOP/s of the dominant 3x3 256->256 layer"""
+    monkeypatch.setenv("ACLGAN_IGEMM_MSUB", str(msub))
     L = N.lib()
     torch.manual_seed(0)
     n, c, h = 8, 256, 64
@@ -145,7 +151,7 @@ def test_conv_fwd_throughput_report(capsys):
     ms = e0.elapsed_time(e1) / iters
     flops = 2.0 * n * h * h * c * c * 9
     with capsys.disabled():
-        print("\n[igemm 3x3 256->256 bs8 64x64] %.3f ms  %.1f TFLOP/s" % (ms, flops / ms / 1e9))
+        print("\n[igemm 3x3 256->256 bs8 64x64 msub=%d] %.3f ms  %.1f TFLOP/s" % (msub, ms, flops / ms / 1e9))
 
 
 WGRAD_CASES = [
@@ -160,6 +166,11 @@ WGRAD_CASES = [
     (6, 64, 4, 2, 1, 1, 2, 32, 32, 1),
     (64, 4, 7, 1, 3, 2, 1, 32, 32, 1),
     (128, 64, 4, 2, 1, 0, 3, 4, 4, 1),
+    (64, 4, 7, 1, 3, 2, 2, 8, 8, 1),
+    (64, 4, 7, 1, 3, 2, 2, 8, 8, 2),
+    (64, 128, 4, 2, 1, 0, 1, 32, 32, 2),
+    (16, 32, 4, 2, 1, 0, 2, 32, 32, 2),
+    (64, 128, 4, 2, 1, 0, 1, 16, 16, 1),
 ]
 
 

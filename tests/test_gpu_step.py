@@ -77,14 +77,17 @@ def test_step_vs_golden(golden_dir, case, precision):
         assert e < ltol, (k, e)
     if precision == "fp32x3":
         gg32, gg64 = g32["dis_grads"], g64["dis_grads"]
+        bad = []
         for i, key in enumerate(gg64["keys"]):
             n, k = key.split(".", 1)
             gr = dict(getattr(tr, n).named_parameters())[k].grad.double().cpu().reshape(-1)
             ref64, ref32 = float(gg64["norm"][i]), float(gg32["norm"][i])
             allow = max(1e-3, 2 * abs(ref32 - ref64) / ref64)
-            assert abs(float(gr.norm()) - ref64) / ref64 < allow, ("dis grad norm", key, float(gr.norm()), ref64)
             hd = gg64["head"][i][:min(8, gr.numel())]
-            assert float((gr[:hd.numel()] - hd).norm()) <= allow * max(float(hd.norm()), 1e-3 * ref64) + 1e-12, ("head", key)
+            if not (abs(float(gr.norm()) - ref64) / ref64 < allow and
+                    float((gr[:hd.numel()] - hd).norm()) <= allow * max(float(hd.norm()), 1e-3 * ref64) + 1e-12):
+                bad.append((key, "%.4e" % float(gr.norm()), "%.4e" % ref64))
+        assert not bad, ("dis grads", bad)
         ps = g32["dis_params_after"]
         for i, key in enumerate(ps["keys"]):
             n, k = key.split(".", 1)
@@ -106,7 +109,7 @@ def test_step_vs_golden(golden_dir, case, precision):
     assert _rel(r["o_rec_a"].t[:, :3], g32["gen_forward"]["x_A_recon"]) < ltol
     if precision == "fp32x3":
         gg32, gg64 = g32["gen_grads"], g64["gen_grads"]
-        worst = 0.0
+        worst, bad = 0.0, []
         for i, key in enumerate(gg64["keys"]):
             n, k = key.split(".", 1)
             ref64, ref32 = float(gg64["norm"][i]), float(gg32["norm"][i])
@@ -116,7 +119,9 @@ def test_step_vs_golden(golden_dir, case, precision):
             allow = max(1e-3, 2 * abs(ref32 - ref64) / ref64)
             e = abs(float(gr.norm()) - ref64) / ref64
             worst = max(worst, e / allow)
-            assert e < allow, ("gen grad norm", key, float(gr.norm()), ref64, ref32)
+            if not e < allow:
+                bad.append((key, "%.4e" % float(gr.norm()), "%.4e" % ref64, "%.4e" % ref32))
+        assert not bad, ("gen grads", bad[:40])
         report.append(("gen grad worst/allow", worst))
     print("\n[step parity %s %s] " % (case, precision) + "  ".join("%s=%.2e" % kv for kv in report))
 
@@ -162,3 +167,42 @@ def test_gradients_vs_live_oracle(golden_dir, precision):
     worst.sort(reverse=True)
     print("\n[grad parity vs live oracle] worst 5:", [(k, "%.2e" % a, "%.2e" % b) for _, k, a, b in worst[:5]])
     assert worst[0][0] < 1.0, worst[:5]
+
+
+@pytest.mark.parametrize("precision", ["fp32x3"])
+def test_dis_gradients_vs_oracle(golden_dir, precision):
+    """one discriminator, one image: every parameter gradient vs the oracle's autograd (isolates the D path)"""
+    import engine as E
+    g32 = _load(golden_dir, "tiny", "fp32")
+    tr, cfg = _build(g32, precision)
+    tr._setup()
+    x_a, _, _ = _inputs(g32)
+    errs = {}
+    for net_name in ("dis_A", "dis_2"):
+        D = getattr(tr, net_name)
+        tr.dis_arena.zero_()
+        tape = E.Tape()
+        xa = E.ImgT(x_a.cuda())
+        if net_name == "dis_2":
+            other = E.ImgT((x_a * 0.5).cuda(), requires_grad=True)
+            outs = D.dis(tape, xa, other)
+        else:
+            other = None
+            xa.requires_grad = True
+            outs = D.dis(tape, xa)
+        tr._lsgan(outs, 1.0, 1.0)
+        tape.backward()
+        torch.cuda.synchronize()
+        p = {k: v.detach().cpu().double().requires_grad_(True) for k, v in D.state_dict().items()}
+        xin = x_a.double() if other is None else torch.cat((x_a, x_a * 0.5), 1).double()
+        xin.requires_grad_(True)
+        loss = O.lsgan(O.dis_forward(xin, p, g32["cfg"]["dis"]), 1.0)
+        loss.backward()
+        for k, q in D.named_parameters():
+            errs[net_name + "." + k] = _rel(q.grad, p[k].grad)
+        img_g = xa.grad if other is None else other.grad
+        ref_g = xin.grad if other is None else xin.grad[:, 3:]
+        errs[net_name + ".image"] = _rel(img_g, ref_g)
+    bad = {k: "%.2e" % v for k, v in errs.items() if v > 1e-3}
+    print("\n[dis grads vs oracle] max %.2e" % max(errs.values()))
+    assert not bad, bad

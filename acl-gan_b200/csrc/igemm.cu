@@ -34,6 +34,7 @@ struct alignas(64) IgemmKParams {
     CUtensorMap b[2];
     int planes, nseg, block_n, n_tiles;
     int m_sub;   // 128-pixel tiles per CTA work item (1 | 2): with 2, every weight (B) stage feeds two A tiles
+    int debug;   // perf triage only (env ACLGAN_IGEMM_DEBUG): 1 = MMA without TMA traffic, 2 = TMA without MMA
     int box_x, box_y, box_z, tiles_x, tiles_y, tiles_z;
     int cchunks, num_taps;
     int flat, flat_w, flat_img;
@@ -232,10 +233,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * stage_bytes;
                         uint8_t* sb = sa + m_sub * kABytes;
-                        mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-                        for (int s = 0; s < m_sub; ++s)
-                            tma_load_4d(sa + s * kABytes, am, &full_bar[stage], cc * 64, x0[s] + dx, y0[s] + dy, z0[s]);
-                        tma_load_2d(sb, &P.b[pb], &full_bar[stage], bk + cc * 64, nt * P.block_n);
+                        if (P.debug == 1) {
+                            mbar_arrive(&full_bar[stage]);
+                        } else {
+                            mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+                            for (int s = 0; s < m_sub; ++s)
+                                tma_load_4d(sa + s * kABytes, am, &full_bar[stage], cc * 64, x0[s] + dx, y0[s] + dy, z0[s]);
+                            tma_load_2d(sb, &P.b[pb], &full_bar[stage], bk + cc * 64, nt * P.block_n);
+                        }
                         if (++stage == num_stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -259,6 +264,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                 const uint32_t sb = sa + m_sub * kABytes;
                 const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+                if (P.debug == 2) {
+                    mbar_arrive(&empty_bar[stage]);
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 for (int s = 0; s < m_sub; ++s) {
                     const uint64_t da = make_smem_desc_sw128(sa + s * kABytes, 16, 1024);
 #pragma unroll
@@ -270,7 +280,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 umma_commit(&empty_bar[stage]);
                 if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&tfull_bar[acc]);
+            if (P.debug == 2) mbar_arrive(&tfull_bar[acc]);
+            else umma_commit(&tfull_bar[acc]);
         }
     } else if (warp >= 4) {
         // ---------------- epilogue ----------------
@@ -370,6 +381,8 @@ static int fill_kparams(const aclgan_igemm_plan* pl, IgemmKParams* kp) {
         int m_sub = (m_tiles * pl->n_tiles >= 2 * num_sms()) ? 2 : 1;
         if (env != nullptr) m_sub = atoi(env) == 2 ? 2 : 1;
         kp->m_sub = m_sub;
+        const char* dbg = getenv("ACLGAN_IGEMM_DEBUG");
+        kp->debug = dbg != nullptr ? atoi(dbg) : 0;
     }
     kp->box_x = pl->box_x; kp->box_y = pl->box_y; kp->box_z = pl->box_z;
     kp->tiles_x = pl->tiles_x; kp->tiles_y = pl->tiles_y; kp->tiles_z = pl->tiles_z;

@@ -202,6 +202,8 @@ def _declare(L):
                                          C.POINTER(WgradPlan)]
     L.aclgan_wgrad_layout.argtypes = [C.POINTER(ConvDesc)]
     L.aclgan_wgrad_launch.argtypes = [C.POINTER(WgradPlan), C.c_void_p]
+    L.aclgan_igemm_launch_repeat.argtypes = [C.POINTER(IgemmPlan), C.c_int, C.c_void_p]
+    L.aclgan_wgrad_launch_repeat.argtypes = [C.POINTER(WgradPlan), C.c_int, C.c_void_p]
     L.aclgan_pack_img.argtypes = [C.POINTER(PackImgArgs), C.c_void_p]
     L.aclgan_norm_stats.argtypes = [C.POINTER(Tensor4), C.c_uint64, C.c_void_p]
     L.aclgan_norm_finalize.argtypes = [C.POINTER(NormFinalizeArgs), C.c_void_p]

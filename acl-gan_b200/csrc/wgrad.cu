@@ -174,7 +174,13 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
 
 using namespace aclgan;
 
+extern "C" int aclgan_wgrad_launch_repeat(const aclgan_wgrad_plan* pl, int repeat, void* stream);
+
 extern "C" int aclgan_wgrad_launch(const aclgan_wgrad_plan* pl, void* stream) {
+    return aclgan_wgrad_launch_repeat(pl, 1, stream);
+}
+
+extern "C" int aclgan_wgrad_launch_repeat(const aclgan_wgrad_plan* pl, int repeat, void* stream) {
     static bool attr_set = false;
     if (pl->planes < 1 || pl->planes > 2 || (pl->nseg != 1 && pl->nseg != 3)) return ACLGAN_ERR_SHAPE;
     if (pl->m_chunks < 1 || pl->m_chunks > 2 || pl->n_chunks < 1 || pl->n_chunks > 4) return ACLGAN_ERR_SHAPE;
@@ -211,6 +217,6 @@ extern "C" int aclgan_wgrad_launch(const aclgan_wgrad_plan* pl, void* stream) {
         attr_set = true;
     }
     const int grid = pl->num_taps * pl->m_tiles * pl->n_tiles * pl->ksplit;
-    wgrad_kernel<<<grid, kWThreads, kWSmemBytes, (cudaStream_t)stream>>>(kp);
+    for (int i = 0; i < repeat; ++i) wgrad_kernel<<<grid, kWThreads, kWSmemBytes, (cudaStream_t)stream>>>(kp);
     return (int)cudaGetLastError();
 }

@@ -143,6 +143,9 @@ int aclgan_wgrad_layout(const aclgan_conv_desc* cd);
 /* launches (networks.py:363,366 Conv2d forward; autograd of it for dgrad / wgrad) */
 int aclgan_igemm_launch(const aclgan_igemm_plan* plan, void* stream);
 int aclgan_wgrad_launch(const aclgan_wgrad_plan* plan, void* stream);
+/* same plan launched `repeat` times back to back (tensor maps encoded once): device-side kernel timing */
+int aclgan_igemm_launch_repeat(const aclgan_igemm_plan* plan, int repeat, void* stream);
+int aclgan_wgrad_launch_repeat(const aclgan_wgrad_plan* plan, int repeat, void* stream);
 
 
 /* ================= element-wise / reduction kernels around the convolutions ================= */

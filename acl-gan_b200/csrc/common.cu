@@ -53,9 +53,11 @@ int num_sms() {
     static int n = 0;
     if (n == 0) {
         int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+            cudaGetLastError();      // no device (host-only plan building): assume a B200
+            n = 148;
+        }
     }
     return n;
 }

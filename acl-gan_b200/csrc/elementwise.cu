@@ -67,6 +67,16 @@ __device__ __forceinline__ F8 load8_planes(const uint64_t (&pl)[2], int planes, 
     return r;
 }
 
+// 8 consecutive fp32 per-channel coefficients (32-byte aligned: channel groups start at multiples of 8)
+__device__ __forceinline__ F8 load_coef8(uint64_t base, int64_t idx) {
+    F8 r;
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+
 __device__ __forceinline__ int reflect_idx(int i, int L) {
     if (i < 0) i = -i;
     if (i >= L) i = 2 * (L - 1) - i;
@@ -119,7 +129,7 @@ __global__ void pack_img_kernel(aclgan_pack_img_args a) {
 // ------------------------------------------------------------------------------------------ norm_stats
 // CTA = 256 threads = (C/8 channel groups) x (pixel lanes); fp32 partials per thread, CTA reduce, fp64 atomics
 constexpr int kStatThreads = 256;
-constexpr int kStatIters = 32;
+constexpr int kStatIters = 8;      // pixels per thread: small ranges -> many CTAs (these kernels are latency / HBM bound)
 
 __global__ void __launch_bounds__(kStatThreads) norm_stats_kernel(aclgan_tensor4 y, double* sums) {
     extern __shared__ float red[];  // [lanes][C][2]
@@ -133,12 +143,16 @@ __global__ void __launch_bounds__(kStatThreads) norm_stats_kernel(aclgan_tensor4
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
     if (lane < lanes) {
         const int64_t p0 = (int64_t)blockIdx.x * lanes * kStatIters + lane;
-        for (int it = 0; it < kStatIters; ++it) {
-            const int64_t pix = p0 + (int64_t)it * lanes;
-            if (pix >= hw) break;
-            const F8 v = load8(y.ptr, y.kind, ((int64_t)n * hw + pix) * y.c + g * 8);
+        F8 buf[kStatIters];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s[i] += v.v[i]; q[i] += v.v[i] * v.v[i]; }
+        for (int it = 0; it < kStatIters; ++it) {       // all loads first (memory-level parallelism), then the math
+            const int64_t pix = p0 + (int64_t)it * lanes;
+            buf[it] = pix < hw ? load8(y.ptr, y.kind, ((int64_t)n * hw + pix) * y.c + g * 8) : f8_zero();
+        }
+#pragma unroll
+        for (int it = 0; it < kStatIters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s[i] += buf[it].v[i]; q[i] += buf[it].v[i] * buf[it].v[i]; }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -219,42 +233,64 @@ __global__ void norm_finalize_kernel(aclgan_norm_finalize_args a) {
 }
 
 // ------------------------------------------------------------------------------------------ norm_apply
-__global__ void norm_apply_kernel(aclgan_apply_args a) {
+constexpr int kApplyPix = 4;     // padded pixels per thread (same image, same channel group -> coefficients stay in registers)
+
+__global__ void __launch_bounds__(256) norm_apply_kernel(aclgan_apply_args a) {
     const int u = a.upsample, p = a.dst.pad;
     const int hd = a.y.h * u, wd = a.y.w * u, hp = hd + 2 * p, wp = wd + 2 * p;
     const int cg = a.y.c / 8;
-    const int64_t total = (int64_t)a.y.n * hp * wp * cg;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int g = (int)(t % cg);
-    int64_t r = t / cg;
-    const int X = (int)(r % wp); r /= wp;
-    const int Y = (int)(r % hp);
-    const int n = (int)(r / hp);
-    const int y = reflect_idx(Y - p, hd) / u, x = reflect_idx(X - p, wd) / u;
-    F8 v = load8(a.y.ptr, a.y.kind, (((int64_t)n * a.y.h + y) * a.y.w + x) * a.y.c + g * 8);
+    const int lanes = 256 / cg;
+    const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+    const int n = blockIdx.y;
+    if (lane >= lanes) return;
+    const int64_t npix = (int64_t)hp * wp;
+    F8 sc, sf;
     if (a.scale != 0) {
-        const float* sc = reinterpret_cast<const float*>(a.scale) + (int64_t)n * a.y.c + g * 8;
-        const float* sf = reinterpret_cast<const float*>(a.shift) + (int64_t)n * a.y.c + g * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v.v[i] = v.v[i] * __ldg(sc + i) + __ldg(sf + i);
+        sc = load_coef8(a.scale, (int64_t)n * a.y.c + g * 8);
+        sf = load_coef8(a.shift, (int64_t)n * a.y.c + g * 8);
     }
+    const int64_t p0 = (int64_t)blockIdx.x * lanes * kApplyPix + lane;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v.v[i] = act_fn(v.v[i], a.act, a.slope);
-    if (a.has_res) {
-        const int rp = a.res.pad, rwp = a.res.w + 2 * rp, rhp = a.res.h + 2 * rp;
-        const F8 rr = load8_planes(a.res.data, a.res.planes,
-                                   (((int64_t)n * rhp + y + rp) * rwp + x + rp) * a.res.c + g * 8);
+    for (int j = 0; j < kApplyPix; ++j) {
+        const int64_t pix = p0 + (int64_t)j * lanes;
+        if (pix >= npix) break;
+        const int Y = (int)(pix / wp), X = (int)(pix % wp);
+        const int y = reflect_idx(Y - p, hd) / u, x = reflect_idx(X - p, wd) / u;
+        F8 v = load8(a.y.ptr, a.y.kind, (((int64_t)n * a.y.h + y) * a.y.w + x) * a.y.c + g * 8);
+        if (a.scale != 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v.v[i] += rr.v[i];
+            for (int i = 0; i < 8; ++i) v.v[i] = v.v[i] * sc.v[i] + sf.v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v.v[i] = act_fn(v.v[i], a.act, a.slope);
+        if (a.has_res) {
+            const int rp = a.res.pad, rwp = a.res.w + 2 * rp, rhp = a.res.h + 2 * rp;
+            const F8 rr = load8_planes(a.res.data, a.res.planes,
+                                       (((int64_t)n * rhp + y + rp) * rwp + x + rp) * a.res.c + g * 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v.v[i] += rr.v[i];
+        }
+        store8_planes(a.dst.data, a.dst.planes, ((int64_t)n * npix + pix) * a.dst.c + g * 8, v);
     }
-    store8_planes(a.dst.data, a.dst.planes, (((int64_t)n * hp + Y) * wp + X) * a.dst.c + g * 8, v);
 }
 
 // ------------------------------------------------------------------------------------------ block backward
 // gradient w.r.t. the logical block output at (n, y, x), channel group g, times the activation derivative;
 // also returns yhat when the block has a norm
-__device__ __forceinline__ void block_dz(const aclgan_block_bwd_args& a, int n, int y, int x, int g, F8& dz, F8& yhat) {
+struct BwdCoef {
+    F8 scale, shift, mean, inv;
+};
+
+__device__ __forceinline__ BwdCoef load_bwd_coef(const aclgan_block_bwd_args& a, int n, int g) {
+    BwdCoef c;
+    const int64_t i = (int64_t)n * a.c + g * 8;
+    if (a.mask_mode == ACLGAN_MASK_FROM_Z) { c.scale = load_coef8(a.scale, i); c.shift = load_coef8(a.shift, i); }
+    if (a.norm) { c.mean = load_coef8(a.mean, i); c.inv = load_coef8(a.inv, i); }
+    return c;
+}
+
+__device__ __forceinline__ void block_dz(const aclgan_block_bwd_args& a, const BwdCoef& cf, int n, int y, int x, int g,
+                                         F8& dz, F8& yhat) {
     F8 acc = f8_zero();
     if (a.gp != 0) {
         const int u = a.upsample, p = a.gp_pad;
@@ -284,11 +320,9 @@ __device__ __forceinline__ void block_dz(const aclgan_block_bwd_args& a, int n, 
     if (a.mask_mode == ACLGAN_MASK_FROM_Z || a.norm)
         yv = load8(a.y.ptr, a.y.kind, (((int64_t)n * a.h + y) * a.w + x) * a.c + g * 8);
     if (a.mask_mode == ACLGAN_MASK_FROM_Z) {
-        const float* sc = reinterpret_cast<const float*>(a.scale) + (int64_t)n * a.c + g * 8;
-        const float* sf = reinterpret_cast<const float*>(a.shift) + (int64_t)n * a.c + g * 8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float z = yv.v[i] * __ldg(sc + i) + __ldg(sf + i);
+            const float z = yv.v[i] * cf.scale.v[i] + cf.shift.v[i];
             if (!(z > 0.f)) acc.v[i] *= a.slope;
         }
     } else if (a.mask_mode == ACLGAN_MASK_FROM_OUT) {
@@ -300,10 +334,8 @@ __device__ __forceinline__ void block_dz(const aclgan_block_bwd_args& a, int n, 
     }
     dz = acc;
     if (a.norm) {
-        const float* mu = reinterpret_cast<const float*>(a.mean) + (int64_t)n * a.c + g * 8;
-        const float* iv = reinterpret_cast<const float*>(a.inv) + (int64_t)n * a.c + g * 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) yhat.v[i] = (yv.v[i] - __ldg(mu + i)) * __ldg(iv + i);
+        for (int i = 0; i < 8; ++i) yhat.v[i] = (yv.v[i] - cf.mean.v[i]) * cf.inv.v[i];
     }
 }
 
@@ -318,12 +350,14 @@ __global__ void __launch_bounds__(kStatThreads) block_bwd_reduce_kernel(aclgan_b
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
     if (lane < lanes) {
+        const BwdCoef cf = load_bwd_coef(a, n, g);
         const int64_t p0 = (int64_t)blockIdx.x * lanes * kStatIters + lane;
+#pragma unroll 4
         for (int it = 0; it < kStatIters; ++it) {
             const int64_t pix = p0 + (int64_t)it * lanes;
             if (pix >= hw) break;
             F8 dz, yh = f8_zero();
-            block_dz(a, n, (int)(pix / a.w), (int)(pix % a.w), g, dz, yh);
+            block_dz(a, cf, n, (int)(pix / a.w), (int)(pix % a.w), g, dz, yh);
 #pragma unroll
             for (int i = 0; i < 8; ++i) { s[i] += dz.v[i]; q[i] += dz.v[i] * yh.v[i]; }
         }
@@ -343,33 +377,39 @@ __global__ void __launch_bounds__(kStatThreads) block_bwd_reduce_kernel(aclgan_b
     }
 }
 
-__global__ void block_bwd_apply_kernel(aclgan_block_bwd_args a) {
+__global__ void __launch_bounds__(256) block_bwd_apply_kernel(aclgan_block_bwd_args a) {
     const int pz = a.dy.pad, hz = a.h + 2 * pz, wz = a.w + 2 * pz;
     const int cg = a.c / 8;
-    const int64_t total = (int64_t)a.n * hz * wz * cg;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int g = (int)(t % cg);
-    int64_t r = t / cg;
-    const int X = (int)(r % wz); r /= wz;
-    const int Y = (int)(r % hz);
-    const int n = (int)(r / hz);
-    const int y = Y - pz, x = X - pz;
-    F8 out = f8_zero();
-    if (y >= 0 && y < a.h && x >= 0 && x < a.w) {
-        F8 dz, yh = f8_zero();
-        block_dz(a, n, y, x, g, dz, yh);
-        if (a.norm) {
-            const float* ca = reinterpret_cast<const float*>(a.ca) + (int64_t)n * a.c + g * 8;
-            const float* cb = reinterpret_cast<const float*>(a.cb) + (int64_t)n * a.c + g * 8;
-            const float* cc = reinterpret_cast<const float*>(a.cc) + (int64_t)n * a.c + g * 8;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) out.v[i] = __ldg(ca + i) * dz.v[i] + __ldg(cb + i) * yh.v[i] + __ldg(cc + i);
-        } else {
-            out = dz;
-        }
+    const int lanes = 256 / cg;
+    const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+    const int n = blockIdx.y;
+    if (lane >= lanes) return;
+    const int64_t npix = (int64_t)hz * wz;
+    const BwdCoef cf = load_bwd_coef(a, n, g);
+    F8 ca, cb, cc;
+    if (a.norm) {
+        const int64_t ci = (int64_t)n * a.c + g * 8;
+        ca = load_coef8(a.ca, ci); cb = load_coef8(a.cb, ci); cc = load_coef8(a.cc, ci);
     }
-    store8_planes(a.dy.data, a.dy.planes, t * 8, out);
+    const int64_t p0 = (int64_t)blockIdx.x * lanes * kApplyPix + lane;
+#pragma unroll
+    for (int j = 0; j < kApplyPix; ++j) {
+        const int64_t pix = p0 + (int64_t)j * lanes;
+        if (pix >= npix) break;
+        const int y = (int)(pix / wz) - pz, x = (int)(pix % wz) - pz;
+        F8 out = f8_zero();
+        if (y >= 0 && y < a.h && x >= 0 && x < a.w) {
+            F8 dz, yh = f8_zero();
+            block_dz(a, cf, n, y, x, g, dz, yh);
+            if (a.norm) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) out.v[i] = ca.v[i] * dz.v[i] + cb.v[i] * yh.v[i] + cc.v[i];
+            } else {
+                out = dz;
+            }
+        }
+        store8_planes(a.dy.data, a.dy.planes, ((int64_t)n * npix + pix) * a.c + g * 8, out);
+    }
 }
 
 __global__ void norm_bwd_finalize_kernel(aclgan_norm_bwd_finalize_args a) {
@@ -536,9 +576,12 @@ extern "C" int aclgan_norm_finalize(const aclgan_norm_finalize_args* a, void* st
 extern "C" int aclgan_norm_apply(const aclgan_apply_args* a, void* stream) {
     if (a->y.c % 8 || a->dst.c != a->y.c || (a->upsample != 1 && a->upsample != 2)) return ACLGAN_ERR_SHAPE;
     if (a->has_res && (a->res.c != a->y.c || a->res.h != a->y.h || a->res.w != a->y.w)) return ACLGAN_ERR_SHAPE;
+    if (check_cg(a->y.c)) return ACLGAN_ERR_SHAPE;
     const int u = a->upsample, p = a->dst.pad;
-    const int64_t total = (int64_t)a->y.n * (a->y.h * u + 2 * p) * (a->y.w * u + 2 * p) * (a->y.c / 8);
-    norm_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*a);
+    const int64_t npix = (int64_t)(a->y.h * u + 2 * p) * (a->y.w * u + 2 * p);
+    const int lanes = 256 / (a->y.c / 8);
+    dim3 grid(grid_for(npix, lanes * kApplyPix), a->y.n);
+    norm_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
 }
 
@@ -553,9 +596,11 @@ extern "C" int aclgan_block_bwd_reduce(const aclgan_block_bwd_args* a, void* str
 }
 
 extern "C" int aclgan_block_bwd_apply(const aclgan_block_bwd_args* a, void* stream) {
-    if (a->c % 8 || a->dy.c != a->c) return ACLGAN_ERR_SHAPE;
-    const int64_t total = (int64_t)a->n * (a->h + 2 * a->dy.pad) * (a->w + 2 * a->dy.pad) * (a->c / 8);
-    block_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*a);
+    if (check_cg(a->c) || a->dy.c != a->c) return ACLGAN_ERR_SHAPE;
+    const int64_t npix = (int64_t)(a->h + 2 * a->dy.pad) * (a->w + 2 * a->dy.pad);
+    const int lanes = 256 / (a->c / 8);
+    dim3 grid(grid_for(npix, lanes * kApplyPix), a->n);
+    block_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
 }
 

@@ -440,6 +440,190 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
 }
 
+// =====================================================================================================================
+// CTA-pair variant (cta_group::2): two CTAs of a cluster (one TPC) compute a 256-pixel x block_n tile.  Each CTA stages
+// its own 128-pixel A tile and HALF of the weight tile; the leader's single thread issues UMMA M=256, which reads A / B
+// from both shared memories and writes each CTA's 128 accumulator rows into that CTA's TMEM.  Per SM and MMA this
+// halves the B bytes read from shared memory (64 B/clk instead of 96 B/clk for N=256) - the 1-CTA kernel above is
+// limited by exactly that operand bandwidth.  Synchronisation: TMA completions of both CTAs are counted on the leader's
+// full barrier; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs; both epilogues report
+// "accumulator drained" to the leader.
+// =====================================================================================================================
+constexpr int kPairStages = 6;
+constexpr int kPairStageBytes = kABytes + kBBytesMax / 2;                  // 16 KB A + up to 16 KB B half
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kStageOutBytes + 1024 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_out = smem + kPairStages * kPairStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + kStageOutBytes);
+    uint64_t* full_bar = bars;                         // [kPairStages]  (the leader's are used)
+    uint64_t* empty_bar = bars + kPairStages;          // [kPairStages]  (local, multicast-arrived)
+    uint64_t* tfull_bar = bars + 2 * kPairStages;      // [2]            (local, multicast-arrived)
+    uint64_t* tempty_bar = bars + 2 * kPairStages + 2; // [2]            (the leader's are used, 8 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int half_n = P.block_n / 2;
+    const int col_stride = P.block_n < 32 ? 32 : P.block_n;
+
+    if (warp == 0 && lane == 0) {
+        for (int p = 0; p < P.planes; ++p) {
+            for (int v = 0; v < ACLGAN_MAX_AVARIANTS; ++v) tma_prefetch_desc(&P.a[p][v]);
+            tma_prefetch_desc(&P.b[p]);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kPairStages; ++s) {
+            mbar_init(&full_bar[s], 2);       // leader's expect_tx arrive + the peer's remote arrive
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 8);     // 4 epilogue warps of each CTA
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(tmem_slot, 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_tiles = P.tiles_x * P.tiles_y * P.tiles_z;
+    const int m_items = (m_tiles + 1) / 2;
+    const int total_items = m_items * P.n_tiles;
+    const int n_clusters = gridDim.x / 2;
+    const int cluster_id = blockIdx.x / 2;
+    const int k_iters = P.nseg * P.num_taps * P.cchunks;
+    const uint32_t cta_tx = kABytes + half_n * 128;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer (both CTAs) ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int item = cluster_id; item < total_items; item += n_clusters) {
+            const int nt = item % P.n_tiles;
+            int mt = (item / P.n_tiles) * 2 + (int)rank;   // past-the-end tile: decodes to z >= N (zero fill, never stored)
+            const int x0 = (mt % P.tiles_x) * P.box_x;
+            mt /= P.tiles_x;
+            const int y0 = (mt % P.tiles_y) * P.box_y;
+            const int z0 = (mt / P.tiles_y) * P.box_z;
+#pragma unroll 1
+            for (int seg = 0; seg < P.nseg; ++seg) {
+                const int pa = (seg == 2) ? 1 : 0;
+                const int pb = (seg == 1) ? 1 : 0;
+#pragma unroll 1
+                for (int t = 0; t < P.num_taps; ++t) {
+                    const CUtensorMap* am = &P.a[pa][P.tap_var[t]];
+                    const int dx = P.tap_dx[t], dy = P.tap_dy[t];
+                    const int bk = P.tap_bk[t];
+#pragma unroll 1
+                    for (int cc = 0; cc < P.cchunks; ++cc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * kPairStageBytes;
+                        uint8_t* sb = sa + kABytes;
+                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * cta_tx);
+                        else mbar_arrive_leader(&full_bar[stage]);
+                        tma_load_4d_pair(sa, am, &full_bar[stage], cc * 64, x0 + dx, y0 + dy, z0);
+                        tma_load_2d_pair(sb, &P.b[pb], &full_bar[stage], bk + cc * 64, nt * P.block_n + (int)rank * half_n);
+                        if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        // ---------------- MMA issuer (leader CTA only) ----------------
+        const uint32_t idesc = make_idesc_bf16(256, (uint32_t)P.block_n, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int item = cluster_id; item < total_items; item += n_clusters, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * col_stride;
+#pragma unroll 1
+            for (int k = 0; k < k_iters; ++k) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * kPairStageBytes);
+                const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+                const uint64_t db = make_smem_desc_sw128(sa + kABytes, 16, 1024);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16_pair(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                umma_commit_pair(&empty_bar[stage], 3);
+                if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit_pair(&tfull_bar[acc], 3);
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue (both CTAs, own 128 rows) ----------------
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const aclgan_out_spec& o = P.out;
+        int it = 0;
+        for (int item = cluster_id; item < total_items; item += n_clusters, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int nt = item % P.n_tiles;
+            int mt = (item / P.n_tiles) * 2 + (int)rank;
+            const bool sub_ok = mt < m_tiles;
+            const int tx = mt % P.tiles_x;
+            mt /= P.tiles_x;
+            const int ty = mt % P.tiles_y;
+            const int tz = mt / P.tiles_y;
+            RowCtx rc;
+            if (P.flat) {
+                const int64_t qq = (int64_t)tx * P.box_x + row;
+                rc.z = (int)(qq / P.flat_img);
+                const int rem = (int)(qq % P.flat_img);
+                rc.y = rem / P.flat_w;
+                rc.x = rem % P.flat_w;
+            } else {
+                rc.x = tx * P.box_x + row % P.box_x;
+                rc.y = ty * P.box_y + (row / P.box_x) % P.box_y;
+                rc.z = tz * P.box_z + row / (P.box_x * P.box_y);
+            }
+            rc.valid = sub_ok && (rc.x < o.W) && (rc.y < o.H) && (rc.z < o.N) && P.debug != 3;
+            rc.pix0 = o.off + (int64_t)rc.z * o.sn + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
+            rc.ny = mirror_coords(rc.y, o.H, o.mirror, rc.ys);
+            rc.nx = mirror_coords(rc.x, o.W, o.mirror, rc.xs);
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            if (P.debug != 4) {
+                const uint32_t t_row = tmem_base + acc * col_stride + ((uint32_t)(q * 32) << 16);
+                const int n0 = nt * P.block_n;
+                const int group = (o.kind == ACLGAN_OUT_F32) ? 32 : 64;
+                const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) &&
+                                  (n0 + P.block_n <= o.C) && (o.stats == 0);
+                if (fast) epilogue_tile_fast(P, t_row, n0, rc, stage_out + q * 8192, lane);
+                else epilogue_tile_generic(P, t_row, n0, rc);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();          // the peer may still be arriving on / reading the leader's barriers and TMEM
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
 static int fill_kparams(const aclgan_igemm_plan* pl, IgemmKParams* kp) {
     if (pl->planes < 1 || pl->planes > 2 || (pl->nseg != 1 && pl->nseg != 3)) return ACLGAN_ERR_SHAPE;
     if (pl->nseg == 3 && pl->planes != 2) return ACLGAN_ERR_SHAPE;
@@ -507,7 +691,37 @@ extern "C" int aclgan_igemm_launch_repeat(const aclgan_igemm_plan* plan, int rep
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    const int total = ((plan->tiles_x * plan->tiles_y * plan->tiles_z + kp.m_sub - 1) / kp.m_sub) * plan->n_tiles;
+    const int m_tiles_all = plan->tiles_x * plan->tiles_y * plan->tiles_z;
+    {
+        // CTA pairs when there is enough work to fill the SMs pairwise (env ACLGAN_IGEMM_PAIR=0|1 overrides)
+        const char* env = getenv("ACLGAN_IGEMM_PAIR");
+        bool pair = (plan->block_n >= 32) && (((m_tiles_all + 1) / 2) * plan->n_tiles >= num_sms() / 2);
+        if (env != nullptr) pair = atoi(env) != 0 && plan->block_n >= 32;
+        if (pair) {
+            static bool pair_attr = false;
+            // the pair kernel loads half of the weight tile per CTA: B boxes of block_n / 2 rows
+            for (int p = 0; p < plan->planes; ++p) {
+                aclgan_tmap_spec bs = plan->b[p];
+                bs.box[1] = plan->block_n / 2;
+                int rc2 = encode_tmap(&bs, &kp.b[p]);
+                if (rc2) return rc2;
+            }
+            if (plan->planes == 1) kp.b[1] = kp.b[0];
+            if (!pair_attr) {
+                cudaError_t e = cudaFuncSetAttribute(igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     kPairSmemBytes);
+                if (e != cudaSuccess) return (int)e;
+                pair_attr = true;
+            }
+            const int items = ((m_tiles_all + 1) / 2) * plan->n_tiles;
+            int clusters = num_sms() / 2;
+            if (items < clusters) clusters = items;
+            for (int i = 0; i < repeat; ++i)
+                igemm_pair_kernel<<<2 * clusters, kThreads, kPairSmemBytes, (cudaStream_t)stream>>>(kp);
+            return (int)cudaGetLastError();
+        }
+    }
+    const int total = ((m_tiles_all + kp.m_sub - 1) / kp.m_sub) * plan->n_tiles;
     if (total <= 0) return ACLGAN_OK;
     const int grid = total < num_sms() ? total : num_sms();
     for (int i = 0; i < repeat; ++i) igemm_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(kp);

@@ -379,9 +379,11 @@ extern "C" int aclgan_plan_conv_wgrad(const aclgan_conv_desc* cd, const aclgan_a
         p->n_chunks = 1; p->n_tiles = 1;
         p->M = cd->cin; p->Nn = 64; p->dw_st = 64;
     }
+    // split-K so that the grid is ONE wave of CTAs (<= number of SMs): a grid of 162 CTAs on 148 SMs would run two
+    // waves and take twice as long as 144
     const int blocks_total = p->blocks_x * p->blocks_y * p->blocks_z;
     const int tiles = p->num_taps * p->m_tiles * p->n_tiles;
-    int ks = ceil_div(148, tiles);
+    int ks = num_sms() / tiles;
     if (ks > blocks_total / 4) ks = blocks_total / 4;
     if (ks < 1) ks = 1;
     p->ksplit = ks;

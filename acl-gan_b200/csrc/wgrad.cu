@@ -11,6 +11,8 @@
 //
 // Replaces: the weight-gradient half of autograd's convolution_backward for nn.Conv2d (reference
 // networks.py:363,366 under loss.backward(), trainer.py:169,292).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace aclgan {
@@ -20,7 +22,8 @@ constexpr int kWChunkBytes = 64 * 128;               // 64 pixels x 64 channels 
 constexpr int kWMBytes = 2 * kWChunkBytes;           // M operand: up to 2 chunks
 constexpr int kWNBytes = 4 * kWChunkBytes;           // N operand: up to 4 chunks
 constexpr int kWStageBytes = kWMBytes + kWNBytes;    // 48 KB
-constexpr int kWSmemBytes = kWStages * kWStageBytes + 1024 + 256;
+constexpr int kWStageOut = 4 * 4096;                 // epilogue staging: 4 warps x (32 rows x 128 B)
+constexpr int kWSmemBytes = kWStages * kWStageBytes + kWStageOut + 1024 + 256;
 constexpr int kWThreads = 256;
 
 struct alignas(64) WgradKParams {
@@ -34,12 +37,14 @@ struct alignas(64) WgradKParams {
     float* dw;
     long long dw_sm, dw_st;
     int M, Nn;
+    int debug;   // perf triage (env ACLGAN_WGRAD_DEBUG): 1 = skip the atomics, 2 = direct (unstaged) atomics
 };
 
 __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_constant__ WgradKParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWStages * kWStageBytes);
+    uint8_t* stage_out = smem + kWStages * kWStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWStages * kWStageBytes + kWStageOut);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kWStages;
     uint64_t* done_bar = bars + 2 * kWStages;
@@ -139,24 +144,43 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
             const int ncols = 64 * P.n_chunks;
             const int n_base = nt * ncols;
             float* row = P.dw + (long long)m * P.dw_sm + (long long)P.tap_out[tap] * P.dw_st;
+            uint8_t* stg = stage_out + q * 4096;
+            const bool row_ok = m < P.M;
+#pragma unroll 1
             for (int c = 0; c < ncols; c += 32) {
                 uint32_t raw[32];
                 tmem_ld_32x32(t_row + c, raw);
                 tmem_ld_wait();
-                if (m < P.M) {
-                    const int n0 = n_base + c;
-                    float* dst = row + n0;
-                    if (n0 + 32 <= P.Nn && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                if (P.debug == 1) continue;
+                const int n0 = n_base + c;
+                float* dst = row + n0;
+                const bool full = (n0 + 32 <= P.Nn) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && P.debug != 2;
+                if (__all_sync(0xffffffffu, full || !row_ok)) {
+                    // stage 32 rows x 128 B, then 8 lanes add one full 128-byte line each (vector reductions that the
+                    // memory system can merge per line instead of 32 scattered 16-byte reductions per instruction)
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            atomicAdd(reinterpret_cast<float4*>(dst + i),
-                                      make_float4(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]),
-                                                  __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3])));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (n0 + i < P.Nn) atomicAdd(dst + i, __uint_as_float(raw[i]));
+                    for (int i = 0; i < 8; ++i) {
+                        uint4 qv;
+                        qv.x = raw[4 * i]; qv.y = raw[4 * i + 1]; qv.z = raw[4 * i + 2]; qv.w = raw[4 * i + 3];
+                        *reinterpret_cast<uint4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) = qv;
                     }
+                    __syncwarp();
+                    const int piece = lane & 7;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + (lane >> 3);
+                        const long long roff = __shfl_sync(0xffffffffu, (long long)(dst - P.dw), r);
+                        const int ok = __shfl_sync(0xffffffffu, (int)row_ok, r);
+                        if (ok) {
+                            const float4 fv = *reinterpret_cast<const float4*>(stg + r * 128 + ((piece ^ (r & 7)) << 4));
+                            atomicAdd(reinterpret_cast<float4*>(P.dw + roff + piece * 4), fv);
+                        }
+                    }
+                    __syncwarp();
+                } else if (row_ok) {
+#pragma unroll 1
+                    for (int i = 0; i < 32; ++i)
+                        if (n0 + i < P.Nn) atomicAdd(dst + i, __uint_as_float(raw[i]));
                 }
             }
         }
@@ -211,6 +235,10 @@ extern "C" int aclgan_wgrad_launch_repeat(const aclgan_wgrad_plan* pl, int repea
     }
     kp.dw = reinterpret_cast<float*>(pl->dw); kp.dw_sm = pl->dw_sm; kp.dw_st = pl->dw_st;
     kp.M = pl->M; kp.Nn = pl->Nn;
+    {
+        const char* dbg = getenv("ACLGAN_WGRAD_DEBUG");
+        kp.debug = dbg != nullptr ? atoi(dbg) : 0;
+    }
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
         if (e != cudaSuccess) return (int)e;

@@ -26,10 +26,12 @@ FWD_CASES = [
 ]
 
 
-@pytest.mark.parametrize("msub", [1, 2])
+@pytest.mark.parametrize("msub", [1, 2, "pair"])
 @pytest.mark.parametrize("cin,cout,k,s,pad,window,n,h,w,planes", FWD_CASES)
 def test_conv_fwd(monkeypatch, msub, cin, cout, k, s, pad, window, n, h, w, planes):
-    monkeypatch.setenv("ACLGAN_IGEMM_MSUB", str(msub))     # 128- vs 256-pixel work items of the igemm kernel
+    # kernel variants: 128- / 256-pixel work items of the 1-CTA kernel, or the CTA-pair (cta_group::2) kernel
+    monkeypatch.setenv("ACLGAN_IGEMM_PAIR", "1" if msub == "pair" else "0")
+    monkeypatch.setenv("ACLGAN_IGEMM_MSUB", "1" if msub == "pair" else str(msub))
     L = N.lib()
     torch.manual_seed(0)
     x = torch.randn(n, cin, h, w, device="cuda")
@@ -87,10 +89,11 @@ DGRAD_CASES = [
 ]
 
 
-@pytest.mark.parametrize("msub", [1, 2])
+@pytest.mark.parametrize("msub", [1, 2, "pair"])
 @pytest.mark.parametrize("cin,cout,k,s,pad,n,ho,wo,planes", DGRAD_CASES)
 def test_conv_dgrad(monkeypatch, msub, cin, cout, k, s, pad, n, ho, wo, planes):
-    monkeypatch.setenv("ACLGAN_IGEMM_MSUB", str(msub))
+    monkeypatch.setenv("ACLGAN_IGEMM_PAIR", "1" if msub == "pair" else "0")
+    monkeypatch.setenv("ACLGAN_IGEMM_MSUB", "1" if msub == "pair" else str(msub))
     L = N.lib()
     torch.manual_seed(1)
     dy = torch.randn(n, cout, ho, wo, device="cuda")
@@ -123,10 +126,11 @@ def test_conv_dgrad(monkeypatch, msub, cin, cout, k, s, pad, n, ho, wo, planes):
     assert err < (2e-5 if planes == 1 else 5e-5), err  # fp32 accumulation over K up to 6400
 
 
-@pytest.mark.parametrize("msub", [1, 2])
+@pytest.mark.parametrize("msub", [1, 2, "pair"])
 def test_conv_fwd_throughput_report(capsys, monkeypatch, msub):
     """not an assertion on speed - prints the achieved TFLOP/s of the dominant 3x3 256->256 layer"""
-    monkeypatch.setenv("ACLGAN_IGEMM_MSUB", str(msub))
+    monkeypatch.setenv("ACLGAN_IGEMM_PAIR", "1" if msub == "pair" else "0")
+    monkeypatch.setenv("ACLGAN_IGEMM_MSUB", "1" if msub == "pair" else str(msub))
     L = N.lib()
     torch.manual_seed(0)
     n, c, h = 8, 256, 64
@@ -138,20 +142,18 @@ def test_conv_fwd_throughput_report(capsys, monkeypatch, msub):
     o, obuf = G.out_spec(n, h, h, c, N.OUT_BF16, pad=1, mirror=1)
     plan = N.IgemmPlan()
     N.check(L.aclgan_plan_conv_fwd(C.byref(desc), C.byref(act), G.wptr(packed), C.byref(o), C.byref(plan)), "plan")
-    for _ in range(3):
-        N.check(L.aclgan_igemm_launch(C.byref(plan), G.stream_ptr()), "launch")
+    N.check(L.aclgan_igemm_launch_repeat(C.byref(plan), 3, G.stream_ptr()), "launch")
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     iters = 20
-    for _ in range(iters):
-        N.check(L.aclgan_igemm_launch(C.byref(plan), G.stream_ptr()), "launch")
+    N.check(L.aclgan_igemm_launch_repeat(C.byref(plan), iters, G.stream_ptr()), "launch")   # device-side timing
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     flops = 2.0 * n * h * h * c * c * 9
     with capsys.disabled():
-        print("\n[igemm 3x3 256->256 bs8 64x64 msub=%d] %.3f ms  %.1f TFLOP/s" % (msub, ms, flops / ms / 1e9))
+        print("\n[igemm 3x3 256->256 bs8 64x64 msub=%s] %.3f ms  %.1f TFLOP/s" % (msub, ms, flops / ms / 1e9))
 
 
 WGRAD_CASES = [

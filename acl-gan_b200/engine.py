@@ -224,6 +224,7 @@ class Engine:
         self._check_device()
         N.lib()
         self.eps = 1e-5
+        self.debug = None           # tests: dict collecting per-layer backward intermediates
 
     def _check_device(self):
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -386,7 +387,7 @@ class Engine:
                 a.res = res.struct()
             a.upsample, a.dst = upsample, out.struct()
             N.check(L.aclgan_norm_apply(C.byref(a), _sp()), "norm_apply")
-            saved = (y, coef, sigma)
+            saved = (y, coef, sigma, sums[:, :, 0].clone() if norm == N.NORM_LN else None)
         need_x_grad = x.requires_grad
         out.requires_grad = need_x_grad or train_w or (res is not None and res.requires_grad) or adain is not None
         if not tape.enabled or not out.requires_grad:
@@ -419,7 +420,7 @@ class Engine:
                     N.check(L.aclgan_block_bwd_reduce(C.byref(b), _sp()), "block_bwd_reduce")
                     layer.db().add_(sums[:, :cout, 0].sum(0).float())
             else:
-                y, coef, sigma = saved
+                y, coef, sigma, fwd_s1 = saved
                 b.norm = 1
                 b.mask_mode = N.MASK_NONE if act == N.ACT_NONE else N.MASK_FROM_Z
                 b.y = self.t4(y)
@@ -438,8 +439,22 @@ class Engine:
                 N.check(L.aclgan_norm_bwd_finalize(C.byref(f), _sp()), "norm_bwd_finalize")
                 if norm == N.NORM_ADAIN:
                     adain[2](dwb[0], dwb[1])        # after the launch: the sink may enqueue copies of dw / db
+                if norm == N.NORM_LN and train_w:
+                    # a conv bias in front of LayerNorm is NOT cancelled (statistics span all channels):
+                    # db[c] = sum_{n,hw} dy with dy = ca*dz + cb*yhat + cc:
+                    #        = sum_n ca*T1 + cb*sum_hw(yhat) + cc*HW,   sum_hw(yhat) = (S1 - HW*mean) * inv
+                    hw = float(ho * wo)
+                    syh = (fwd_s1[:, :cout] - hw * coef[2, :, :cout].double()) * coef[3, :, :cout].double()
+                    db = (cf[0, :, :cout].double() * sums[:, :cout, 0] + cf[1, :, :cout].double() * syh +
+                          cf[2, :, :cout].double() * hw).sum(0)
+                    layer.db().add_(db.float())
                 b.ca, b.cb, b.cc = (cf[i].data_ptr() for i in range(3))
             N.check(L.aclgan_block_bwd_apply(C.byref(b), _sp()), "block_bwd_apply")
+            if self.debug is not None:
+                self.debug.setdefault(id(layer), []).append(dict(
+                    dy=dy.value_nchw(), gp=None if gp is None else gp.float().clone(),
+                    gr=None if gr is None else gr.float().clone(), out_pad=out.pad, upsample=upsample,
+                    xpad=x.buf[:, :x.numel].float().sum(0).view(x.n, x.h + 2 * x.pad, x.w + 2 * x.pad, x.c).clone()))
             if train_w:
                 self.conv_wgrad(layer, dy, x)
             if need_x_grad:

@@ -255,6 +255,13 @@ class _EngineNet(nn.Module):
         for p, (off, numel) in getattr(self, "_dense_grads", []):
             p.grad = self._arena.view(off, numel).view(p.shape)
 
+    def refresh_grads(self):
+        """conv layers whose packed gradient layout has a negative kw stride (final conv) expose `.grad` as a copy:
+        re-materialise it after a backward pass (the fused Adam kernel reads the arena directly, not this copy)"""
+        for blk in self.modules():
+            if isinstance(blk, Conv2dBlock) and blk._layer is not None and blk._layer.aff[blk._layer.layout][4] < 0:
+                blk.conv.weight.grad = blk._layer.grad_views()[0]
+
     def _reserve_dense(self, p):
         if not hasattr(self, "_dense_grads"):
             self._dense_grads = []

@@ -62,6 +62,7 @@ class aclgan_Trainer(nn.Module):
         self.use_graphs = bool(int(hp.get("cuda_graphs", os.environ.get("ACLGAN_CUDA_GRAPHS", "1"))))
         self._graphs = {}
         self._launches = {}
+        self.expose_grads = bool(int(hp.get("expose_grads", 1)))   # keep every param.grad readable after an update
         self._ready = False
         self._noise = None          # optional injected style noise (tests / graph replay): list of 3 tensors
 
@@ -280,6 +281,9 @@ class aclgan_Trainer(nn.Module):
             self._gen_fwd_bwd(x_a, x_b, hyperparameters, self._draw_noise(x_a.size(0)))
         self._allreduce(self.gen_arena)
         self._adam_step(self._adam_gen)
+        if self.expose_grads:
+            self.gen_AB.refresh_grads()
+            self.gen_BA.refresh_grads()
 
     def _gen_fwd_bwd(self, x_a, x_b, hyperparameters, zs):
         hp = hyperparameters

@@ -102,7 +102,9 @@ def cpu_baseline(cfg, size, steps=1, warmup=0):
     """the reference algorithm on the host cores: oracle port (plain torch CPU fp32), bs=1 step-pairs at `size`^2"""
     import torch
     import aclgan_oracle as O
-    cores = os.cpu_count() or 1
+    # intra-op threads: all host cores up to 32 (beyond that torch's CPU convolutions on these small per-image
+    # shapes slow down from oversubscription: 128 threads measured 34x slower than 8)
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     ot = O.OracleTrainer(copy.deepcopy(cfg))
@@ -118,8 +120,9 @@ def cpu_baseline(cfg, size, steps=1, warmup=0):
         ot.gen_update(x_a, x_b)
     dt = (time.time() - t0) / steps
     return dict(value=1.0 / dt, unit="images/s", cores=cores, kind="port",
-                sample="%d step-pair(s) of the oracle port (oracle/aclgan_oracle.py, torch CPU fp32, %d threads) at "
-                       "%dx%d bs=1 after %d warm-up" % (steps, cores, size, size, warmup), s_per_step_pair=dt)
+                sample="%d step-pair(s) of the oracle port (oracle/aclgan_oracle.py, torch CPU fp32, %d threads of %d host "
+                       "cores) at %dx%d bs=1 after %d warm-up" % (steps, cores, os.cpu_count() or 1, size, size, warmup),
+                s_per_step_pair=dt)
 
 
 def run_reference(args):

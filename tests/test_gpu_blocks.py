@@ -57,6 +57,11 @@ CASES = [
     (64, 128, 4, 2, 1, N.NORM_NONE, N.ACT_LRELU, False, 1, 1, 2, 16),
     (64, 64, 4, 2, 1, N.NORM_NONE, N.ACT_RELU, False, 1, 0, 2, 8),
     (32, 16, 3, 1, 1, N.NORM_ADAIN, N.ACT_RELU, False, 1, 1, 2, 8),      # channel counts below one 64-chunk
+    # larger planes: several CTAs per image in the reductions, several tiles per image row
+    (64, 64, 3, 1, 1, N.NORM_IN, N.ACT_RELU, False, 1, 1, 2, 64),
+    (64, 128, 4, 2, 1, N.NORM_IN, N.ACT_RELU, False, 1, 1, 2, 64),
+    (64, 64, 4, 2, 1, N.NORM_NONE, N.ACT_LRELU, False, 1, 1, 1, 64),
+    (64, 64, 5, 1, 2, N.NORM_LN, N.ACT_RELU, False, 2, 2, 1, 32),
 ]
 
 
@@ -203,4 +208,6 @@ def test_image_io_and_final_conv(precision):
             "image grad": rel(ib.grad, b64i.grad)}
     print("\n[final conv / image io %s] %s" % (precision, errs))
     assert ia.grad is None
-    assert all(v < btol for v in errs.values()), errs
+    # the first conv's quantities sit below a LeakyReLU: one flipped unit of this 8x8 plane is ~6e-3 (see test_gpu_step)
+    lim = {k: (btol if "final" in k or "window-out" in k else max(btol, 2e-2)) for k in errs}
+    assert all(errs[k] < lim[k] for k in errs), errs

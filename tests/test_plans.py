@@ -100,6 +100,8 @@ DGRAD_CASES = [
     (128, 64, 5, 1, 2, 1, 4, 8, 1),
     (3, 64, 7, 1, 3, 1, 4, 4, 1),
     (64, 64, 4, 2, 1, 2, 2, 2, 2),
+    (64, 4, 7, 1, 3, 2, 4, 4, 1),
+    (64, 4, 7, 1, 3, 1, 8, 8, 2),
 ]
 
 
@@ -110,9 +112,10 @@ def test_conv_dgrad_plan(cin, cout, k, s, pad, n, ho, wo, planes):
     mem = emul.Memory()
     dy = torch.randn(n, cout, ho, wo)
     wt = torch.randn(cout, cin, k, k) * 0.1
-    desc = N.ConvDesc(cin, cout, k, s, pad, 0)
+    window = 2 if cout <= 8 else 0
+    desc = N.ConvDesc(cin, cout, k, s, pad, window)
     pz = k - 1 if s == 1 else k // 2 - 1
-    cs = ((cout + 63) // 64) * 64
+    cs = 8 if window else ((cout + 63) // 64) * 64
     act, abuf, dyeff = make_act(mem, dy, pz, cs, planes, mode="constant")
     dyeff = dyeff[:, :, pz:pz + ho, pz:pz + wo] if pz > 0 else dyeff
     wts = [emul.pack_weight(desc, wt, True)]

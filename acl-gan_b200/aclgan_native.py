@@ -42,6 +42,7 @@ class IgemmPlan(C.Structure):
                 ("tap_dx", C.c_int32 * MAX_TAPS), ("tap_dy", C.c_int32 * MAX_TAPS),
                 ("tap_var", C.c_int32 * MAX_TAPS), ("tap_bk", C.c_int32 * MAX_TAPS),
                 ("flat", C.c_int32), ("flat_w", C.c_int32), ("flat_img", C.c_int32),
+                ("n_groups", C.c_int32), ("group_taps", C.c_int32), ("group_off", C.c_int64 * 4),
                 ("out", OutSpec)]
 
 

@@ -39,6 +39,8 @@ struct alignas(64) IgemmKParams {
     int box_x, box_y, box_z, tiles_x, tiles_y, tiles_z;
     int cchunks, num_taps;
     int flat, flat_w, flat_img;
+    int n_groups, group_taps;
+    long long group_off[4];
     int tap_dx[ACLGAN_MAX_TAPS];
     int tap_dy[ACLGAN_MAX_TAPS];
     int tap_var[ACLGAN_MAX_TAPS];
@@ -294,8 +296,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 
     const int m_tiles = P.tiles_x * P.tiles_y * P.tiles_z;
     const int m_items = (m_tiles + m_sub - 1) / m_sub;
-    const int total_tiles = m_items * P.n_tiles;               // CTA work items
-    const int k_iters = P.nseg * P.num_taps * P.cchunks;
+    const int group_items = m_items * P.n_tiles;
+    const int total_tiles = group_items * P.n_groups;          // CTA work items (x output-parity groups)
+    const int k_iters = P.nseg * P.group_taps * P.cchunks;
     const uint32_t stage_tx = m_sub * kABytes + P.block_n * 128;
 
     if (warp == 0 && lane == 0) {
@@ -303,8 +306,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int nt = tile % P.n_tiles;
-            const int mi = tile / P.n_tiles;
+            const int grp = tile / group_items;
+            const int gt = tile % group_items;
+            const int nt = gt % P.n_tiles;
+            const int mi = gt / P.n_tiles;
+            const int tap0 = grp * P.group_taps;
             int x0[2], y0[2], z0[2];
             for (int s = 0; s < m_sub; ++s) {
                 int mt = mi * m_sub + s;       // a tile index past the end decodes to z >= N: zero-filled, never stored
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 const int pa = (seg == 2) ? 1 : 0;   // A plane: hi, hi, lo
                 const int pb = (seg == 1) ? 1 : 0;   // B plane: hi, lo, hi
 #pragma unroll 1
-                for (int t = 0; t < P.num_taps; ++t) {
+                for (int t = tap0; t < tap0 + P.group_taps; ++t) {
                     const CUtensorMap* am = &P.a[pa][P.tap_var[t]];
                     const int dx = P.tap_dx[t], dy = P.tap_dy[t];
                     const int bk = P.tap_bk[t];
@@ -389,8 +395,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it % acc_sets;
             const uint32_t acc_phase = (it / acc_sets) & 1;
-            const int nt = tile % P.n_tiles;
-            const int mi = tile / P.n_tiles;
+            const int grp = tile / group_items;
+            const int gt = tile % group_items;
+            const int nt = gt % P.n_tiles;
+            const int mi = gt / P.n_tiles;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 }
                 rc.valid = sub_ok && (rc.x < o.W) && (rc.y < o.H) && (rc.z < o.N) && P.debug != 3;
                 if (P.debug == 4) continue;
-                rc.pix0 = o.off + (int64_t)rc.z * o.sn + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
+                rc.pix0 = o.off + P.group_off[grp] + (int64_t)rc.z * o.sn + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
                 rc.ny = mirror_coords(rc.y, o.H, o.mirror, rc.ys);
                 rc.nx = mirror_coords(rc.x, o.W, o.mirror, rc.xs);
                 const uint32_t t_row = tmem_base + acc * set_cols + sub * col_stride + ((uint32_t)(q * 32) << 16);
@@ -500,10 +508,11 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
 
     const int m_tiles = P.tiles_x * P.tiles_y * P.tiles_z;
     const int m_items = (m_tiles + 1) / 2;
-    const int total_items = m_items * P.n_tiles;
+    const int group_items = m_items * P.n_tiles;
+    const int total_items = group_items * P.n_groups;
     const int n_clusters = gridDim.x / 2;
     const int cluster_id = blockIdx.x / 2;
-    const int k_iters = P.nseg * P.num_taps * P.cchunks;
+    const int k_iters = P.nseg * P.group_taps * P.cchunks;
     const uint32_t cta_tx = kABytes + half_n * 128;
 
     if (warp == 0 && lane == 0) {
@@ -511,8 +520,11 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
         int stage = 0;
         uint32_t phase = 0;
         for (int item = cluster_id; item < total_items; item += n_clusters) {
-            const int nt = item % P.n_tiles;
-            int mt = (item / P.n_tiles) * 2 + (int)rank;   // past-the-end tile: decodes to z >= N (zero fill, never stored)
+            const int grp = item / group_items;
+            const int gi = item % group_items;
+            const int tap0 = grp * P.group_taps;
+            const int nt = gi % P.n_tiles;
+            int mt = (gi / P.n_tiles) * 2 + (int)rank;   // past-the-end tile: decodes to z >= N (zero fill, never stored)
             const int x0 = (mt % P.tiles_x) * P.box_x;
             mt /= P.tiles_x;
             const int y0 = (mt % P.tiles_y) * P.box_y;
@@ -522,7 +534,7 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
                 const int pa = (seg == 2) ? 1 : 0;
                 const int pb = (seg == 1) ? 1 : 0;
 #pragma unroll 1
-                for (int t = 0; t < P.num_taps; ++t) {
+                for (int t = tap0; t < tap0 + P.group_taps; ++t) {
                     const CUtensorMap* am = &P.a[pa][P.tap_var[t]];
                     const int dx = P.tap_dx[t], dy = P.tap_dy[t];
                     const int bk = P.tap_bk[t];
@@ -576,8 +588,10 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
         for (int item = cluster_id; item < total_items; item += n_clusters, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int nt = item % P.n_tiles;
-            int mt = (item / P.n_tiles) * 2 + (int)rank;
+            const int grp = item / group_items;
+            const int gi = item % group_items;
+            const int nt = gi % P.n_tiles;
+            int mt = (gi / P.n_tiles) * 2 + (int)rank;
             const bool sub_ok = mt < m_tiles;
             const int tx = mt % P.tiles_x;
             mt /= P.tiles_x;
@@ -596,7 +610,7 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
                 rc.z = tz * P.box_z + row / (P.box_x * P.box_y);
             }
             rc.valid = sub_ok && (rc.x < o.W) && (rc.y < o.H) && (rc.z < o.N) && P.debug != 3;
-            rc.pix0 = o.off + (int64_t)rc.z * o.sn + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
+            rc.pix0 = o.off + P.group_off[grp] + (int64_t)rc.z * o.sn + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
             rc.ny = mirror_coords(rc.y, o.H, o.mirror, rc.ys);
             rc.nx = mirror_coords(rc.x, o.W, o.mirror, rc.xs);
             mbar_wait(&tfull_bar[acc], acc_phase);
@@ -651,7 +665,7 @@ static int fill_kparams(const aclgan_igemm_plan* pl, IgemmKParams* kp) {
         // enough work items remain to keep the SMs busy
         const int m_tiles = pl->tiles_x * pl->tiles_y * pl->tiles_z;
         const char* env = getenv("ACLGAN_IGEMM_MSUB");
-        int m_sub = (m_tiles * pl->n_tiles >= 2 * num_sms()) ? 2 : 1;
+        int m_sub = (m_tiles * pl->n_tiles * (pl->n_groups > 1 ? pl->n_groups : 1) >= 2 * num_sms()) ? 2 : 1;
         if (env != nullptr) m_sub = atoi(env) == 2 ? 2 : 1;
         kp->m_sub = m_sub;
         const char* dbg = getenv("ACLGAN_IGEMM_DEBUG");
@@ -661,6 +675,10 @@ static int fill_kparams(const aclgan_igemm_plan* pl, IgemmKParams* kp) {
     kp->tiles_x = pl->tiles_x; kp->tiles_y = pl->tiles_y; kp->tiles_z = pl->tiles_z;
     kp->cchunks = pl->cchunks; kp->num_taps = pl->num_taps;
     kp->flat = pl->flat; kp->flat_w = pl->flat_w > 0 ? pl->flat_w : 1; kp->flat_img = pl->flat_img > 0 ? pl->flat_img : 1;
+    kp->n_groups = pl->n_groups > 0 ? pl->n_groups : 1;
+    kp->group_taps = pl->n_groups > 1 ? pl->group_taps : pl->num_taps;
+    if (kp->n_groups > 4 || kp->n_groups * kp->group_taps != pl->num_taps) return ACLGAN_ERR_SHAPE;
+    for (int g = 0; g < 4; ++g) kp->group_off[g] = pl->n_groups > 1 ? pl->group_off[g] : 0;
     for (int t = 0; t < ACLGAN_MAX_TAPS; ++t) {
         kp->tap_dx[t] = pl->tap_dx[t]; kp->tap_dy[t] = pl->tap_dy[t];
         kp->tap_var[t] = pl->tap_var[t]; kp->tap_bk[t] = pl->tap_bk[t];
@@ -695,7 +713,8 @@ extern "C" int aclgan_igemm_launch_repeat(const aclgan_igemm_plan* plan, int rep
     {
         // CTA pairs when there is enough work to fill the SMs pairwise (env ACLGAN_IGEMM_PAIR=0|1 overrides)
         const char* env = getenv("ACLGAN_IGEMM_PAIR");
-        bool pair = (plan->block_n >= 32) && (((m_tiles_all + 1) / 2) * plan->n_tiles >= num_sms() / 2);
+        const int n_groups = plan->n_groups > 1 ? plan->n_groups : 1;
+        bool pair = (plan->block_n >= 32) && (((m_tiles_all + 1) / 2) * plan->n_tiles * n_groups >= num_sms() / 2);
         if (env != nullptr) pair = atoi(env) != 0 && plan->block_n >= 32;
         if (pair) {
             static bool pair_attr = false;
@@ -713,7 +732,7 @@ extern "C" int aclgan_igemm_launch_repeat(const aclgan_igemm_plan* plan, int rep
                 if (e != cudaSuccess) return (int)e;
                 pair_attr = true;
             }
-            const int items = ((m_tiles_all + 1) / 2) * plan->n_tiles;
+            const int items = ((m_tiles_all + 1) / 2) * plan->n_tiles * n_groups;
             int clusters = num_sms() / 2;
             if (items < clusters) clusters = items;
             for (int i = 0; i < repeat; ++i)
@@ -721,7 +740,7 @@ extern "C" int aclgan_igemm_launch_repeat(const aclgan_igemm_plan* plan, int rep
             return (int)cudaGetLastError();
         }
     }
-    const int total = ((m_tiles_all + kp.m_sub - 1) / kp.m_sub) * plan->n_tiles;
+    const int total = ((m_tiles_all + kp.m_sub - 1) / kp.m_sub) * plan->n_tiles * kp.n_groups;
     if (total <= 0) return ACLGAN_OK;
     const int grid = total < num_sms() ? total : num_sms();
     for (int i = 0; i < repeat; ++i) igemm_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(kp);

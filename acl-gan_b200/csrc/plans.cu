@@ -182,6 +182,8 @@ extern "C" int aclgan_plan_conv_fwd(const aclgan_conv_desc* cd, const aclgan_act
     }
     p->out = *out;
     if (p->out.N <= 0) { p->out.N = x->n; p->out.H = ho; p->out.W = wo; }
+    p->n_groups = 1;
+    p->group_taps = p->num_taps;
     return ACLGAN_OK;
 }
 
@@ -222,13 +224,15 @@ extern "C" int aclgan_plan_conv_dgrad(const aclgan_conv_desc* cd, const aclgan_a
                     p->tap_bk[t] = (kh * k + kw) * cs;
                 }
         } else {
-            const int pa = phase >> 1, pb = phase & 1;
-            for (int kh = pa; kh < k; kh += 2)
-                for (int kw = pb; kw < k; kw += 2, ++t) {
-                    const int a = (kh - pa) / 2, b = (kw - pb) / 2;
-                    p->tap_dx[t] = (pz - a) * wz + (pz - b);
-                    p->tap_bk[t] = (kh * k + kw) * cs;
-                }
+            for (int ph = (phase < 0 ? 0 : phase); ph <= (phase < 0 ? 3 : phase); ++ph) {
+                const int pa = ph >> 1, pb = ph & 1;
+                for (int kh = pa; kh < k; kh += 2)
+                    for (int kw = pb; kw < k; kw += 2, ++t) {
+                        const int a = (kh - pa) / 2, b = (kw - pb) / 2;
+                        p->tap_dx[t] = (pz - a) * wz + (pz - b);
+                        p->tap_bk[t] = (kh * k + kw) * cs;
+                    }
+            }
         }
         p->num_taps = t;
     } else {
@@ -244,6 +248,15 @@ extern "C" int aclgan_plan_conv_dgrad(const aclgan_conv_desc* cd, const aclgan_a
         }
     }
     p->out = *out;
+    p->n_groups = 1;
+    p->group_taps = p->num_taps;
+    if (s == 2 && phase < 0) {
+        // all four output-parity phases in one launch: `out` is the strided view of phase (0,0)
+        if (p->num_taps > ACLGAN_MAX_TAPS || (p->num_taps % 4) != 0) return ACLGAN_ERR_UNSUPPORTED;
+        p->n_groups = 4;
+        p->group_taps = p->num_taps / 4;
+        for (int ph = 0; ph < 4; ++ph) p->group_off[ph] = (ph >> 1) * (out->sy / 2) + (ph & 1) * (out->sx / 2);
+    }
     return ACLGAN_OK;
 }
 
@@ -296,12 +309,20 @@ extern "C" int aclgan_plan_conv_wgrad(const aclgan_conv_desc* cd, const aclgan_a
     p->dw = dw;
     p->dw_sm = kt;
 
-    // reduction grid and its 64-pixel boxes
+    // reduction grid and its pixel boxes: 64 pixels per pipeline stage, or 128 when the operands are narrow (at most
+    // three 64-channel chunks per stage) so that the per-stage barrier / issue overhead is amortised
     const int gw = (cd->window == ACLGAN_WINDOW_OUT) ? wp : wo, gh = ho;
-    int bx = pow2_floor(gw < 64 ? gw : 64);
-    int by = 64 / bx;
+    int chunks_guess;
+    if (cd->window != ACLGAN_WINDOW_NONE) chunks_guess = 2;
+    else {
+        const int cm = layout == 0 ? dy->c : x->c, cn = layout == 0 ? x->c : dy->c;
+        chunks_guess = (cm / 64 >= 2 ? 2 : 1) + (cn / 64 > 4 ? 4 : cn / 64);
+    }
+    const int pix = (chunks_guess <= 3 && (int64_t)gw * gh * x->n >= 4096) ? 128 : 64;
+    int bx = pow2_floor(gw < pix ? gw : pix);
+    int by = pix / bx;
     if (by > pow2_ceil(gh)) by = pow2_ceil(gh);
-    const int bz = 64 / (bx * by);
+    const int bz = pix / (bx * by);
     p->box_x = bx; p->box_y = by; p->box_z = bz;
     p->blocks_x = ceil_div(gw, bx); p->blocks_y = ceil_div(gh, by); p->blocks_z = ceil_div(x->n, bz);
 

@@ -30,6 +30,7 @@ struct alignas(64) WgradKParams {
     CUtensorMap mop[2][ACLGAN_MAX_AVARIANTS];
     CUtensorMap nop[2][ACLGAN_MAX_AVARIANTS];
     int planes, nseg, m_chunks, n_chunks, m_tiles, n_tiles;
+    int pix;     // pixels per stage (64 | 128): small-channel layers use 128 to halve the per-stage barrier overhead
     int box_x, box_y, box_z, blocks_x, blocks_y, blocks_z, ksplit, num_taps;
     int m_dx[ACLGAN_MAX_TAPS], m_dy[ACLGAN_MAX_TAPS], m_var[ACLGAN_MAX_TAPS];
     int n_dx[ACLGAN_MAX_TAPS], n_dy[ACLGAN_MAX_TAPS], n_var[ACLGAN_MAX_TAPS];
@@ -82,7 +83,9 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t stage_tx = (uint32_t)(P.m_chunks + P.n_chunks) * kWChunkBytes;
+    const int chunk_bytes = P.pix * 128;                       // one 64-channel chunk of P.pix pixels
+    const int n_off = P.pix == 64 ? kWMBytes : P.m_chunks * chunk_bytes;   // N operand region inside a stage
+    const uint32_t stage_tx = (uint32_t)(P.m_chunks + P.n_chunks) * chunk_bytes;
 
     if (n_iters > 0) {
         if (warp == 0 && lane == 0) {
@@ -99,15 +102,15 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
                     const int pn = (seg == 1) ? 1 : 0;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sm = smem + stage * kWStageBytes;
-                    uint8_t* sn = sm + kWMBytes;
+                    uint8_t* sn = sm + n_off;
                     mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
                     const CUtensorMap* mm = &P.mop[pm][P.m_var[tap]];
                     const CUtensorMap* nm = &P.nop[pn][P.n_var[tap]];
                     for (int c = 0; c < P.m_chunks; ++c)
-                        tma_load_4d(sm + c * kWChunkBytes, mm, &full_bar[stage], (mt * 2 + c) * 64, x0 + P.m_dx[tap],
+                        tma_load_4d(sm + c * chunk_bytes, mm, &full_bar[stage], (mt * 2 + c) * 64, x0 + P.m_dx[tap],
                                     y0 + P.m_dy[tap], z0);
                     for (int c = 0; c < P.n_chunks; ++c)
-                        tma_load_4d(sn + c * kWChunkBytes, nm, &full_bar[stage], (nt * P.n_chunks + c) * 64,
+                        tma_load_4d(sn + c * chunk_bytes, nm, &full_bar[stage], (nt * P.n_chunks + c) * 64,
                                     x0 + P.n_dx[tap], y0 + P.n_dy[tap], z0);
                     if (++stage == kWStages) { stage = 0; phase ^= 1; }
                 }
@@ -121,12 +124,13 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t sm = smem_u32(smem + stage * kWStageBytes);
-                const uint32_t sn = sm + kWMBytes;
-                // MN-major, 128B swizzle: LBO = next 64-channel chunk (8 KB), SBO = next 8 pixel rows (1 KB)
-                const uint64_t dm = make_smem_desc_sw128(sm, kWChunkBytes, 1024);
-                const uint64_t dn = make_smem_desc_sw128(sn, kWChunkBytes, 1024);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t sn = sm + n_off;
+                // MN-major, 128B swizzle: LBO = next 64-channel chunk, SBO = next 8 pixel rows (1 KB)
+                const uint64_t dm = make_smem_desc_sw128(sm, chunk_bytes, 1024);
+                const uint64_t dn = make_smem_desc_sw128(sn, chunk_bytes, 1024);
+                const int n_mma = P.pix / 16;
+#pragma unroll 4
+                for (int kk = 0; kk < n_mma; ++kk) {
                     // 16 pixels (= one UMMA K) further down: 16 rows x 128 B = 2048 B -> +128 encoded
                     umma_bf16(tmem_base, dm + 128 * kk, dn + 128 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
                 }
@@ -208,7 +212,9 @@ extern "C" int aclgan_wgrad_launch_repeat(const aclgan_wgrad_plan* pl, int repea
     static bool attr_set = false;
     if (pl->planes < 1 || pl->planes > 2 || (pl->nseg != 1 && pl->nseg != 3)) return ACLGAN_ERR_SHAPE;
     if (pl->m_chunks < 1 || pl->m_chunks > 2 || pl->n_chunks < 1 || pl->n_chunks > 4) return ACLGAN_ERR_SHAPE;
-    if (pl->box_x * pl->box_y * pl->box_z != 64) return ACLGAN_ERR_SHAPE;
+    const int pix = pl->box_x * pl->box_y * pl->box_z;
+    if (pix != 64 && pix != 128) return ACLGAN_ERR_SHAPE;
+    if (pix == 128 && (pl->m_chunks + pl->n_chunks) * 128 * 128 > kWStageBytes) return ACLGAN_ERR_SHAPE;
     if (pl->num_taps < 1 || pl->num_taps > ACLGAN_MAX_TAPS || pl->ksplit < 1) return ACLGAN_ERR_SHAPE;
     if (pl->n_mvariants < 1 || pl->n_mvariants > ACLGAN_MAX_AVARIANTS || pl->n_nvariants < 1 ||
         pl->n_nvariants > ACLGAN_MAX_AVARIANTS)
@@ -224,6 +230,7 @@ extern "C" int aclgan_wgrad_launch_repeat(const aclgan_wgrad_plan* pl, int repea
         }
     }
     kp.planes = pl->planes; kp.nseg = pl->nseg; kp.m_chunks = pl->m_chunks; kp.n_chunks = pl->n_chunks;
+    kp.pix = pix;
     kp.m_tiles = pl->m_tiles; kp.n_tiles = pl->n_tiles;
     kp.box_x = pl->box_x; kp.box_y = pl->box_y; kp.box_z = pl->box_z;
     kp.blocks_x = pl->blocks_x; kp.blocks_y = pl->blocks_y; kp.blocks_z = pl->blocks_z;

@@ -321,17 +321,16 @@ class Engine:
             g = self.new_dense(x.n, hp, wp, cs, zero=(cs != round_up(layer.cin, 16)))
         dys = dy.struct()
         s = layer.stride
-        for phase in range(1 if s == 1 else 4):
-            o = self._out_dense(g)
-            pa, pb = phase >> 1, phase & 1
-            if s == 2:
-                o.off = (pa * wp + pb) * cs
-                o.sy, o.sx = 2 * wp * cs, 2 * cs
-                o.H, o.W = hp // 2, wp // 2
-            plan = N.IgemmPlan()
-            N.check(N.lib().aclgan_plan_conv_dgrad(C.byref(layer.desc), C.byref(dys), layer.wptr(1), phase,
-                                                   C.byref(o), C.byref(plan)), "plan_conv_dgrad")
-            N.check(N.lib().aclgan_igemm_launch(C.byref(plan), _sp()), "igemm_launch(dgrad)")
+        o = self._out_dense(g)
+        if s == 2:
+            # the four output-parity phases of the transposed stride-2 conv run as ONE launch (phase = -1):
+            # `o` describes the phase-(0,0) sub-grid, the plan adds the per-phase offsets
+            o.sy, o.sx = 2 * wp * cs, 2 * cs
+            o.H, o.W = hp // 2, wp // 2
+        plan = N.IgemmPlan()
+        N.check(N.lib().aclgan_plan_conv_dgrad(C.byref(layer.desc), C.byref(dys), layer.wptr(1), -1 if s == 2 else 0,
+                                               C.byref(o), C.byref(plan)), "plan_conv_dgrad")
+        N.check(N.lib().aclgan_igemm_launch(C.byref(plan), _sp()), "igemm_launch(dgrad)")
         return g
 
     def conv_wgrad(self, layer, dy, x):

@@ -233,6 +233,46 @@ class aclgan_Trainer(nn.Module):
             tape.push(bwd)
         return res
 
+    def _cat(self, tape, imgs):
+        """batch-concatenates image nodes so a discriminator runs ONCE over all of them (3x fewer, 3x larger launches)"""
+        if len(imgs) == 1:
+            return imgs[0]
+        res = E.ImgT(torch.cat([i.t for i in imgs], 0), requires_grad=any(i.requires_grad for i in imgs))
+        if tape.enabled and res.requires_grad:
+            def bwd():
+                if res.grad is None:
+                    return
+                off = 0
+                for i in imgs:
+                    n = i.t.shape[0]
+                    if i.requires_grad:
+                        i.add_grad(res.grad[off:off + n])
+                    off += n
+                res.grad = None
+            tape.push(bwd)
+        return res
+
+    @staticmethod
+    def _lsgan_multi(outs, n, targets, weights):
+        """LSGAN terms of several images pushed through a discriminator as one batch: per image group i (rows
+        [i*n, (i+1)*n) of every scale's logits) sum_scales mean((o - t_i)^2); seeds d loss / d logits with weight w_i"""
+        k = len(targets)
+        totals = [0] * k
+        for o in outs:
+            t = o.t
+            shape = [k * n] + [1] * (t.dim() - 1)
+            # (fill kernels only: a host->device copy of a Python list would break CUDA-graph capture)
+            tv = torch.cat([torch.full((n,), float(v), dtype=t.dtype, device=t.device) for v in targets]).view(shape)
+            diff = t - tv
+            sq = (diff * diff).view(k, -1)
+            per = sq.mean(1)
+            for i in range(k):
+                totals[i] = totals[i] + per[i]
+            if o.requires_grad:
+                wv = torch.cat([torch.full((n,), float(v), dtype=t.dtype, device=t.device) for v in weights]).view(shape)
+                o.add_grad(diff * wv * (2.0 / sq.shape[1]))
+        return totals
+
     @staticmethod
     def _lsgan(outs, target, weight):
         """sum over scales of mean((o - t)^2) (networks.py:67,83,98); seeds d loss / d logits scaled by `weight`"""
@@ -297,11 +337,14 @@ class aclgan_Trainer(nn.Module):
         r = self._cycle(tape, xa, xb, zs, need_recon=True)
 
         gw, gcw = hp["gan_w"], hp["gan_cw"]
-        self.loss_gen_adv_A = (self._lsgan(self.dis_A.dis(tape, r["x_A_fake"]), 1.0, 0.5 * gw) +
-                               self._lsgan(self.dis_A.dis(tape, r["x_A2_fake"]), 1.0, 0.5 * gw)) * 0.5
+        la = self._lsgan_multi(self.dis_A.dis(tape, self._cat(tape, [r["x_A_fake"], r["x_A2_fake"]])), n,
+                               [1.0, 1.0], [0.5 * gw, 0.5 * gw])
+        self.loss_gen_adv_A = (la[0] + la[1]) * 0.5
         self.loss_gen_adv_B = self._lsgan(self.dis_B.dis(tape, r["x_B_fake"]), 1.0, gw)
-        self.loss_gen_adv_2 = (self._lsgan(self.dis_2.dis(tape, xa, r["x_A_fake"]), 1.0, gcw) +
-                               self._lsgan(self.dis_2.dis(tape, xa, r["x_A2_fake"]), 0.0, gcw))
+        l2 = self._lsgan_multi(self.dis_2.dis(tape, self._cat(tape, [xa, xa]),
+                                              self._cat(tape, [r["x_A_fake"], r["x_A2_fake"]])), n,
+                               [1.0, 0.0], [gcw, gcw])
+        self.loss_gen_adv_2 = l2[0] + l2[1]
         total = gw * self.loss_gen_adv_A + gw * self.loss_gen_adv_B + gcw * self.loss_gen_adv_2
 
         if focus:
@@ -359,13 +402,16 @@ class aclgan_Trainer(nn.Module):
 
         tape = E.Tape()
         gw, gcw = hp["gan_w"], hp["gan_cw"]
-        real_a = self._lsgan(self.dis_A.dis(tape, xa), 1.0, gw)           # counted twice with weight 1/2 in the reference
-        self.loss_dis_A = (self._lsgan(self.dis_A.dis(tape, fake_a), 0.0, 0.5 * gw) +
-                           self._lsgan(self.dis_A.dis(tape, fake_a2), 0.0, 0.5 * gw) + 2.0 * real_a) * 0.5
-        self.loss_dis_B = (self._lsgan(self.dis_B.dis(tape, fake_b), 0.0, gw) +
-                           self._lsgan(self.dis_B.dis(tape, xb), 1.0, gw))
-        self.loss_dis_2 = (self._lsgan(self.dis_2.dis(tape, xa, fake_a), 0.0, gcw) +
-                           self._lsgan(self.dis_2.dis(tape, xa, fake_a2), 1.0, gcw))
+        # each discriminator runs once over the batch-concatenation of its inputs; dis_A(x_a) is counted twice with
+        # weight 1/2 in the reference (trainer.py:283-284) == once with weight 1
+        la = self._lsgan_multi(self.dis_A.dis(tape, self._cat(tape, [xa, fake_a, fake_a2])), n,
+                               [1.0, 0.0, 0.0], [gw, 0.5 * gw, 0.5 * gw])
+        self.loss_dis_A = (la[1] + la[2] + 2.0 * la[0]) * 0.5
+        lb = self._lsgan_multi(self.dis_B.dis(tape, self._cat(tape, [fake_b, xb])), n, [0.0, 1.0], [gw, gw])
+        self.loss_dis_B = lb[0] + lb[1]
+        l2 = self._lsgan_multi(self.dis_2.dis(tape, self._cat(tape, [xa, xa]), self._cat(tape, [fake_a, fake_a2])), n,
+                               [0.0, 1.0], [gcw, gcw])
+        self.loss_dis_2 = l2[0] + l2[1]
         self.loss_dis_total = gw * self.loss_dis_A + gw * self.loss_dis_B + gcw * self.loss_dis_2
         tape.backward()
 

@@ -78,6 +78,9 @@ typedef struct aclgan_igemm_plan {
     int32_t flat;        /* 0: tile rows decode as (x,y,z) box coordinates; 1: q = x0 + row, decoded with pitches */
     int32_t flat_w;      /* flat: x = q % flat_w */
     int32_t flat_img;    /* flat: z = q / flat_img, y = (q % flat_img) / flat_w */
+    int32_t n_groups;    /* 1, or the 4 output-parity phases of a stride-2 data gradient merged into one launch */
+    int32_t group_taps;  /* taps per group: group g uses taps [g*group_taps, (g+1)*group_taps) */
+    int64_t group_off[4];/* element offset added to out.off for the rows of group g */
     aclgan_out_spec out;
 } aclgan_igemm_plan;
 
@@ -91,7 +94,7 @@ typedef struct aclgan_wgrad_plan {
     int32_t m_chunks;            /* 64-channel chunks of the M operand per tile (1 | 2); UMMA M is always 128 */
     int32_t n_chunks;            /* 64-channel chunks of the N operand per tile (1..4);  UMMA N = 64 * n_chunks */
     int32_t m_tiles, n_tiles;
-    int32_t box_x, box_y, box_z; /* pixel box (product 64) */
+    int32_t box_x, box_y, box_z; /* pixel box (product 64 or 128 = pixels reduced per pipeline stage) */
     int32_t blocks_x, blocks_y, blocks_z; /* pixel blocks covering the reduction grid */
     int32_t ksplit;              /* CTAs per (tap, m_tile, n_tile), each reducing a contiguous range of pixel blocks */
     int32_t num_taps;
@@ -127,6 +130,8 @@ const char* aclgan_build_info(void);
 /* plan builders: pure host code, usable without a GPU (unit-tested by CPU emulation) */
 int aclgan_plan_conv_fwd(const aclgan_conv_desc* cd, const aclgan_act* x, const uint64_t w[2],
                          const aclgan_out_spec* out, aclgan_igemm_plan* plan);
+/* stride 2: phase = 0..3 builds one output-parity phase (out describes that phase's strided view); phase = -1 merges
+ * all four into one launch (out describes phase 0; the other phases are reached through group_off) */
 int aclgan_plan_conv_dgrad(const aclgan_conv_desc* cd, const aclgan_act* dy, const uint64_t wt[2], int phase,
                            const aclgan_out_spec* out, aclgan_igemm_plan* plan);
 int aclgan_plan_conv_wgrad(const aclgan_conv_desc* cd, const aclgan_act* dy, const aclgan_act* x, uint64_t dw,

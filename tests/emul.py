@@ -86,14 +86,17 @@ def run_igemm(mem, plan):
         bias = bt.reshape(-1)[boff:].double()
     segs = [(0, 0)] if plan.nseg == 1 else [(0, 0), (0, 1), (1, 0)]
     bn = plan.block_n
-    for tz in range(plan.tiles_z):
+    n_groups = plan.n_groups if plan.n_groups > 1 else 1
+    gtaps = plan.group_taps if plan.n_groups > 1 else plan.num_taps
+    for grp in range(n_groups):
+      for tz in range(plan.tiles_z):
         for ty in range(plan.tiles_y):
             for tx in range(plan.tiles_x):
                 x0, y0, z0 = tx * plan.box_x, ty * plan.box_y, tz * plan.box_z
                 for nt in range(plan.n_tiles):
                     acc = torch.zeros(128, bn, dtype=torch.float64)
                     for pa, pb in segs:
-                        for t in range(plan.num_taps):
+                        for t in range(grp * gtaps, (grp + 1) * gtaps):
                             am = plan.a[pa][plan.tap_var[t]]
                             for cc in range(plan.cchunks):
                                 A = tma_box(mem, am, (cc * 64, x0 + plan.tap_dx[t], y0 + plan.tap_dy[t], z0))
@@ -122,7 +125,7 @@ def run_igemm(mem, plan):
                         v = _act(v, o.act, o.slope)
                         for yy in _mirror(y, o.H, o.mirror):
                             for xx in _mirror(x, o.W, o.mirror):
-                                pix = o.off + z * o.sn + yy * o.sy + xx * o.sx
+                                pix = o.off + (plan.group_off[grp] if n_groups > 1 else 0) + z * o.sn + yy * o.sy + xx * o.sx
                                 for pl in range(nplanes_out):
                                     t, toff = outs[pl]
                                     flat = t.reshape(-1)
@@ -171,6 +174,7 @@ def run_wgrad(mem, plan):
     dw = dwt.reshape(-1)
     segs = [(0, 0)] if plan.nseg == 1 else [(0, 0), (0, 1), (1, 0)]
     ncols = 64 * plan.n_chunks
+    pix = plan.box_x * plan.box_y * plan.box_z
     for tap in range(plan.num_taps):
         for mt in range(plan.m_tiles):
             for nt in range(plan.n_tiles):
@@ -182,14 +186,14 @@ def run_wgrad(mem, plan):
                             for pm, pn in segs:
                                 mm = plan.mop[pm][plan.m_var[tap]]
                                 nm = plan.nop[pn][plan.n_var[tap]]
-                                Mt = torch.zeros(64, 128, dtype=torch.float64)
+                                Mt = torch.zeros(pix, 128, dtype=torch.float64)
                                 for c in range(plan.m_chunks):
                                     Mt[:, c * 64:(c + 1) * 64] = tma_box(
-                                        mem, mm, ((mt * 2 + c) * 64, x0 + plan.m_dx[tap], y0 + plan.m_dy[tap], z0)).reshape(64, 64)
-                                Nt = torch.zeros(64, ncols, dtype=torch.float64)
+                                        mem, mm, ((mt * 2 + c) * 64, x0 + plan.m_dx[tap], y0 + plan.m_dy[tap], z0)).reshape(pix, 64)
+                                Nt = torch.zeros(pix, ncols, dtype=torch.float64)
                                 for c in range(plan.n_chunks):
                                     Nt[:, c * 64:(c + 1) * 64] = tma_box(
-                                        mem, nm, ((nt * plan.n_chunks + c) * 64, x0 + plan.n_dx[tap], y0 + plan.n_dy[tap], z0)).reshape(64, 64)
+                                        mem, nm, ((nt * plan.n_chunks + c) * 64, x0 + plan.n_dx[tap], y0 + plan.n_dy[tap], z0)).reshape(pix, 64)
                                 acc += Mt.t() @ Nt
                 for r in range(128):
                     m = mt * 128 + r

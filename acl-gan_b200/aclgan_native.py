@@ -43,6 +43,9 @@ class IgemmPlan(C.Structure):
                 ("tap_var", C.c_int32 * MAX_TAPS), ("tap_bk", C.c_int32 * MAX_TAPS),
                 ("flat", C.c_int32), ("flat_w", C.c_int32), ("flat_img", C.c_int32),
                 ("n_groups", C.c_int32), ("group_taps", C.c_int32), ("group_off", C.c_int64 * 4),
+                ("seg_mode", C.c_int32), ("seg_rows", C.c_int32), ("num_segs", C.c_int32), ("seg_taps", C.c_int32),
+                ("seg_dx", C.c_int32 * 16), ("seg_dy", C.c_int32 * 16), ("tap_row", C.c_int32 * MAX_TAPS),
+                ("a_seg", TmapSpec * 2),
                 ("out", OutSpec)]
 
 
@@ -89,7 +92,7 @@ class NormFinalizeArgs(C.Structure):
     _fields_ = [("mode", C.c_int32), ("n", C.c_int32), ("c", C.c_int32), ("hw", C.c_int32),
                 ("c_valid", C.c_int32), ("eps", C.c_float), ("sums", C.c_uint64), ("w", C.c_uint64),
                 ("b", C.c_uint64), ("scale", C.c_uint64), ("shift", C.c_uint64), ("mean", C.c_uint64),
-                ("inv", C.c_uint64), ("sigma", C.c_uint64)]
+                ("inv", C.c_uint64), ("sigma", C.c_uint64), ("wb_stride", C.c_int64)]
 
 
 class ApplyArgs(C.Structure):
@@ -103,14 +106,14 @@ class BlockBwdArgs(C.Structure):
                 ("mask_mode", C.c_int32), ("slope", C.c_float), ("y", Tensor4), ("scale", C.c_uint64),
                 ("shift", C.c_uint64), ("out", Act), ("norm", C.c_int32), ("mean", C.c_uint64),
                 ("inv", C.c_uint64), ("sums", C.c_uint64), ("ca", C.c_uint64), ("cb", C.c_uint64),
-                ("cc", C.c_uint64), ("dy", Act)]
+                ("cc", C.c_uint64), ("dy", Act), ("dbias", C.c_uint64), ("dbias_n", C.c_int32)]
 
 
 class NormBwdFinalizeArgs(C.Structure):
     _fields_ = [("mode", C.c_int32), ("n", C.c_int32), ("c", C.c_int32), ("hw", C.c_int32),
                 ("c_valid", C.c_int32), ("sums", C.c_uint64), ("inv", C.c_uint64), ("sigma", C.c_uint64),
                 ("w", C.c_uint64), ("ca", C.c_uint64), ("cb", C.c_uint64), ("cc", C.c_uint64),
-                ("dw", C.c_uint64), ("db", C.c_uint64)]
+                ("dw", C.c_uint64), ("db", C.c_uint64), ("wb_stride", C.c_int64)]
 
 
 class ImgGradPackArgs(C.Structure):
@@ -199,6 +202,7 @@ def _declare(L):
     L.aclgan_packed_weight_index.argtypes = [C.POINTER(ConvDesc), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.aclgan_packed_weight_index.restype = C.c_int64
     L.aclgan_igemm_launch.argtypes = [C.POINTER(IgemmPlan), C.c_void_p]
+    L.aclgan_igemm_stats_supported.argtypes = [C.POINTER(IgemmPlan)]
     L.aclgan_plan_conv_wgrad.argtypes = [C.POINTER(ConvDesc), C.POINTER(Act), C.POINTER(Act), C.c_uint64,
                                          C.POINTER(WgradPlan)]
     L.aclgan_wgrad_layout.argtypes = [C.POINTER(ConvDesc)]

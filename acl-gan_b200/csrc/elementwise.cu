@@ -3,6 +3,8 @@
 // and their backward passes (fold of the reflect/upsample gather, activation mask, two-moment norm backward).
 // All work on 8-channel (16 B bf16 / 32 B fp32) vectors of NHWC planes; reductions go warp/CTA-local first and
 // then to fp64 atomics so the statistics do not suffer from fp32 cancellation.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace aclgan {
@@ -223,8 +225,9 @@ __global__ void norm_finalize_kernel(aclgan_norm_finalize_args a) {
         const double r = 1.0 / sqrt(var + (double)a.eps);
         double sc = r, sf = -mu * r;
         if (a.mode == ACLGAN_NORM_ADAIN) {
-            const double w = reinterpret_cast<const float*>(a.w)[(int64_t)n * c_valid + c];
-            const double b = reinterpret_cast<const float*>(a.b)[(int64_t)n * c_valid + c];
+            const int64_t ld = a.wb_stride > 0 ? a.wb_stride : c_valid;
+            const double w = reinterpret_cast<const float*>(a.w)[(int64_t)n * ld + c];
+            const double b = reinterpret_cast<const float*>(a.b)[(int64_t)n * ld + c];
             sc = r * w;
             sf = b - mu * sc;
         }
@@ -235,7 +238,7 @@ __global__ void norm_finalize_kernel(aclgan_norm_finalize_args a) {
 // ------------------------------------------------------------------------------------------ norm_apply
 constexpr int kApplyPix = 4;     // padded pixels per thread (same image, same channel group -> coefficients stay in registers)
 
-__global__ void __launch_bounds__(256) norm_apply_kernel(aclgan_apply_args a) {
+__global__ void __launch_bounds__(256, 2) norm_apply_kernel(aclgan_apply_args a) {
     const int u = a.upsample, p = a.dst.pad;
     const int hd = a.y.h * u, wd = a.y.w * u, hp = hd + 2 * p, wp = wd + 2 * p;
     const int cg = a.y.c / 8;
@@ -243,34 +246,46 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(aclgan_apply_args a) {
     const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
     const int n = blockIdx.y;
     if (lane >= lanes) return;
-    const int64_t npix = (int64_t)hp * wp;
+    const int npix = hp * wp;                 // (the launcher rejects planes of 2^30 pixels or more)
     F8 sc, sf;
     if (a.scale != 0) {
         sc = load_coef8(a.scale, (int64_t)n * a.y.c + g * 8);
         sf = load_coef8(a.shift, (int64_t)n * a.y.c + g * 8);
     }
-    const int64_t p0 = (int64_t)blockIdx.x * lanes * kApplyPix + lane;
+    const int rp = a.res.pad, rwp = a.res.w + 2 * rp, rhp = a.res.h + 2 * rp;
+    const int batch = lanes * kApplyPix;
+    // CTAs stride over pixel batches of their image; per batch all loads of the thread's pixels are issued first
+    // (memory-level parallelism), then the arithmetic and the stores
+    for (int p0 = blockIdx.x * batch + lane; p0 - lane < npix; p0 += gridDim.x * batch) {
+        F8 yv[kApplyPix], rv[kApplyPix];
 #pragma unroll
-    for (int j = 0; j < kApplyPix; ++j) {
-        const int64_t pix = p0 + (int64_t)j * lanes;
-        if (pix >= npix) break;
-        const int Y = (int)(pix / wp), X = (int)(pix % wp);
-        const int y = reflect_idx(Y - p, hd) / u, x = reflect_idx(X - p, wd) / u;
-        F8 v = load8(a.y.ptr, a.y.kind, (((int64_t)n * a.y.h + y) * a.y.w + x) * a.y.c + g * 8);
-        if (a.scale != 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v.v[i] = v.v[i] * sc.v[i] + sf.v[i];
+        for (int j = 0; j < kApplyPix; ++j) {
+            int pix = p0 + j * lanes;
+            if (pix >= npix) pix = npix - 1;
+            const int Y = pix / wp, X = pix - Y * wp;
+            int y = reflect_idx(Y - p, hd), x = reflect_idx(X - p, wd);
+            if (u == 2) { y >>= 1; x >>= 1; }
+            yv[j] = load8(a.y.ptr, a.y.kind, (((int64_t)n * a.y.h + y) * a.y.w + x) * a.y.c + g * 8);
+            if (a.has_res)
+                rv[j] = load8_planes(a.res.data, a.res.planes, (((int64_t)n * rhp + y + rp) * rwp + x + rp) * a.res.c + g * 8);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v.v[i] = act_fn(v.v[i], a.act, a.slope);
-        if (a.has_res) {
-            const int rp = a.res.pad, rwp = a.res.w + 2 * rp, rhp = a.res.h + 2 * rp;
-            const F8 rr = load8_planes(a.res.data, a.res.planes,
-                                       (((int64_t)n * rhp + y + rp) * rwp + x + rp) * a.res.c + g * 8);
+        for (int j = 0; j < kApplyPix; ++j) {
+            const int pix = p0 + j * lanes;
+            if (pix >= npix) break;
+            F8 v = yv[j];
+            if (a.scale != 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v.v[i] += rr.v[i];
+                for (int i = 0; i < 8; ++i) v.v[i] = v.v[i] * sc.v[i] + sf.v[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v.v[i] = act_fn(v.v[i], a.act, a.slope);
+            if (a.has_res) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v.v[i] += rv[j].v[i];
+            }
+            store8_planes(a.dst.data, a.dst.planes, ((int64_t)n * npix + pix) * a.dst.c + g * 8, v);
         }
-        store8_planes(a.dst.data, a.dst.planes, ((int64_t)n * npix + pix) * a.dst.c + g * 8, v);
     }
 }
 
@@ -412,6 +427,358 @@ __global__ void __launch_bounds__(256) block_bwd_apply_kernel(aclgan_block_bwd_a
     }
 }
 
+// ---- fast variants (every plane extent > 2 * pad + 1, so a coordinate has at most ONE reflect image) ----------------
+// All unconditional loads of a thread's K pixels are issued before any arithmetic (memory-level parallelism: these
+// kernels are pure HBM/L2 streams); the reflect images of border pixels are added under a rare, mostly warp-uniform branch.
+__device__ __forceinline__ bool mirror_of1(int c, int L, int p, int& m) {
+    if (c >= 1 && c <= p) { m = -c; return true; }
+    if (c >= L - 1 - p && c <= L - 2) { m = 2 * (L - 1) - c; return true; }
+    return false;
+}
+
+template <int U>
+__device__ __forceinline__ int64_t gp_index(const aclgan_block_bwd_args& a, int n, int cy, int cx, int g) {
+    const int p = a.gp_pad, hpp = a.h * U + 2 * p, wpp = a.w * U + 2 * p;
+    return (((int64_t)n * hpp + cy + p) * wpp + cx + p) * a.c + g * 8;
+}
+
+// adds the reflect images of the U x U source pixels of (y, x); returns false when there are none
+template <int U>
+__device__ __forceinline__ void add_mirrors(const aclgan_block_bwd_args& a, int n, int y, int x, int g, F8& acc) {
+    const int p = a.gp_pad, hu = a.h * U, wu = a.w * U;
+#pragma unroll
+    for (int da = 0; da < U; ++da) {
+        const int cy = y * U + da;
+        int my = 0;
+        const bool hy = mirror_of1(cy, hu, p, my);
+#pragma unroll
+        for (int db = 0; db < U; ++db) {
+            const int cx = x * U + db;
+            int mx = 0;
+            const bool hx = mirror_of1(cx, wu, p, mx);
+            if (hy) {
+                const F8 t = load8(a.gp, a.g_kind, gp_index<U>(a, n, my, cx, g));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc.v[i] += t.v[i];
+            }
+            if (hx) {
+                const F8 t = load8(a.gp, a.g_kind, gp_index<U>(a, n, cy, mx, g));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc.v[i] += t.v[i];
+            }
+            if (hy && hx) {
+                const F8 t = load8(a.gp, a.g_kind, gp_index<U>(a, n, my, mx, g));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc.v[i] += t.v[i];
+            }
+        }
+    }
+}
+
+template <int U>
+__device__ __forceinline__ bool has_mirrors(const aclgan_block_bwd_args& a, int y, int x) {
+    const int p = a.gp_pad, hu = a.h * U, wu = a.w * U;
+    if (p == 0) return false;
+    const int y0 = y * U, y1 = y * U + U - 1, x0 = x * U, x1 = x * U + U - 1;
+    return (y0 <= p && y1 >= 1) || (y1 >= hu - 1 - p && y0 <= hu - 2) || (x0 <= p && x1 >= 1) ||
+           (x1 >= wu - 1 - p && x0 <= wu - 2);
+}
+
+// raw 8-channel vectors as loaded (bf16: 16 B = 4 registers, fp32: 32 B), expanded to fp32 only when consumed, so the
+// K pixels a thread keeps in flight stay cheap in registers
+template <int KIND> struct Raw8;
+template <> struct Raw8<0> { uint4 q; };
+template <> struct Raw8<1> { float4 a, b; };
+
+template <int KIND>
+__device__ __forceinline__ Raw8<KIND> raw_load(uint64_t base, int64_t idx);
+template <>
+__device__ __forceinline__ Raw8<0> raw_load<0>(uint64_t base, int64_t idx) {
+    Raw8<0> r;
+    r.q = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+    return r;
+}
+template <>
+__device__ __forceinline__ Raw8<1> raw_load<1>(uint64_t base, int64_t idx) {
+    Raw8<1> r;
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    r.a = p[0]; r.b = p[1];
+    return r;
+}
+__device__ __forceinline__ F8 raw_f8(const Raw8<0>& r) {
+    F8 o;
+    const uint32_t w[4] = {r.q.x, r.q.y, r.q.z, r.q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        o.v[2 * i] = __uint_as_float(w[i] << 16);
+        o.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+    return o;
+}
+__device__ __forceinline__ F8 raw_f8(const Raw8<1>& r) {
+    F8 o;
+    o.v[0] = r.a.x; o.v[1] = r.a.y; o.v[2] = r.a.z; o.v[3] = r.a.w;
+    o.v[4] = r.b.x; o.v[5] = r.b.y; o.v[6] = r.b.z; o.v[7] = r.b.w;
+    return o;
+}
+
+// loads of one pixel that do not depend on anything else: gradient sources, raw conv output, forward output
+template <int U, int KIND>
+struct PixIn {
+    Raw8<KIND> g[U * U];
+    Raw8<KIND> gr, yv;
+    Raw8<0> ov;
+};
+
+template <int U, int KIND>
+__device__ __forceinline__ void pix_load(const aclgan_block_bwd_args& a, int n, int y, int x, int g, PixIn<U, KIND>& in) {
+    if (a.gp != 0) {
+#pragma unroll
+        for (int da = 0; da < U; ++da)
+#pragma unroll
+            for (int db = 0; db < U; ++db)
+                in.g[da * U + db] = raw_load<KIND>(a.gp, gp_index<U>(a, n, y * U + da, x * U + db, g));
+    }
+    const int64_t di = (((int64_t)n * a.h + y) * a.w + x) * a.c + g * 8;
+    if (a.gr != 0) in.gr = raw_load<KIND>(a.gr, di);
+    if (a.mask_mode == ACLGAN_MASK_FROM_Z || a.norm) in.yv = raw_load<KIND>(a.y.ptr, di);
+    if (a.mask_mode == ACLGAN_MASK_FROM_OUT) {
+        const int po = a.out.pad, wo = a.out.w + 2 * po, ho = a.out.h + 2 * po;
+        in.ov = raw_load<0>(a.out.data[0], (((int64_t)n * ho + y + po) * wo + x + po) * a.out.c + g * 8);
+    }
+}
+
+template <int U, int KIND>
+__device__ __forceinline__ void pix_dz(const aclgan_block_bwd_args& a, const BwdCoef& cf, int n, int y, int x, int g,
+                                       const PixIn<U, KIND>& in, F8& dz, F8& yhat) {
+    F8 acc = f8_zero();
+    if (a.gp != 0) {
+#pragma unroll
+        for (int k = 0; k < U * U; ++k) {
+            const F8 t = raw_f8(in.g[k]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc.v[i] += t.v[i];
+        }
+        if (has_mirrors<U>(a, y, x)) add_mirrors<U>(a, n, y, x, g, acc);
+    }
+    if (a.gr != 0) {
+        const F8 t = raw_f8(in.gr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc.v[i] += t.v[i];
+    }
+    F8 yv = f8_zero();
+    if (a.mask_mode == ACLGAN_MASK_FROM_Z || a.norm) yv = raw_f8(in.yv);
+    if (a.mask_mode == ACLGAN_MASK_FROM_Z) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float z = yv.v[i] * cf.scale.v[i] + cf.shift.v[i];
+            if (!(z > 0.f)) acc.v[i] *= a.slope;
+        }
+    } else if (a.mask_mode == ACLGAN_MASK_FROM_OUT) {
+        const F8 ov = raw_f8(in.ov);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (!(ov.v[i] > 0.f)) acc.v[i] *= a.slope;
+    }
+    dz = acc;
+    if (a.norm) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) yhat.v[i] = (yv.v[i] - cf.mean.v[i]) * cf.inv.v[i];
+    }
+}
+
+// CTA-level reduction of per-thread channel partials (s, q) -> fp64 atomics (stat != null) / fp32 atomics (dbias != null)
+__device__ __forceinline__ void cta_channel_reduce(float* red, const float (&s)[8], const float (&q)[8], int c, int g, int lane,
+                                                   int lanes, bool active, double* stat, float* dbias, int dbias_n) {
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            red[((lane * c) + g * 8 + i) * 2] = s[i];
+            red[((lane * c) + g * 8 + i) * 2 + 1] = q[i];
+        }
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float x = 0.f, y = 0.f;
+        for (int l = 0; l < lanes; ++l) { x += red[(l * c + ch) * 2]; y += red[(l * c + ch) * 2 + 1]; }
+        if (stat != nullptr) {
+            atomicAdd(&stat[ch * 2], (double)x);
+            atomicAdd(&stat[ch * 2 + 1], (double)y);
+        }
+        if (dbias != nullptr && ch < dbias_n) atomicAdd(dbias + ch, x);
+    }
+}
+
+constexpr int kBwdPix1 = 4;     // pixels per thread, no upsample
+constexpr int kBwdPix2 = 2;     // pixels per thread, 2x upsample (4 gradient sources per pixel)
+
+// per-(image, channel) coefficient rows staged in shared memory (one image per CTA): keeps ~56 registers per thread free
+// for loads in flight.  Row r of `coef` holds c floats.
+enum { CF_SCALE = 0, CF_SHIFT, CF_MEAN, CF_INV, CF_CA, CF_CB, CF_CC, CF_ROWS };
+
+__device__ __forceinline__ void stage_coefs(const aclgan_block_bwd_args& a, int n, float* coef, bool apply) {
+    const uint64_t src[CF_ROWS] = {a.mask_mode == ACLGAN_MASK_FROM_Z ? a.scale : 0, a.mask_mode == ACLGAN_MASK_FROM_Z ? a.shift : 0,
+                                   a.norm ? a.mean : 0, a.norm ? a.inv : 0, (a.norm && apply) ? a.ca : 0,
+                                   (a.norm && apply) ? a.cb : 0, (a.norm && apply) ? a.cc : 0};
+#pragma unroll
+    for (int r = 0; r < CF_ROWS; ++r) {
+        if (src[r] == 0) continue;
+        const float* p = reinterpret_cast<const float*>(src[r]) + (int64_t)n * a.c;
+        for (int i = threadIdx.x; i < a.c; i += blockDim.x) coef[r * a.c + i] = __ldg(p + i);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ F8 coef8(const float* coef, int row, int c, int g) {
+    F8 r;
+    const float4* p = reinterpret_cast<const float4*>(coef + row * c + g * 8);
+    const float4 x = p[0], y = p[1];
+    r.v[0] = x.x; r.v[1] = x.y; r.v[2] = x.z; r.v[3] = x.w;
+    r.v[4] = y.x; r.v[5] = y.y; r.v[6] = y.z; r.v[7] = y.w;
+    return r;
+}
+
+// dz (and yhat) of one pixel from its raw loads; coefficients come from shared memory
+template <int U, int KIND>
+__device__ __forceinline__ void pix_dz_s(const aclgan_block_bwd_args& a, const float* coef, int n, int y, int x, int g,
+                                         const PixIn<U, KIND>& in, F8& dz, F8& yhat) {
+    F8 acc = f8_zero();
+    if (a.gp != 0) {
+#pragma unroll
+        for (int k = 0; k < U * U; ++k) {
+            const F8 t = raw_f8(in.g[k]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc.v[i] += t.v[i];
+        }
+        if (has_mirrors<U>(a, y, x)) add_mirrors<U>(a, n, y, x, g, acc);
+    }
+    if (a.gr != 0) {
+        const F8 t = raw_f8(in.gr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc.v[i] += t.v[i];
+    }
+    F8 yv = f8_zero();
+    if (a.mask_mode == ACLGAN_MASK_FROM_Z || a.norm) yv = raw_f8(in.yv);
+    if (a.mask_mode == ACLGAN_MASK_FROM_Z) {
+        const F8 sc = coef8(coef, CF_SCALE, a.c, g), sf = coef8(coef, CF_SHIFT, a.c, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float z = yv.v[i] * sc.v[i] + sf.v[i];
+            if (!(z > 0.f)) acc.v[i] *= a.slope;
+        }
+    } else if (a.mask_mode == ACLGAN_MASK_FROM_OUT) {
+        const F8 ov = raw_f8(in.ov);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (!(ov.v[i] > 0.f)) acc.v[i] *= a.slope;
+    }
+    dz = acc;
+    if (a.norm) {
+        const F8 mu = coef8(coef, CF_MEAN, a.c, g), iv = coef8(coef, CF_INV, a.c, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) yhat.v[i] = (yv.v[i] - mu.v[i]) * iv.v[i];
+    }
+}
+
+template <int U, int KIND, int MINB>
+__global__ void __launch_bounds__(kStatThreads, MINB) block_bwd_reduce_fast(aclgan_block_bwd_args a) {
+    constexpr int K = (U == 1) ? kBwdPix1 : kBwdPix2;
+    extern __shared__ float smem_f[];
+    float* coef = smem_f;                       // [CF_ROWS][c]
+    float* red = smem_f + CF_ROWS * a.c;        // [lanes][c][2]
+    const int cg = a.c / 8;
+    const int lanes = kStatThreads / cg;
+    const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+    const int n = blockIdx.y;
+    const int hw = a.h * a.w;
+    stage_coefs(a, n, coef, false);
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    const bool active = lane < lanes;
+    if (active) {
+        for (int p0 = blockIdx.x * lanes * K + lane; p0 - lane < hw; p0 += gridDim.x * lanes * K) {
+            PixIn<U, KIND> in[K];
+            int py[K], px[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                int pix = p0 + j * lanes;
+                if (pix >= hw) pix = hw - 1;            // clamped duplicate: loaded, not counted
+                py[j] = pix / a.w; px[j] = pix - py[j] * a.w;
+                pix_load<U, KIND>(a, n, py[j], px[j], g, in[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                F8 dz, yh = f8_zero();
+                pix_dz_s<U, KIND>(a, coef, n, py[j], px[j], g, in[j], dz, yh);
+                const float wgt = (p0 + j * lanes < hw) ? 1.f : 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s[i] += wgt * dz.v[i]; q[i] += wgt * dz.v[i] * yh.v[i]; }
+            }
+        }
+    }
+    cta_channel_reduce(red, s, q, a.c, g, lane, lanes, active, reinterpret_cast<double*>(a.sums) + (int64_t)n * a.c * 2,
+                       nullptr, 0);
+}
+
+template <int U, int KIND, int MINB>
+__global__ void __launch_bounds__(kStatThreads, MINB) block_bwd_apply_fast(aclgan_block_bwd_args a) {
+    constexpr int K = (U == 1) ? kBwdPix1 : kBwdPix2;
+    extern __shared__ float smem_f[];
+    float* coef = smem_f;
+    float* red = smem_f + CF_ROWS * a.c;
+    const int pz = a.dy.pad, hz = a.h + 2 * pz, wz = a.w + 2 * pz;
+    const int cg = a.c / 8;
+    const int lanes = kStatThreads / cg;
+    const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+    const int n = blockIdx.y;
+    const int npix = hz * wz;
+    const bool active = lane < lanes;
+    stage_coefs(a, n, coef, true);
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    if (active) {
+        for (int p0 = blockIdx.x * lanes * K + lane; p0 - lane < npix; p0 += gridDim.x * lanes * K) {
+            PixIn<U, KIND> in[K];
+            int py[K], px[K];
+            bool inside[K];
+            // loads are unconditional (border / tail pixels load a clamped in-range pixel and discard it): no divergent
+            // control flow between the loads, so all of them are in flight before the first use
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int pix = p0 + j * lanes;
+                const int Y = pix / wz;
+                const int y = Y - pz, x = pix - Y * wz - pz;
+                inside[j] = pix < npix && y >= 0 && y < a.h && x >= 0 && x < a.w;
+                py[j] = min(max(y, 0), a.h - 1);
+                px[j] = min(max(x, 0), a.w - 1);
+                pix_load<U, KIND>(a, n, py[j], px[j], g, in[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int pix = p0 + j * lanes;
+                F8 dz, yh = f8_zero();
+                pix_dz_s<U, KIND>(a, coef, n, py[j], px[j], g, in[j], dz, yh);
+                F8 out;
+                if (a.norm) {
+                    const F8 ca = coef8(coef, CF_CA, a.c, g), cb = coef8(coef, CF_CB, a.c, g), cc = coef8(coef, CF_CC, a.c, g);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) out.v[i] = ca.v[i] * dz.v[i] + cb.v[i] * yh.v[i] + cc.v[i];
+                } else {
+                    out = dz;
+                }
+                const float wgt = inside[j] ? 1.f : 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { out.v[i] *= wgt; s[i] += wgt * dz.v[i]; }
+                if (pix < npix) store8_planes(a.dy.data, a.dy.planes, ((int64_t)n * npix + pix) * a.c + g * 8, out);
+            }
+        }
+    }
+    if (a.dbias != 0)      // bias gradient of a block without norm: sum of dz over (n, h, w)
+        cta_channel_reduce(red, s, q, a.c, g, lane, lanes, active, nullptr, reinterpret_cast<float*>(a.dbias), a.dbias_n);
+}
+
 __global__ void norm_bwd_finalize_kernel(aclgan_norm_bwd_finalize_args a) {
     __shared__ double sh[32];
     const int c_valid = a.c_valid;
@@ -447,9 +814,10 @@ __global__ void norm_bwd_finalize_kernel(aclgan_norm_bwd_finalize_args a) {
         if (c >= c_valid) { ca[c] = cb[c] = cc[c] = 0.f; continue; }
         double g = 1.0;
         if (a.mode == ACLGAN_NORM_ADAIN) {
-            g = reinterpret_cast<const float*>(a.w)[(int64_t)n * c_valid + c];
-            reinterpret_cast<float*>(a.dw)[(int64_t)n * c_valid + c] = (float)sums[2 * c + 1];
-            reinterpret_cast<float*>(a.db)[(int64_t)n * c_valid + c] = (float)sums[2 * c];
+            const int64_t ld = a.wb_stride > 0 ? a.wb_stride : c_valid;
+            g = reinterpret_cast<const float*>(a.w)[(int64_t)n * ld + c];
+            reinterpret_cast<float*>(a.dw)[(int64_t)n * ld + c] = (float)sums[2 * c + 1];
+            reinterpret_cast<float*>(a.db)[(int64_t)n * ld + c] = (float)sums[2 * c];
         }
         const double r = inv[c];
         ca[c] = (float)(r * g);
@@ -540,6 +908,14 @@ __global__ void pack_weight_kernel(aclgan_pack_weight_args a) {
 
 static inline int grid_for(int64_t total, int block) { return (int)((total + block - 1) / block); }
 
+// CTAs per image of the grid-stride element-wise kernels: about four CTAs per SM over all images (two resident at a
+// time), so a CTA lives long enough to amortise its prologue and the per-CTA reductions / atomics stay few
+static inline int strided_grid(int batches, int n_images) {
+    int per = (4 * num_sms() + n_images - 1) / n_images;
+    if (per < 1) per = 1;
+    return batches < per ? batches : per;
+}
+
 }  // namespace aclgan
 
 using namespace aclgan;
@@ -579,16 +955,56 @@ extern "C" int aclgan_norm_apply(const aclgan_apply_args* a, void* stream) {
     if (check_cg(a->y.c)) return ACLGAN_ERR_SHAPE;
     const int u = a->upsample, p = a->dst.pad;
     const int64_t npix = (int64_t)(a->y.h * u + 2 * p) * (a->y.w * u + 2 * p);
+    if (npix >= (1LL << 30)) return ACLGAN_ERR_SHAPE;
     const int lanes = 256 / (a->y.c / 8);
-    dim3 grid(grid_for(npix, lanes * kApplyPix), a->y.n);
+    dim3 grid(strided_grid(grid_for(npix, lanes * kApplyPix), a->y.n), a->y.n);
     norm_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
+}
+
+// register budget of the fast kernels: 1 = uncapped (about 180 registers, 8 warps / SM), 2 = capped at 128 (some spills,
+// 16 warps / SM); env ACLGAN_BWD_OCC overrides
+static int bwd_minb() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("ACLGAN_BWD_OCC");
+        v = (e != nullptr && atoi(e) == 1) ? 1 : 2;
+    }
+    return v;
+}
+
+// fast kernels: at most one reflect image per coordinate, 32-bit pixel indices
+static bool bwd_fast_ok(const aclgan_block_bwd_args* a) {
+    const int u = a->upsample, p = a->gp_pad;
+    if (u != 1 && u != 2) return false;
+    if ((a->mask_mode == ACLGAN_MASK_FROM_Z || a->norm) && a->y.kind != a->g_kind) return false;
+    if (a->gp != 0 && (a->h * u <= 2 * p + 1 || a->w * u <= 2 * p + 1)) return false;
+    if ((int64_t)(a->h + 2 * a->dy.pad) * (a->w + 2 * a->dy.pad) >= (1LL << 30)) return false;
+    return getenv("ACLGAN_BWD_GENERIC") == nullptr;
 }
 
 extern "C" int aclgan_block_bwd_reduce(const aclgan_block_bwd_args* a, void* stream) {
     if (check_cg(a->c)) return ACLGAN_ERR_SHAPE;
     const int lanes = kStatThreads / (a->c / 8);
     const int64_t hw = (int64_t)a->h * a->w;
+    if (bwd_fast_ok(a)) {
+        const int K = a->upsample == 1 ? kBwdPix1 : kBwdPix2;
+        dim3 grid(strided_grid(grid_for(hw, lanes * K), a->n), a->n);
+        const size_t smem = ((size_t)lanes * a->c * 2 + (size_t)CF_ROWS * a->c) * sizeof(float);
+        const int sel = (a->upsample == 1 ? 0 : 2) + (a->g_kind ? 1 : 0) + (bwd_minb() == 2 ? 4 : 0);
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (sel) {
+            case 0: block_bwd_reduce_fast<1, 0, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 1: block_bwd_reduce_fast<1, 1, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 2: block_bwd_reduce_fast<2, 0, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 3: block_bwd_reduce_fast<2, 1, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 4: block_bwd_reduce_fast<1, 0, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 5: block_bwd_reduce_fast<1, 1, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 6: block_bwd_reduce_fast<2, 0, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            default: block_bwd_reduce_fast<2, 1, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+        }
+        return (int)cudaGetLastError();
+    }
     dim3 grid(grid_for(hw, lanes * kStatIters), a->n);
     const size_t smem = (size_t)lanes * a->c * 2 * sizeof(float);
     block_bwd_reduce_kernel<<<grid, kStatThreads, smem, (cudaStream_t)stream>>>(*a);
@@ -599,6 +1015,25 @@ extern "C" int aclgan_block_bwd_apply(const aclgan_block_bwd_args* a, void* stre
     if (check_cg(a->c) || a->dy.c != a->c) return ACLGAN_ERR_SHAPE;
     const int64_t npix = (int64_t)(a->h + 2 * a->dy.pad) * (a->w + 2 * a->dy.pad);
     const int lanes = 256 / (a->c / 8);
+    if (bwd_fast_ok(a)) {
+        const int K = a->upsample == 1 ? kBwdPix1 : kBwdPix2;
+        dim3 grid(strided_grid(grid_for(npix, lanes * K), a->n), a->n);
+        const size_t smem = ((a->dbias != 0 ? (size_t)lanes * a->c * 2 : 0) + (size_t)CF_ROWS * a->c) * sizeof(float);
+        const int sel = (a->upsample == 1 ? 0 : 2) + (a->g_kind ? 1 : 0) + (bwd_minb() == 2 ? 4 : 0);
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (sel) {
+            case 0: block_bwd_apply_fast<1, 0, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 1: block_bwd_apply_fast<1, 1, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 2: block_bwd_apply_fast<2, 0, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 3: block_bwd_apply_fast<2, 1, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 4: block_bwd_apply_fast<1, 0, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 5: block_bwd_apply_fast<1, 1, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 6: block_bwd_apply_fast<2, 0, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            default: block_bwd_apply_fast<2, 1, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+        }
+        return (int)cudaGetLastError();
+    }
+    if (a->dbias != 0) return ACLGAN_ERR_UNSUPPORTED;     // the generic kernel has no fused bias gradient
     dim3 grid(grid_for(npix, lanes * kApplyPix), a->n);
     block_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();

@@ -10,6 +10,8 @@
 //  dgrad         : dX_pad = full correlation of the zero-bordered dY with the flipped filter, evaluated over
 //                  the flattened (pitch = stored dY width) grid so every tile is 128 consecutive pixels;
 //                  stride 2 splits into 4 output-parity phases of 2x2 taps each.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace aclgan {
@@ -71,6 +73,12 @@ static void rect_tiles(aclgan_igemm_plan* p, int wo, int ho, int n) {
 }
 
 // stored channel count of the K dimension of a packing
+// segment mode can be switched off for A/B comparisons (env ACLGAN_SEG=0): the plans then keep the box-per-tap geometry
+static bool seg_enabled() {
+    const char* e = getenv("ACLGAN_SEG");
+    return e == nullptr || atoi(e) != 0;
+}
+
 static int k_channels(const aclgan_conv_desc* cd, int transposed) {
     return round_up(transposed ? cd->cout : cd->cin, 64);
 }
@@ -131,7 +139,50 @@ extern "C" int aclgan_plan_conv_fwd(const aclgan_conv_desc* cd, const aclgan_act
     aclgan_packed_weight_shape(cd, 0, &rows, &kt);
     for (int pl = 0; pl < x->planes; ++pl) weight_map2(&p->b[pl], w[pl], kt, rows, p->block_n);
 
-    if (cd->window != ACLGAN_WINDOW_IN) {
+    if (cd->window == ACLGAN_WINDOW_NONE && s == 1 && k > 1 && k <= 8 && seg_enabled()) {
+        // stride 1: segment mode.  Tiles are 128 consecutive pixels of one output row when the rows are long enough,
+        // otherwise 128 consecutive positions of the flattened padded input grid (outputs at the k - 1 right-most
+        // columns / bottom rows of that grid are computed and dropped by the epilogue's extent check).
+        if (cs % 64 != 0 || cs != k_channels(cd, 0)) return ACLGAN_ERR_SHAPE;
+        p->cchunks = cs / 64;
+        p->num_taps = k * k;
+        p->n_avariants = 1;
+        p->seg_mode = 1;
+        p->seg_rows = round_up(128 + k - 1, 8);
+        p->num_segs = k;
+        p->seg_taps = k;
+        const bool row_tiles = (wo % 128 == 0);
+        const int64_t total = (int64_t)x->n * hp * wp;
+        if (row_tiles) {
+            p->box_x = 128; p->box_y = 1; p->box_z = 1;
+            p->tiles_x = wo / 128; p->tiles_y = ho; p->tiles_z = x->n;
+        } else {
+            p->box_x = 128; p->box_y = 1; p->box_z = 1;
+            p->tiles_x = (int)((total + 127) / 128); p->tiles_y = 1; p->tiles_z = 1;
+            p->flat = 1; p->flat_w = wp; p->flat_img = hp * wp;
+        }
+        for (int pl = 0; pl < x->planes; ++pl) {
+            if (row_tiles) {
+                plane_map4(&p->a[pl][0], x->data[pl], cs, wp, hp, x->n, px, row, img, 128, 1, 1);
+                plane_map4(&p->a_seg[pl], x->data[pl], cs, wp, hp, x->n, px, row, img, p->seg_rows, 1, 1);
+            } else {
+                plane_map4(&p->a[pl][0], x->data[pl], cs, total, 1, 1, px, total * px, total * px, 128, 1, 1);
+                plane_map4(&p->a_seg[pl], x->data[pl], cs, total, 1, 1, px, total * px, total * px, p->seg_rows, 1, 1);
+            }
+        }
+        for (int kh = 0; kh < k; ++kh) {
+            p->seg_dx[kh] = row_tiles ? 0 : kh * wp;
+            p->seg_dy[kh] = row_tiles ? kh : 0;
+            for (int kw = 0; kw < k; ++kw) {
+                const int t = kh * k + kw;
+                p->tap_dx[t] = row_tiles ? kw : kh * wp + kw;
+                p->tap_dy[t] = row_tiles ? kh : 0;
+                p->tap_var[t] = 0;
+                p->tap_bk[t] = t * cs;
+                p->tap_row[t] = kw;
+            }
+        }
+    } else if (cd->window != ACLGAN_WINDOW_IN) {
         if (cs % 64 != 0 || cs != k_channels(cd, 0)) return ACLGAN_ERR_SHAPE;
         if (k * k > ACLGAN_MAX_TAPS) return ACLGAN_ERR_UNSUPPORTED;
         p->cchunks = cs / 64;
@@ -222,7 +273,18 @@ extern "C" int aclgan_plan_conv_dgrad(const aclgan_conv_desc* cd, const aclgan_a
                 for (int kw = 0; kw < k; ++kw, ++t) {
                     p->tap_dx[t] = (k - 1 - kh) * wz + (k - 1 - kw);
                     p->tap_bk[t] = (kh * k + kw) * cs;
+                    p->tap_row[t] = k - 1 - kw;
                 }
+            if (k > 1 && k <= 8 && seg_enabled()) {
+                p->seg_mode = 1;
+                p->seg_rows = round_up(128 + k - 1, 8);
+                p->num_segs = k;
+                p->seg_taps = k;
+                for (int kh = 0; kh < k; ++kh) p->seg_dx[kh] = (k - 1 - kh) * wz;
+                for (int pl = 0; pl < dy->planes; ++pl)
+                    plane_map4(&p->a_seg[pl], dy->data[pl], cs, total, 1, 1, (int64_t)cs * 2, total * cs * 2, total * cs * 2,
+                               p->seg_rows, 1, 1);
+            }
         } else {
             for (int ph = (phase < 0 ? 0 : phase); ph <= (phase < 0 ? 3 : phase); ++ph) {
                 const int pa = ph >> 1, pb = ph & 1;

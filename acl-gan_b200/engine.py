@@ -11,6 +11,7 @@ ResBlock.forward :306-310, nn.Upsample :256, AdaptiveInstanceNorm2d.forward :490
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -62,10 +63,10 @@ class ActT:
         self.c = cs if cs is not None else round_up(c_valid, 64)
         self.planes = eng.prec.planes
         self.numel = n * (h + 2 * pad) * (w + 2 * pad) * self.c
+        # planes with fewer than 64 channels are read through pixel-window tensor maps that overrun the plane by up to
+        # 64 elements (zeroed slack); full-width planes are only ever read inside their extent (TMA zero-fills beyond)
         alloc = torch.zeros if (zero or self.c < 64 or self.c != c_valid) else torch.empty
         self.buf = alloc((self.planes, self.numel + 64), dtype=torch.bfloat16, device=eng.device)
-        if alloc is torch.empty:
-            self.buf[:, self.numel:].zero_()
         self.gp = None            # gradient of the padded plane [n, h+2p, w+2p, c] (engine gradient dtype)
         self.gr = None            # dense gradient [n, h, w, c] (residual branches / heads)
         self.requires_grad = False
@@ -102,6 +103,33 @@ class ImgT:
 
     def add_grad(self, g):
         self.grad = g if self.grad is None else self.grad.add_(g)
+
+
+class SumsPool:
+    """fp64 workspace for the per-(n, c) statistics of one update: ONE memset per update instead of one fill kernel per
+    layer.  In counting mode (buf is None) it hands out fresh zeroed tensors and records the total size."""
+
+    def __init__(self, device, numel=None):
+        self.buf = None if numel is None else torch.zeros(max(2, numel), dtype=torch.float64, device=device)
+        self.device = device
+        self.off = 0
+
+    def begin(self):
+        self.off = 0
+        if self.buf is not None:
+            self.buf.zero_()
+
+    def take(self, shape):
+        numel = 1
+        for d in shape:
+            numel *= d
+        numel = round_up(numel, 2)
+        if self.buf is None or self.off + numel > self.buf.numel():
+            self.off += numel
+            return torch.zeros(shape, dtype=torch.float64, device=self.device)
+        t = self.buf[self.off:self.off + numel].view(shape)
+        self.off += numel
+        return t
 
 
 class GradArena:
@@ -225,6 +253,13 @@ class Engine:
         N.lib()
         self.eps = 1e-5
         self.debug = None           # tests: dict collecting per-layer backward intermediates
+        self.pool = None            # SumsPool of the update being recorded (trainer), or None: per-layer zeroed tensors
+        self.fuse_stats = os.environ.get("ACLGAN_FUSE_STATS", "1") != "0"
+
+    def sums(self, n, cs):
+        if self.pool is not None:
+            return self.pool.take((n, cs, 2))
+        return torch.zeros((n, cs, 2), dtype=torch.float64, device=self.device)
 
     def _check_device(self):
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -300,12 +335,19 @@ class Engine:
         o.bias_n = bias.numel() if bias is not None else 0
         return o
 
-    def conv_fwd_launch(self, layer, x, ospec):
+    def conv_fwd_launch(self, layer, x, ospec, stats=None):
+        """stats: fp64 [n, c, 2] tensor the epilogue accumulates (sum, sum of squares) into; returns False when this
+        plan's epilogue cannot (the caller then runs the separate statistics kernel)"""
         plan = N.IgemmPlan()
         xs = x.struct()
-        N.check(N.lib().aclgan_plan_conv_fwd(C.byref(layer.desc), C.byref(xs), layer.wptr(0), C.byref(ospec),
-                                             C.byref(plan)), "plan_conv_fwd")
-        N.check(N.lib().aclgan_igemm_launch(C.byref(plan), _sp()), "igemm_launch(fwd)")
+        L = N.lib()
+        N.check(L.aclgan_plan_conv_fwd(C.byref(layer.desc), C.byref(xs), layer.wptr(0), C.byref(ospec),
+                                       C.byref(plan)), "plan_conv_fwd")
+        fused = stats is not None and self.fuse_stats and bool(L.aclgan_igemm_stats_supported(C.byref(plan)))
+        if fused:
+            plan.out.stats = stats.data_ptr()
+        N.check(L.aclgan_igemm_launch(C.byref(plan), _sp()), "igemm_launch(fwd)")
+        return fused
 
     def conv_out_hw(self, layer, x):
         hp, wp = x.h + 2 * x.pad, x.w + 2 * x.pad
@@ -349,7 +391,8 @@ class Engine:
     def conv_block(self, tape, layer, x, norm=N.NORM_NONE, act=N.ACT_NONE, out_pad=0, upsample=1, res=None,
                    adain=None, ln=None, train_w=True):
         """pad -> conv -> norm -> activation (-> + residual) -> [2x nearest upsample] -> reflect pad of the consumer.
-        adain = (weight [n,c], bias [n,c], grad holder dict) ; ln = (gamma, beta, dgamma view, dbeta view)."""
+        adain = (weight, bias, d_weight, d_bias): fp32 [n, c] views with a common row stride (slices of the MLP output
+        row and of its gradient; d_* may be None) ; ln = (gamma, beta, dgamma view, dbeta view)."""
         L = N.lib()
         ho, wo = self.conv_out_hw(layer, x)
         n, cout = x.n, layer.cout
@@ -362,17 +405,18 @@ class Engine:
         else:
             cs = round_up(cout, 64)
             y = self.new_dense(n, ho, wo, cs, zero=(cs != cout))
-            self.conv_fwd_launch(layer, x, self._out_dense(y, layer.bias))
-            sums = torch.zeros((n, cs, 2), dtype=torch.float64, device=self.device)
+            sums = self.sums(n, cs)
             y4 = self.t4(y)
-            N.check(L.aclgan_norm_stats(C.byref(y4), sums.data_ptr(), _sp()), "norm_stats")
+            if not self.conv_fwd_launch(layer, x, self._out_dense(y, layer.bias), stats=sums):
+                N.check(L.aclgan_norm_stats(C.byref(y4), sums.data_ptr(), _sp()), "norm_stats")
             coef = torch.empty((4, n, cs), dtype=torch.float32, device=self.device)   # scale, shift, mean, inv
             sigma = torch.empty((n,), dtype=torch.float32, device=self.device)
             f = N.NormFinalizeArgs()
             f.mode, f.n, f.c, f.hw, f.c_valid, f.eps = norm, n, cs, ho * wo, cout, self.eps
             f.sums = sums.data_ptr()
             if norm == N.NORM_ADAIN:
-                f.w, f.b = adain[0].data_ptr(), adain[1].data_ptr()
+                assert adain[0].stride(1) == 1 and adain[1].stride() == adain[0].stride()
+                f.w, f.b, f.wb_stride = adain[0].data_ptr(), adain[1].data_ptr(), adain[0].stride(0)
             elif norm == N.NORM_LN:
                 f.w, f.b = ln[0].data_ptr(), ln[1].data_ptr()
             f.scale, f.shift, f.mean, f.inv = (coef[i].data_ptr() for i in range(4))
@@ -409,17 +453,16 @@ class Engine:
             b.slope = 0.0 if act == N.ACT_RELU else slope
             dy = ActT(self, n, ho, wo, cout, self.dy_pad(layer))
             b.dy = dy.struct()
-            sums = torch.zeros((n, cs, 2), dtype=torch.float64, device=self.device)
-            b.sums = sums.data_ptr()
             if norm == N.NORM_NONE:
                 b.norm = 0
                 b.mask_mode = N.MASK_NONE if act == N.ACT_NONE else N.MASK_FROM_OUT
                 b.out = out.struct()
-                if train_w:
-                    N.check(L.aclgan_block_bwd_reduce(C.byref(b), _sp()), "block_bwd_reduce")
-                    layer.db().add_(sums[:, :cout, 0].sum(0).float())
+                if train_w:         # conv bias gradient = sum of dz: fused into the apply pass below
+                    b.dbias, b.dbias_n = layer.db().data_ptr(), cout
             else:
                 y, coef, sigma, fwd_s1 = saved
+                sums = self.sums(n, cs)
+                b.sums = sums.data_ptr()
                 b.norm = 1
                 b.mask_mode = N.MASK_NONE if act == N.ACT_NONE else N.MASK_FROM_Z
                 b.y = self.t4(y)
@@ -430,14 +473,13 @@ class Engine:
                 f.mode, f.n, f.c, f.hw, f.c_valid = norm, n, cs, ho * wo, cout
                 f.sums, f.inv, f.sigma = sums.data_ptr(), coef[3].data_ptr(), sigma.data_ptr()
                 if norm == N.NORM_ADAIN:
-                    dwb = torch.empty((2, n, cout), dtype=torch.float32, device=self.device)
-                    f.w, f.dw, f.db = adain[0].data_ptr(), dwb[0].data_ptr(), dwb[1].data_ptr()
+                    assert adain[2].stride() == adain[0].stride() and adain[3].stride() == adain[0].stride()
+                    f.w, f.dw, f.db = adain[0].data_ptr(), adain[2].data_ptr(), adain[3].data_ptr()
+                    f.wb_stride = adain[0].stride(0)
                 elif norm == N.NORM_LN:
                     f.w, f.dw, f.db = ln[0].data_ptr(), ln[2].data_ptr(), ln[3].data_ptr()
                 f.ca, f.cb, f.cc = (cf[i].data_ptr() for i in range(3))
                 N.check(L.aclgan_norm_bwd_finalize(C.byref(f), _sp()), "norm_bwd_finalize")
-                if norm == N.NORM_ADAIN:
-                    adain[2](dwb[0], dwb[1])        # after the launch: the sink may enqueue copies of dw / db
                 if norm == N.NORM_LN and train_w:
                     # a conv bias in front of LayerNorm is NOT cancelled (statistics span all channels):
                     # db[c] = sum_{n,hw} dy with dy = ca*dz + cb*yhat + cc:
@@ -448,7 +490,16 @@ class Engine:
                           cf[2, :, :cout].double() * hw).sum(0)
                     layer.db().add_(db.float())
                 b.ca, b.cb, b.cc = (cf[i].data_ptr() for i in range(3))
-            N.check(L.aclgan_block_bwd_apply(C.byref(b), _sp()), "block_bwd_apply")
+            rc = L.aclgan_block_bwd_apply(C.byref(b), _sp())
+            if rc == -3 and b.dbias:
+                # degenerate plane sizes (generic kernels): separate reduction for the bias gradient
+                b.dbias = 0
+                sums = self.sums(n, cs)
+                b.sums = sums.data_ptr()
+                N.check(L.aclgan_block_bwd_reduce(C.byref(b), _sp()), "block_bwd_reduce")
+                layer.db().add_(sums[:, :cout, 0].sum(0).float())
+                rc = L.aclgan_block_bwd_apply(C.byref(b), _sp())
+            N.check(rc, "block_bwd_apply")
             if self.debug is not None:
                 self.debug.setdefault(id(layer), []).append(dict(
                     dy=dy.value_nchw(), gp=None if gp is None else gp.float().clone(),

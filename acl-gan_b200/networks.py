@@ -437,25 +437,22 @@ class AdaINGen(_EngineNet):
         i_adain = 0
         for rb in m[0].model:
             for j, blk in enumerate(rb.model):
-                blkp = ap.t[:, i_adain * 2 * c:(i_adain + 1) * 2 * c]
-                bias = blkp[:, :c].contiguous()
-                weight = blkp[:, c:2 * c].contiguous()
-                if d_ap is not None:
-                    def sink(dw, db, k=i_adain):
-                        d_ap[:, k * 2 * c:k * 2 * c + c] = db
-                        d_ap[:, k * 2 * c + c:(k + 1) * 2 * c] = dw
-                else:
-                    sink = None
+                # networks.py:154-163: first c columns of the module's slice -> bias, next c -> weight; read (and their
+                # gradients written) in place, as strided views of the MLP output row / of its gradient
+                lo = i_adain * 2 * c
+                bias, weight = ap.t[:, lo:lo + c], ap.t[:, lo + c:lo + 2 * c]
+                d_bias = d_ap[:, lo:lo + c] if d_ap is not None else None
+                d_weight = d_ap[:, lo + c:lo + 2 * c] if d_ap is not None else None
                 i_adain += 1
                 last_rb = rb is m[0].model[-1] and j == 1
                 if j == 0:
                     h = eng.conv_block(tape, blk._layer, x, norm=N.NORM_ADAIN, act=act, out_pad=1,
-                                       adain=(weight, bias, sink), train_w=tw)
+                                       adain=(weight, bias, d_weight, d_bias), train_w=tw)
                 else:
                     up = 2 if (last_rb and len(m) > 2) else 1
                     nxt = m[2].spec["pad"] if (last_rb and len(m) > 2) else (m[-1].spec["pad"] if last_rb else 1)
                     x = eng.conv_block(tape, blk._layer, h, norm=N.NORM_ADAIN, act=N.ACT_NONE, out_pad=nxt,
-                                       upsample=up, res=x, adain=(weight, bias, sink), train_w=tw)
+                                       upsample=up, res=x, adain=(weight, bias, d_weight, d_bias), train_w=tw)
         ups = [b for b in m[1:-1] if isinstance(b, Conv2dBlock)]
         for i, blk in enumerate(ups):
             last = i + 1 == len(ups)

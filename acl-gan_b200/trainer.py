@@ -328,6 +328,8 @@ class aclgan_Trainer(nn.Module):
     def _gen_fwd_bwd(self, x_a, x_b, hyperparameters, zs):
         hp = hyperparameters
         self.gen_arena.zero_()
+        if self.eng.pool is not None:
+            self.eng.pool.begin()
         for d in (self.dis_A, self.dis_B, self.dis_2):
             d.train_weights = False                       # their weight grads are discarded (trainer.py:248)
         tape = E.Tape()
@@ -394,6 +396,8 @@ class aclgan_Trainer(nn.Module):
     def _dis_fwd_bwd(self, x_a, x_b, hyperparameters, zs):
         hp = hyperparameters
         self.dis_arena.zero_()
+        if self.eng.pool is not None:
+            self.eng.pool.begin()
         n = x_a.size(0)
         xa, xb = E.ImgT(x_a.detach().float()), E.ImgT(x_b.detach().float())
         # the generators only produce the fakes here: no backward pass is recorded for them (trainer.py:91)
@@ -458,7 +462,11 @@ class aclgan_Trainer(nn.Module):
         impl = self._gen_fwd_bwd if kind == "gen" else self._dis_fwd_bwd
 
         def run():
-            impl(ent["xa"], ent["xb"], hp, [E.ImgT(ent["z"][i]) for i in range(3)])
+            self.eng.pool = ent["pool"]
+            try:
+                impl(ent["xa"], ent["xb"], hp, [E.ImgT(ent["z"][i]) for i in range(3)])
+            finally:
+                self.eng.pool = None
 
         # warm-up off the capture stream (lazy initialisation of kernels / cuBLAS); forward + backward only,
         # so no parameter, optimizer or RNG state is touched
@@ -468,10 +476,12 @@ class aclgan_Trainer(nn.Module):
                     l.repack()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        ent["pool"] = E.SumsPool(dev)           # counting mode: the warm-up run measures the statistics workspace
         with torch.cuda.stream(side):
             run()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        ent["pool"] = E.SumsPool(dev, ent["pool"].off)
         before = set(k for k in vars(self) if k.startswith("loss_"))
         graph = torch.cuda.CUDAGraph()
         n0 = N.launch_count

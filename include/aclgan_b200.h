@@ -55,7 +55,8 @@ typedef struct aclgan_out_spec {
     int32_t N, H, W, C;     /* valid logical extent: rows outside are not stored; channels >= C dropped */
     uint64_t bias;          /* fp32 [bias_n] or 0 */
     int32_t bias_n;         /* channels >= bias_n get no bias (stored padding channels) */
-    uint64_t stats;         /* fp32 [N][C][2] (sum, sum of squares) accumulated with atomics, or 0 */
+    uint64_t stats;         /* double [N][C][2] (sum, sum of squares of the stored values) accumulated with atomics, or 0:
+                               the statistics pass of InstanceNorm / AdaIN / LayerNorm fused into the conv epilogue */
 } aclgan_out_spec;
 
 /* ---- implicit GEMM plan:  D[pixel][n] = sum_seg sum_tap sum_chunk A_tap[pixel][64] * B[n][k(tap,chunk) + 64] ---- */
@@ -81,6 +82,18 @@ typedef struct aclgan_igemm_plan {
     int32_t n_groups;    /* 1, or the 4 output-parity phases of a stride-2 data gradient merged into one launch */
     int32_t group_taps;  /* taps per group: group g uses taps [g*group_taps, (g+1)*group_taps) */
     int64_t group_off[4];/* element offset added to out.off for the rows of group g */
+    /* segment mode (stride-1 convolutions): the A rows of the k taps of ONE filter row are consecutive pixels, so
+     * they are staged ONCE per 64-channel chunk as a segment of seg_rows = 128 + k - 1 (rounded up to 8) pixels and
+     * tap j of the segment reads rows [tap_row, tap_row + 128) of it - k times less activation traffic from L2.
+     * Tap t belongs to segment t / seg_taps.  Executed by the segment kernel; the per-tap fields above describe the
+     * same computation for the plain kernel. */
+    int32_t seg_mode;    /* 0 | 1 */
+    int32_t seg_rows;    /* pixels per staged segment (multiple of 8, <= 256) */
+    int32_t num_segs;    /* segments per 64-channel chunk (= filter rows) */
+    int32_t seg_taps;    /* taps per segment (= filter columns) */
+    int32_t seg_dx[16], seg_dy[16]; /* box offset of segment s relative to the tile origin (like tap_dx / tap_dy) */
+    int32_t tap_row[ACLGAN_MAX_TAPS]; /* first segment row of tap t */
+    aclgan_tmap_spec a_seg[2];        /* [plane] the variant-0 map with a seg_rows-pixel box */
     aclgan_out_spec out;
 } aclgan_igemm_plan;
 
@@ -147,6 +160,8 @@ int aclgan_wgrad_layout(const aclgan_conv_desc* cd);
 
 /* launches (networks.py:363,366 Conv2d forward; autograd of it for dgrad / wgrad) */
 int aclgan_igemm_launch(const aclgan_igemm_plan* plan, void* stream);
+/* 1 when the epilogue of this plan can accumulate out.stats (otherwise run aclgan_norm_stats on the output) */
+int aclgan_igemm_stats_supported(const aclgan_igemm_plan* plan);
 int aclgan_wgrad_launch(const aclgan_wgrad_plan* plan, void* stream);
 /* same plan launched `repeat` times back to back (tensor maps encoded once): device-side kernel timing */
 int aclgan_igemm_launch_repeat(const aclgan_igemm_plan* plan, int repeat, void* stream);
@@ -193,6 +208,8 @@ typedef struct aclgan_norm_finalize_args {
     uint64_t scale, shift;  /* out fp32 [n][c] */
     uint64_t mean, inv;     /* out fp32 [n][c] (LN: broadcast per sample) */
     uint64_t sigma;         /* out fp32 [n] (LN only: the unbiased std) */
+    int64_t wb_stride;      /* ADAIN: elements between consecutive samples of w / b (0 = c_valid): the parameters are read
+                               in place from the MLP output row (networks.py:154-163 slices, never copied) */
 } aclgan_norm_finalize_args;
 int aclgan_norm_finalize(const aclgan_norm_finalize_args* a, void* stream);
 
@@ -231,6 +248,8 @@ typedef struct aclgan_block_bwd_args {
     uint64_t sums;          /* double [n][c][2]: T1, T2 (written by reduce) */
     uint64_t ca, cb, cc;    /* fp32 [n][c] (read by apply when norm) */
     aclgan_act dy;          /* apply output, dy.pad = zero border */
+    uint64_t dbias;         /* apply, blocks without norm: fp32 [dbias_n] += sum over (n,h,w) of dz (conv bias gradient), or 0 */
+    int32_t dbias_n;
 } aclgan_block_bwd_args;
 int aclgan_block_bwd_reduce(const aclgan_block_bwd_args* a, void* stream);
 int aclgan_block_bwd_apply(const aclgan_block_bwd_args* a, void* stream);
@@ -244,6 +263,7 @@ typedef struct aclgan_norm_bwd_finalize_args {
     uint64_t w;             /* ADAIN: fp32 [n][c] weight; LN: fp32 [c] gamma */
     uint64_t ca, cb, cc;    /* out fp32 [n][c] */
     uint64_t dw, db;        /* out: ADAIN fp32 [n][c] (assigned); LN fp32 [c] (accumulated: +=) ; IN unused */
+    int64_t wb_stride;      /* ADAIN: sample stride of w, dw and db in elements (0 = c_valid) */
 } aclgan_norm_bwd_finalize_args;
 int aclgan_norm_bwd_finalize(const aclgan_norm_bwd_finalize_args* a, void* stream);
 

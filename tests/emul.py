@@ -73,8 +73,14 @@ def _act(v, act, slope):
     return v
 
 
-def run_igemm(mem, plan):
-    """Executes an IgemmPlan on CPU buffers registered in `mem` (writes the output buffers in place)."""
+def run_igemm(mem, plan, use_seg=None):
+    """Executes an IgemmPlan on CPU buffers registered in `mem` (writes the output buffers in place).
+    use_seg: execute the segment description of the plan (what igemm_seg_kernel does: one staged block of seg_rows
+    pixels per filter row and chunk, taps = row-shifted 128-row windows of it) instead of the box-per-tap one;
+    default: whenever the plan has one."""
+    if use_seg is None:
+        use_seg = bool(plan.seg_mode)
+    assert not use_seg or (plan.seg_mode and plan.num_segs * plan.seg_taps == plan.num_taps)
     o = plan.out
     outs = []
     nplanes_out = 2 if o.kind == N.OUT_SPLIT else 1
@@ -96,6 +102,17 @@ def run_igemm(mem, plan):
                 for nt in range(plan.n_tiles):
                     acc = torch.zeros(128, bn, dtype=torch.float64)
                     for pa, pb in segs:
+                        if use_seg:
+                            for cc in range(plan.cchunks):
+                                for sg in range(plan.num_segs):
+                                    S = tma_box(mem, plan.a_seg[pa], (cc * 64, x0 + plan.seg_dx[sg], y0 + plan.seg_dy[sg], z0))
+                                    S = S.reshape(plan.seg_rows, 64)
+                                    for j in range(plan.seg_taps):
+                                        t = sg * plan.seg_taps + j
+                                        A = S[plan.tap_row[t]:plan.tap_row[t] + 128]
+                                        B = tma_box(mem, plan.b[pb], (plan.tap_bk[t] + cc * 64, nt * bn)).reshape(bn, 64)
+                                        acc += A @ B.t()
+                            continue
                         for t in range(grp * gtaps, (grp + 1) * gtaps):
                             am = plan.a[pa][plan.tap_var[t]]
                             for cc in range(plan.cchunks):

@@ -90,8 +90,11 @@ def test_conv_block(precision, cin, cout, k, stride, pad, norm, act, use_res, up
     ra = plane_from_nchw(eng, res, 1) if use_res else None
     if ra is not None:
         ra.requires_grad = True
-    got_adain = {}
-    adain = (adain_w, adain_b, lambda dw, db: got_adain.update(dw=dw, db=db)) if norm == N.NORM_ADAIN else None
+    # AdaIN parameters / gradients as strided column slices of one row per sample (how AdaINGen.decode passes them)
+    ap = torch.cat((adain_b, adain_w), 1)
+    d_ap = torch.zeros_like(ap)
+    got_adain = dict(dw=d_ap[:, cout:], db=d_ap[:, :cout])
+    adain = (ap[:, cout:], ap[:, :cout], got_adain["dw"], got_adain["db"]) if norm == N.NORM_ADAIN else None
     ln = (gamma, beta, arena.view(ln_off[0], cout), arena.view(ln_off[1], cout)) if norm == N.NORM_LN else None
     tape = E.Tape()
     out = eng.conv_block(tape, layer, xa, norm=norm, act=act, out_pad=out_pad, upsample=upsample, res=ra,

@@ -56,6 +56,8 @@ FWD_CASES = [
     (6, 16, 4, 2, 1, 1, 2, 8, 8, 1),
     (64, 4, 7, 1, 3, 0, 1, 8, 8, 1),
     (64, 48, 4, 2, 1, 0, 1, 2, 2, 1),
+    (64, 64, 5, 1, 2, 0, 1, 3, 128, 1),        # row tiles (128-pixel output rows) in segment mode
+    (128, 16, 3, 1, 1, 0, 2, 3, 128, 2),
 ]
 
 
@@ -81,16 +83,20 @@ def test_conv_fwd_plan(cin, cout, k, s, pad, window, n, h, w, planes):
     o, obuf = out_spec(mem, n, ho, wo, cout, N.OUT_F32, pad=1, act=N.ACT_LRELU, bias=bias, mirror=1)
     plan = N.IgemmPlan()
     N.check(L.aclgan_plan_conv_fwd(C.byref(desc), C.byref(act), wptr, C.byref(o), C.byref(plan)), "plan fwd")
-    emul.run_igemm(mem, plan)
-    ref = F.conv2d(xeff, weff, bias.double(), stride=s)
-    ref = F.leaky_relu(ref, 0.2)
-    ref = F.pad(ref, (1, 1, 1, 1), mode="reflect") if min(ho, wo) > 1 else None
-    got = obuf[0].permute(0, 3, 1, 2).double()
-    if ref is None:
-        ref = F.leaky_relu(F.conv2d(xeff, weff, bias.double(), stride=s), 0.2)
-        got = got[:, :, 1:-1, 1:-1]
-    tol = 1e-6 if planes == 1 else 2e-4
-    assert torch.allclose(got, ref, rtol=tol, atol=tol), float((got - ref).abs().max())
+    assert bool(plan.seg_mode) == (s == 1 and not window and k > 1)
+    # the box-per-tap description (plain kernels) and, when present, the segment description (igemm_seg_kernel)
+    for use_seg in ([False, True] if plan.seg_mode else [False]):
+        obuf.zero_()
+        emul.run_igemm(mem, plan, use_seg=use_seg)
+        ref = F.conv2d(xeff, weff, bias.double(), stride=s)
+        ref = F.leaky_relu(ref, 0.2)
+        ref = F.pad(ref, (1, 1, 1, 1), mode="reflect") if min(ho, wo) > 1 else None
+        got = obuf[0].permute(0, 3, 1, 2).double()
+        if ref is None:
+            ref = F.leaky_relu(F.conv2d(xeff, weff, bias.double(), stride=s), 0.2)
+            got = got[:, :, 1:-1, 1:-1]
+        tol = 1e-6 if planes == 1 else 2e-4
+        assert torch.allclose(got, ref, rtol=tol, atol=tol), (use_seg, float((got - ref).abs().max()))
 
 
 DGRAD_CASES = [
@@ -130,6 +136,7 @@ def test_conv_dgrad_plan(cin, cout, k, s, pad, n, ho, wo, planes):
     obuf = torch.zeros(n, hp, wp, cin_s, dtype=torch.float32)
     optr = mem.add(obuf)
     merged = (s == 2 and n % 2 == 0)          # even batch sizes exercise the single-launch (4 phases merged) plan
+    seg_pass = (s == 1 and not window)        # stride-1 regular layouts: run the segment description of the plan
     for phase in ([-1] if merged else range(1 if s == 1 else 4)):
         o = N.OutSpec()
         o.ptr[0] = optr
@@ -140,7 +147,14 @@ def test_conv_dgrad_plan(cin, cout, k, s, pad, n, ho, wo, planes):
         o.N, o.H, o.W, o.C = n, hp // s, wp // s, cin_s
         plan = N.IgemmPlan()
         N.check(L.aclgan_plan_conv_dgrad(C.byref(desc), C.byref(act), wptr, phase, C.byref(o), C.byref(plan)), "plan dgrad")
+        assert bool(plan.seg_mode) == seg_pass
+        if seg_pass:
+            emul.run_igemm(mem, plan, use_seg=False)
+            first = obuf.clone()
+            obuf.zero_()
         emul.run_igemm(mem, plan)
+        if seg_pass:
+            assert torch.equal(first, obuf) or torch.allclose(first, obuf, rtol=1e-6, atol=1e-6)
     ref = F.conv_transpose2d(dyeff, weff, stride=s)            # gradient w.r.t. the padded input
     got = obuf.permute(0, 3, 1, 2).double()[:, :cin]
     tol = 1e-6 if planes == 1 else 2e-4

@@ -1,0 +1,53 @@
+"""Kernel timeline of ONE graph-replayed step-pair through torch.profiler (CUPTI): real in-graph kernel durations and
+the idle gaps between kernels (what ncu's serialised cold-cache launch list cannot show).
+usage (GPU box): python tools/trace_step.py > gpurun_out/trace.txt"""
+import collections
+import copy
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "acl-gan_b200"))
+import torch  # noqa: E402
+import yaml  # noqa: E402
+import trainer as T  # noqa: E402
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+cfg = yaml.safe_load(open(os.path.join(ROOT, "acl-gan_b200", "configs", "male2female.yaml")))
+cfg["precision"] = "bf16"
+torch.manual_seed(0)
+tr = T.aclgan_Trainer(cfg).cuda()
+b = int(os.environ.get("BATCH", "8"))
+xa = torch.rand(b, 3, 256, 256, device="cuda") * 2 - 1
+xb = torch.rand(b, 3, 256, 256, device="cuda") * 2 - 1
+for _ in range(3):
+    tr.dis_update(xa, xb, cfg)
+    tr.gen_update(xa, xb, cfg)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    tr.dis_update(xa, xb, cfg)
+    tr.gen_update(xa, xb, cfg)
+    torch.cuda.synchronize()
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs), key=lambda t: t[0])
+agg = collections.defaultdict(lambda: [0, 0.0])
+busy, gaps, last_end = 0.0, 0.0, None
+gap_after = collections.defaultdict(float)
+for s, e, name in ks:
+    k = name.split("(")[0][:60]
+    agg[k][0] += 1
+    agg[k][1] += e - s
+    if last_end is not None and s > last_end:
+        gaps += s - last_end
+        gap_after[prev] += s - last_end
+    busy += e - s
+    if last_end is None or e > last_end:
+        last_end, prev = e, k
+span = ks[-1][1] - ks[0][0]
+print("kernels %d  span %.2f ms  sum of kernel time %.2f ms  idle gaps %.2f ms" % (len(ks), span / 1e3, busy / 1e3, gaps / 1e3))
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+    print("%6d %9.3f ms %5.1f%%  avg %7.1f us  gap-after %7.3f ms  %s" % (v[0], v[1] / 1e3, 100 * v[1] / span, v[1] / v[0], gap_after[k] / 1e3, k))
+# the longest individual kernels
+print("-- longest launches")
+for s, e, name in sorted(ks, key=lambda t: t[0] - t[1])[:25]:
+    print("%9.1f us  %s" % (e - s, name[:100]))

@@ -47,13 +47,37 @@ struct alignas(64) IgemmKParams {
     int tap_bk[ACLGAN_MAX_TAPS];
     // segment mode (igemm_seg_kernel)
     CUtensorMap a_seg[2];
+    CUtensorMap b_seg[2];                           // rank 3 (k element, weight row, tap): box = 64 x rows x seg_taps
     int seg_rows, num_segs, seg_taps;
-    int seg_a_bytes, seg_b_bytes, seg_na, seg_nb;   // shared-memory ring geometry chosen by the host
+    int seg_a_bytes, seg_btile_bytes, seg_stage_bytes, seg_ns;   // shared-memory ring geometry chosen by the host
     int seg_bo;                                     // 1: descriptors carry the matrix base offset of the shifted start row
+    int epi_direct;
+    long long* prof;                                // perf triage: per-CTA role timers [cta][8] (clock cycles) or null
     int seg_dx[16], seg_dy[16];
     int tap_row[ACLGAN_MAX_TAPS];
     aclgan_out_spec out;
 };
+
+// What the epilogue needs, BY VALUE: the non-inlined epilogue functions must not dereference the kernel parameter
+// struct through a pointer (that turns every field access into a generic load from the constant window - hundreds of
+// cycles each, in the middle of the unrolled conversion loops)
+struct EpiArgs {
+    uint64_t ptr0, ptr1, bias, stats;
+    int64_t sy, sx, sc;
+    int kind, act, mirror, N, C, bias_n, block_n;
+    float slope;
+    int direct;      // 1: registers -> global without shared-memory staging / shuffles (perf triage, env ACLGAN_EPI_DIRECT)
+};
+
+__device__ __forceinline__ EpiArgs make_epi_args(const IgemmKParams& P) {
+    EpiArgs e;
+    e.ptr0 = P.out.ptr[0]; e.ptr1 = P.out.ptr[1]; e.bias = P.out.bias; e.stats = P.out.stats;
+    e.sy = P.out.sy; e.sx = P.out.sx; e.sc = P.out.sc;
+    e.kind = P.out.kind; e.act = P.out.act; e.mirror = P.out.mirror; e.N = P.out.N; e.C = P.out.C;
+    e.bias_n = P.out.bias_n; e.block_n = P.block_n; e.slope = P.out.slope;
+    e.direct = P.epi_direct;
+    return e;
+}
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     if (act == ACLGAN_ACT_RELU) return fmaxf(v, 0.f);
@@ -88,10 +112,10 @@ struct RowCtx {
 };
 
 // ---- generic (cold) path: any output kind / stride / partial channel count; scalar, rolled loops (small code) ----
-__device__ __noinline__ void store_generic(const aclgan_out_spec& o, int64_t pix, int ch0, int cnt, const float* v) {
+__device__ __noinline__ void store_generic(const EpiArgs o, int64_t pix, int ch0, int cnt, const float* v) {
     if (o.kind == ACLGAN_OUT_BF16 || o.kind == ACLGAN_OUT_SPLIT) {
-        __nv_bfloat16* d0 = reinterpret_cast<__nv_bfloat16*>(o.ptr[0]) + pix + (int64_t)ch0 * o.sc;
-        __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(o.ptr[1]) + pix + (int64_t)ch0 * o.sc;
+        __nv_bfloat16* d0 = reinterpret_cast<__nv_bfloat16*>(o.ptr0) + pix + (int64_t)ch0 * o.sc;
+        __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(o.ptr1) + pix + (int64_t)ch0 * o.sc;
 #pragma unroll 1
         for (int i = 0; i < cnt; ++i) {
             const __nv_bfloat16 hi = __float2bfloat16_rn(v[i]);
@@ -99,7 +123,7 @@ __device__ __noinline__ void store_generic(const aclgan_out_spec& o, int64_t pix
             if (o.kind == ACLGAN_OUT_SPLIT) d1[(int64_t)i * o.sc] = __float2bfloat16_rn(v[i] - __bfloat162float(hi));
         }
     } else {
-        float* d = reinterpret_cast<float*>(o.ptr[0]) + pix + (int64_t)ch0 * o.sc;
+        float* d = reinterpret_cast<float*>(o.ptr0) + pix + (int64_t)ch0 * o.sc;
 #pragma unroll 1
         for (int i = 0; i < cnt; ++i) {
             if (o.kind == ACLGAN_OUT_F32_ATOMIC) atomicAdd(d + (int64_t)i * o.sc, v[i]);
@@ -108,12 +132,11 @@ __device__ __noinline__ void store_generic(const aclgan_out_spec& o, int64_t pix
     }
 }
 
-__device__ __noinline__ void epilogue_tile_generic(const IgemmKParams& P, uint32_t t_row, int n0, const RowCtx& rc) {
-    const aclgan_out_spec& o = P.out;
+__device__ __noinline__ void epilogue_tile_generic(const EpiArgs o, uint32_t t_row, int n0, const RowCtx& rc) {
     const float* bias = reinterpret_cast<const float*>(o.bias);
-    const int step = P.block_n >= 32 ? 32 : 16;
+    const int step = o.block_n >= 32 ? 32 : 16;
 #pragma unroll 1
-    for (int c = 0; c < P.block_n; c += step) {
+    for (int c = 0; c < o.block_n; c += step) {
         uint32_t raw[32];
         if (step == 32) {
             tmem_ld_32x32(t_row + c, raw);
@@ -155,7 +178,7 @@ __device__ __forceinline__ void stage_piece(uint8_t* stg, int lane, int piece, c
 
 // staged 32 rows x 128 B -> global memory as full 128-byte lines (4 rows per store instruction), then the reflect-halo
 // replicas of border pixels (each lane copies its own row again, read back from the staging tile)
-__device__ __forceinline__ void flush_rows(const aclgan_out_spec& o, const uint8_t* stg, uint8_t* base, int64_t row_byte_off,
+__device__ __noinline__ void flush_rows(const int64_t o_sy, const int64_t o_sx, const uint8_t* stg, uint8_t* base, int64_t row_byte_off,
                                            const RowCtx& rc, int esz, int lane) {
     __syncwarp();
     const int piece = lane & 7;
@@ -175,7 +198,7 @@ __device__ __forceinline__ void flush_rows(const aclgan_out_spec& o, const uint8
 #pragma unroll 1
             for (int ix = (iy == 0 ? 1 : 0); ix < rc.nx; ++ix) {
                 uint8_t* dst = base + row_byte_off +
-                               ((int64_t)(rc.ys[iy] - rc.y) * o.sy + (int64_t)(rc.xs[ix] - rc.x) * o.sx) * esz;
+                               ((int64_t)(rc.ys[iy] - rc.y) * o_sy + (int64_t)(rc.xs[ix] - rc.x) * o_sx) * esz;
 #pragma unroll
                 for (int pc = 0; pc < 8; ++pc)
                     *reinterpret_cast<uint4*>(dst + (pc << 4)) =
@@ -222,9 +245,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 // combine != 0: the tile's rows belong to image n_first (set 0) and, when `straddle`, n_first + 1 (set 1); the four warps
 // are summed first (4x fewer atomics).  combine == 0 (tiny planes, several images per tile): every warp's 32 rows
 // belong to the single image n_first (the host guarantees box_x * box_y % 32 == 0) and the warp adds its own slots.
-__device__ __forceinline__ void stats_tile_end(const IgemmKParams& P, uint8_t* stage_out, int q, int lane, int n0, bool combine,
+__device__ __forceinline__ void stats_tile_end(const EpiArgs& o, uint8_t* stage_out, int q, int lane, int n0, bool combine,
                                                int n_first, bool straddle, bool tile_ok) {
-    const aclgan_out_spec& o = P.out;
     double* stats = reinterpret_cast<double*>(o.stats);
     if (combine) {
         named_bar_sync(1, 128);
@@ -232,7 +254,7 @@ __device__ __forceinline__ void stats_tile_end(const IgemmKParams& P, uint8_t* s
             for (int set = 0; set < (straddle ? 2 : 1); ++set) {
                 const int n = n_first + set;
                 if (n >= o.N) break;
-                for (int ch = q * 32 + lane; ch < P.block_n; ch += 128) {
+                for (int ch = q * 32 + lane; ch < o.block_n; ch += 128) {
                     float s = 0.f, qq = 0.f;
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
@@ -250,7 +272,7 @@ __device__ __forceinline__ void stats_tile_end(const IgemmKParams& P, uint8_t* s
         __syncwarp();
         if (tile_ok && n_first < o.N) {
             const float* red = reinterpret_cast<const float*>(stage_out + q * 8192 + 4096);
-            for (int ch = lane; ch < P.block_n; ch += 32) {
+            for (int ch = lane; ch < o.block_n; ch += 32) {
                 double* d = stats + ((int64_t)n_first * o.C + n0 + ch) * 2;
                 atomicAdd(d, (double)red[ch * 2]);
                 atomicAdd(d + 1, (double)red[ch * 2 + 1]);
@@ -286,82 +308,145 @@ __device__ __forceinline__ StatCtx make_stat_ctx(const IgemmKParams& P, int tx, 
     return sc;
 }
 
-__device__ __noinline__ void epilogue_tile_fast(const IgemmKParams& P, uint32_t t_row, int n0, const RowCtx& rc, uint8_t* stg,
-                                                int lane, int stat_rb) {
-    const aclgan_out_spec& o = P.out;
+// one 32-column chunk of the accumulator row: bias, activation, conversion, staging, and - once a full 128-byte row
+// segment is staged - statistics and the global stores
+__device__ __forceinline__ void epilogue_chunk(const EpiArgs& o, int c, const uint32_t (&raw)[32], float bl, int n0,
+                                               const RowCtx& rc, uint8_t* stg, int lane, int stat_rb) {
     const bool f32 = (o.kind == ACLGAN_OUT_F32);
     const bool st = o.stats != 0;
     const int esz = f32 ? 4 : 2;
-    const float* bias = reinterpret_cast<const float*>(o.bias);
-#pragma unroll 1
-    for (int c = 0; c < P.block_n; c += 32) {
-        uint32_t raw[32];
-        tmem_ld_32x32(t_row + c, raw);
-        const int ch0 = n0 + c;
-        // one bias value per lane, broadcast with shuffles (instead of 32 loads per thread)
-        float bl = 0.f;
-        if (bias != nullptr && ch0 + lane < o.bias_n) bl = __ldg(bias + ch0 + lane);
-        tmem_ld_wait();
-        float v[32];
+    const int ch0 = n0 + c;
+    float v[32];
+    if (o.direct && o.kind == ACLGAN_OUT_BF16 && !st && o.mirror == 0) {
+        // no shared memory at all: broadcast bias loads, each lane stores its own row's 64 bytes
+        const float4* bp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(o.bias) + ch0);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) + __shfl_sync(0xffffffffu, bl, i);
+        for (int i = 0; i < 8; ++i) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (o.bias != 0 && ch0 + 4 * i + 3 < o.bias_n) b4 = __ldg(bp + i);
+            v[4 * i] = __uint_as_float(raw[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + b4.y;
+            v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + b4.w;
+        }
         if (o.act == ACLGAN_ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         } else if (o.act == ACLGAN_ACT_LRELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * o.slope;
-        } else if (o.act == ACLGAN_ACT_TANH) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
         }
-        if (st && !rc.valid) {
+        if (rc.valid) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(o.ptr0) + rc.pix0 + ch0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;       // rows outside the output contribute nothing to the statistics
+            for (int i = 0; i < 4; ++i) {
+                uint4 qv;
+                qv.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); qv.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+                qv.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); qv.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+                dst[i] = qv;
+            }
         }
-        if (rc.valid || st) {
-            if (f32) {
+        return;
+    }
+    // bias: every lane needs the same 32 values -> broadcast loads (one L1 transaction each; shuffles would go through the
+    // shared-memory crossbar, which the tensor core's operand reads keep busy)
+    if (o.bias != 0 && ch0 + 31 < o.bias_n) {
+        const float4* bp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(o.bias) + ch0);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    uint4 qv;
-                    qv.x = __float_as_uint(v[4 * i]); qv.y = __float_as_uint(v[4 * i + 1]);
-                    qv.z = __float_as_uint(v[4 * i + 2]); qv.w = __float_as_uint(v[4 * i + 3]);
-                    stage_piece(stg, lane, i, qv);
-                }
-            } else {
-                const int piece0 = (c & 32) ? 4 : 0;
+        for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(bp + i);
+            v[4 * i] = __uint_as_float(raw[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + b4.y;
+            v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + b4.w;
+        }
+    } else if (o.bias != 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) + __shfl_sync(0xffffffffu, bl, i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+    }
+    if (o.act == ACLGAN_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else if (o.act == ACLGAN_ACT_LRELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * o.slope;
+    }
+    if (st && !rc.valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;       // rows outside the output contribute nothing to the statistics
+    }
+    if (rc.valid || st) {
+        if (f32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint4 qv;
+                qv.x = __float_as_uint(v[4 * i]); qv.y = __float_as_uint(v[4 * i + 1]);
+                qv.z = __float_as_uint(v[4 * i + 2]); qv.w = __float_as_uint(v[4 * i + 3]);
+                stage_piece(stg, lane, i, qv);
+            }
+        } else {
+            const int piece0 = (c & 32) ? 4 : 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint4 qv;
+                qv.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); qv.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+                qv.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); qv.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+                stage_piece(stg, lane, piece0 + i, qv);
+            }
+            if (o.kind == ACLGAN_OUT_SPLIT) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint4 qv;
                     qv.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); qv.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
                     qv.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); qv.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                    stage_piece(stg, lane, piece0 + i, qv);
-                }
-                if (o.kind == ACLGAN_OUT_SPLIT) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 qv;
-                        qv.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); qv.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                        qv.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); qv.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                        stage_piece(stg + 4096, lane, piece0 + i, qv);
-                    }
+                    stage_piece(stg + 4096, lane, piece0 + i, qv);
                 }
             }
-        }
-        if (f32 || (c & 32)) {      // a full 128-byte row segment is staged: 32 fp32 or 64 bf16 channels
-            const int g0 = f32 ? ch0 : ch0 - 32;
-            const int64_t row_off = (rc.pix0 + g0) * esz;
-            if (st) {
-                __syncwarp();
-                stage_colsums(stg, reinterpret_cast<float*>(stg + 4096), g0 - n0, f32, lane, stat_rb);
-            }
-            flush_rows(o, stg, reinterpret_cast<uint8_t*>(o.ptr[0]), row_off, rc, esz, lane);
-            if (o.kind == ACLGAN_OUT_SPLIT)
-                flush_rows(o, stg + 4096, reinterpret_cast<uint8_t*>(o.ptr[1]), row_off, rc, esz, lane);
         }
     }
+    if (f32 || (c & 32)) {      // a full 128-byte row segment is staged: 32 fp32 or 64 bf16 channels
+        const int g0 = f32 ? ch0 : ch0 - 32;
+        const int64_t row_off = (rc.pix0 + g0) * esz;
+        if (st) {
+            __syncwarp();
+            stage_colsums(stg, reinterpret_cast<float*>(stg + 4096), g0 - n0, f32, lane, stat_rb);
+        }
+        flush_rows(o.sy, o.sx, stg, reinterpret_cast<uint8_t*>(o.ptr0), row_off, rc, esz, lane);
+        if (o.kind == ACLGAN_OUT_SPLIT)
+            flush_rows(o.sy, o.sx, stg + 4096, reinterpret_cast<uint8_t*>(o.ptr1), row_off, rc, esz, lane);
+    }
+}
+
+// Software-pipelined over 32-column chunks: the TMEM load (and the bias load) of the next chunk is in flight while the
+// current one is converted and stored - a single warp has no other source of latency hiding here.
+__device__ __noinline__ void epilogue_tile_fast(const EpiArgs o, uint32_t t_row, int n0, const RowCtx& rc, uint8_t* stg,
+                                                int lane, int stat_rb, long long* pt = nullptr) {
+    const float* bias = reinterpret_cast<const float*>(o.bias);
+    const long long pt0 = pt ? clock64() : 0;
+    long long pt_ld = 0, pt_chunk = 0;
+    // one copy of the chunk code (instruction-cache footprint: the epilogue is otherwise fetch-bound): the next chunk's
+    // TMEM / bias loads are issued into `nxt`, moved to `cur` (32 register moves) when they have landed
+    uint32_t cur[32], nxt[32];
+    float bl_cur, bl_nxt = 0.f;
+    tmem_ld_32x32(t_row, nxt);
+    if (bias != nullptr && n0 + lane < o.bias_n) bl_nxt = __ldg(bias + n0 + lane);
+#pragma unroll 1
+    for (int c = 0; c < o.block_n; c += 32) {
+        long long t1 = pt ? clock64() : 0;
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
+        bl_cur = bl_nxt;
+        if (c + 32 < o.block_n) {
+            tmem_ld_32x32(t_row + c + 32, nxt);
+            bl_nxt = (bias != nullptr && n0 + c + 32 + lane < o.bias_n) ? __ldg(bias + n0 + c + 32 + lane) : 0.f;
+        }
+        if (pt) { const long long t2 = clock64(); pt_ld += t2 - t1; t1 = t2; }
+        epilogue_chunk(o, c, cur, bl_cur, n0, rc, stg, lane, stat_rb);
+        if (pt) pt_chunk += clock64() - t1;
+    }
+    if (pt && lane == 0) { pt[0] += clock64() - pt0; pt[1] += pt_ld; pt[2] += pt_chunk; }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmKParams P) {
@@ -508,6 +593,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         const int q = warp & 3;              // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;
         const aclgan_out_spec& o = P.out;
+        const EpiArgs ea = make_epi_args(P);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it % acc_sets;
@@ -547,12 +633,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 const int n0 = nt * P.block_n;
                 const int group = (o.kind == ACLGAN_OUT_F32) ? 32 : 64;
                 const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) &&
-                                  (n0 + P.block_n <= o.C) && (P.debug != 5);
+                                  (n0 + P.block_n <= o.C) && (o.act != ACLGAN_ACT_TANH) && (P.debug != 5);
                 StatCtx sc;
                 if (o.stats != 0) sc = make_stat_ctx(P, tx, tz, q, lane, rc);
-                if (fast) epilogue_tile_fast(P, t_row, n0, rc, stage_out + q * 8192, lane, o.stats != 0 ? sc.rb : 32);
-                else epilogue_tile_generic(P, t_row, n0, rc);
-                if (o.stats != 0) stats_tile_end(P, stage_out, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
+                if (fast) epilogue_tile_fast(ea, t_row, n0, rc, stage_out + q * 8192, lane, o.stats != 0 ? sc.rb : 32);
+                else epilogue_tile_generic(ea, t_row, n0, rc);
+                if (o.stats != 0) stats_tile_end(ea, stage_out, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
             }
             tc_fence_before();
             __syncwarp();
@@ -704,6 +790,7 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const aclgan_out_spec& o = P.out;
+        const EpiArgs ea = make_epi_args(P);
         int it = 0;
         for (int item = cluster_id; item < total_items; item += n_clusters, ++it) {
             const int acc = it & 1;
@@ -743,9 +830,9 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
                                   (n0 + P.block_n <= o.C);
                 StatCtx sc;
                 if (o.stats != 0) sc = make_stat_ctx(P, tx, tz, q, lane, rc);
-                if (fast) epilogue_tile_fast(P, t_row, n0, rc, stage_out + q * 8192, lane, o.stats != 0 ? sc.rb : 32);
-                else epilogue_tile_generic(P, t_row, n0, rc);
-                if (o.stats != 0) stats_tile_end(P, stage_out, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
+                if (fast) epilogue_tile_fast(ea, t_row, n0, rc, stage_out + q * 8192, lane, o.stats != 0 ? sc.rb : 32);
+                else epilogue_tile_generic(ea, t_row, n0, rc);
+                if (o.stats != 0) stats_tile_end(ea, stage_out, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
             }
             tc_fence_before();
             __syncwarp();
@@ -772,26 +859,42 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
 // per filter row and chunk) and B weight tiles (one per tap).
 // Templated on PAIR: cta_group::2 (two CTAs, 256-pixel tile, B split in halves) or one CTA.
 // =====================================================================================================================
-constexpr int kSegMaxA = 4;
-constexpr int kSegMaxB = 12;
-constexpr int kSegSmemBytes = 232448;   // the whole opt-in budget; the rings are sized from it by the host
+constexpr int kSegMaxStages = 6;
+constexpr int kSegSmemBytes = 232448;   // the whole opt-in budget; the ring is sized from it by the host
 
 __device__ __forceinline__ uint64_t with_base_offset(uint64_t desc, uint32_t rows) {
     return desc | (static_cast<uint64_t>(rows & 7u) << 49);
 }
 
+// One pipeline stage = one filter row of one 64-channel chunk: the A segment (seg_rows pixels) and the weight tiles of
+// the row's k taps ([tap][b_rows][64], ONE rank-3 TMA box), i.e. two TMA instructions, one barrier round trip and 4*k
+// MMAs per stage - the single-thread producer / issuer loops cost a few hundred cycles per round trip, which a stage of
+// only 4 MMAs does not hide once N < 256.
+// the 4 * K MMAs of one filter row, straight-line (descriptor arithmetic on compile-time tap / k-slice indices)
+template <int K, bool PAIR>
+__device__ __forceinline__ void issue_row(uint32_t d_tmem, uint64_t da0, uint64_t db0, int64_t rstep8, uint32_t bt16, uint32_t idesc,
+                                          uint32_t accum) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const uint64_t da = da0 + (uint64_t)(j * rstep8);
+        const uint64_t db = db0 + (uint64_t)j * bt16;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t acc = (j == 0 && kk == 0) ? accum : 1u;
+            if (PAIR) umma_bf16_pair(d_tmem, da + 2 * kk, db + 2 * kk, idesc, acc);
+            else umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, acc);
+        }
+    }
+}
+
 template <bool PAIR>
 __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* smem_raw) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* a_ring = smem;
-    uint8_t* b_ring = a_ring + P.seg_na * P.seg_a_bytes;
-    uint8_t* stage_out = b_ring + P.seg_nb * P.seg_b_bytes;
+    uint8_t* stage_out = smem + P.seg_ns * P.seg_stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + kStageOutBytes);
-    uint64_t* a_full = bars;
-    uint64_t* a_empty = a_full + kSegMaxA;
-    uint64_t* b_full = a_empty + kSegMaxA;
-    uint64_t* b_empty = b_full + kSegMaxB;
-    uint64_t* tfull_bar = b_empty + kSegMaxB;
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = full_bar + kSegMaxStages;
+    uint64_t* tfull_bar = empty_bar + kSegMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -801,16 +904,16 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
     const bool leader = rank == 0;
     const int b_rows = PAIR ? P.block_n / 2 : P.block_n;
     const int col_stride = P.block_n < 32 ? 32 : P.block_n;
+    const bool prof = P.prof != nullptr;
 
     if (warp == 0 && lane == 0) {
         for (int p = 0; p < P.planes; ++p) {
             tma_prefetch_desc(&P.a_seg[p]);
-            tma_prefetch_desc(&P.b[p]);
+            tma_prefetch_desc(&P.b_seg[p]);
         }
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kSegMaxA; ++s) { mbar_init(&a_full[s], PAIR ? 2 : 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < kSegMaxB; ++s) { mbar_init(&b_full[s], PAIR ? 2 : 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < kSegMaxStages; ++s) { mbar_init(&full_bar[s], PAIR ? 2 : 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], PAIR ? 8 : 4); }
         fence_barrier_init();
     }
@@ -828,13 +931,15 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
     const int total_items = m_items * P.n_tiles;
     const int n_workers = PAIR ? gridDim.x / 2 : gridDim.x;
     const int worker = PAIR ? blockIdx.x / 2 : blockIdx.x;
-    const uint32_t a_tx = (uint32_t)P.seg_a_bytes * (PAIR ? 2u : 1u);
-    const uint32_t b_tx = (uint32_t)b_rows * 128u * (PAIR ? 2u : 1u);
+    const uint32_t stage_tx = (uint32_t)(P.seg_a_bytes + P.seg_taps * P.seg_btile_bytes) * (PAIR ? 2u : 1u);
+    const int n_rounds = P.nseg * P.cchunks * P.num_segs;       // stages per work item
 
     if (warp == 0 && lane == 0) {
         // ---------------- TMA producer ----------------
-        int as = 0, bs = 0;
-        uint32_t aph = 0, bph = 0;
+        int st = 0;
+        uint32_t ph = 0;
+        long long t_wait = 0;
+        const long long t_begin = prof ? clock64() : 0;
         for (int item = worker; item < total_items; item += n_workers) {
             const int nt = item % P.n_tiles;
             int mt = (item / P.n_tiles) * (PAIR ? 2 : 1) + (int)rank;   // past-the-end tile: zero fill, never stored
@@ -842,87 +947,98 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
             mt /= P.tiles_x;
             const int y0 = (mt % P.tiles_y) * P.box_y;
             const int z0 = (mt / P.tiles_y) * P.box_z;
+            const int brow = nt * P.block_n + (int)rank * b_rows;
 #pragma unroll 1
             for (int seg = 0; seg < P.nseg; ++seg) {
-                const int pa = (seg == 2) ? 1 : 0;
-                const int pb = (seg == 1) ? 1 : 0;
+                const CUtensorMap* am = &P.a_seg[(seg == 2) ? 1 : 0];
+                const CUtensorMap* bm = &P.b_seg[(seg == 1) ? 1 : 0];
 #pragma unroll 1
                 for (int cc = 0; cc < P.cchunks; ++cc) {
 #pragma unroll 1
                     for (int sg = 0; sg < P.num_segs; ++sg) {
-                        mbar_wait(&a_empty[as], aph ^ 1);
-                        if (!PAIR) mbar_arrive_expect_tx(&a_full[as], a_tx);
-                        else if (leader) mbar_arrive_expect_tx(&a_full[as], a_tx);
-                        else mbar_arrive_leader(&a_full[as]);
-                        uint8_t* sa = a_ring + as * P.seg_a_bytes;
-                        if (PAIR) tma_load_4d_pair(sa, &P.a_seg[pa], &a_full[as], cc * 64, x0 + P.seg_dx[sg], y0 + P.seg_dy[sg], z0);
-                        else tma_load_4d(sa, &P.a_seg[pa], &a_full[as], cc * 64, x0 + P.seg_dx[sg], y0 + P.seg_dy[sg], z0);
-                        if (++as == P.seg_na) { as = 0; aph ^= 1; }
-#pragma unroll 1
-                        for (int j = 0; j < P.seg_taps; ++j) {
-                            const int t = sg * P.seg_taps + j;
-                            mbar_wait(&b_empty[bs], bph ^ 1);
-                            if (!PAIR) mbar_arrive_expect_tx(&b_full[bs], b_tx);
-                            else if (leader) mbar_arrive_expect_tx(&b_full[bs], b_tx);
-                            else mbar_arrive_leader(&b_full[bs]);
-                            uint8_t* sb = b_ring + bs * P.seg_b_bytes;
-                            const int brow = nt * P.block_n + (int)rank * b_rows;
-                            if (PAIR) tma_load_2d_pair(sb, &P.b[pb], &b_full[bs], P.tap_bk[t] + cc * 64, brow);
-                            else tma_load_2d(sb, &P.b[pb], &b_full[bs], P.tap_bk[t] + cc * 64, brow);
-                            if (++bs == P.seg_nb) { bs = 0; bph ^= 1; }
+                        const long long tw = prof ? clock64() : 0;
+                        mbar_wait(&empty_bar[st], ph ^ 1);
+                        if (prof) t_wait += clock64() - tw;
+                        uint8_t* sa = smem + st * P.seg_stage_bytes;
+                        uint8_t* sb = sa + P.seg_a_bytes;
+                        if (P.debug == 1) {          // MMA without TMA traffic
+                            if (!PAIR || leader) mbar_arrive(&full_bar[st]); else mbar_arrive_leader(&full_bar[st]);
+                        } else if (PAIR) {
+                            if (leader) mbar_arrive_expect_tx(&full_bar[st], stage_tx); else mbar_arrive_leader(&full_bar[st]);
+                            tma_load_4d_pair(sa, am, &full_bar[st], cc * 64, x0 + P.seg_dx[sg], y0 + P.seg_dy[sg], z0);
+                            tma_load_3d_pair(sb, bm, &full_bar[st], cc * 64, brow, sg * P.seg_taps);
+                        } else {
+                            mbar_arrive_expect_tx(&full_bar[st], stage_tx);
+                            tma_load_4d(sa, am, &full_bar[st], cc * 64, x0 + P.seg_dx[sg], y0 + P.seg_dy[sg], z0);
+                            tma_load_3d(sb, bm, &full_bar[st], cc * 64, brow, sg * P.seg_taps);
                         }
+                        if (++st == P.seg_ns) { st = 0; ph ^= 1; }
                     }
                 }
             }
         }
+        if (prof) { P.prof[blockIdx.x * 16 + 0] = clock64() - t_begin; P.prof[blockIdx.x * 16 + 1] = t_wait; }
     } else if (warp == 1 && lane == 0 && leader) {
         // ---------------- MMA issuer ----------------
         const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, (uint32_t)P.block_n, 0, 0);
-        int as = 0, bs = 0;
-        uint32_t aph = 0, bph = 0;
+        int st = 0;
+        uint32_t ph = 0;
         int it = 0;
+        long long t_wfull = 0, t_wacc = 0;
+        const long long t_begin = prof ? clock64() : 0;
+        // (the host checked that tap_row is the same arithmetic progression in every filter row)
+        const int row0 = P.tap_row[0];
+        const int64_t rstep8 = P.seg_taps > 1 ? (int64_t)(P.tap_row[1] - P.tap_row[0]) * 8 : 0;   // rows -> descriptor units
+        const uint32_t bt16 = (uint32_t)P.seg_btile_bytes >> 4;
         for (int item = worker; item < total_items; item += n_workers, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
+            long long tw = prof ? clock64() : 0;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            if (prof) t_wacc += clock64() - tw;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * col_stride;
-            uint32_t first = 1;
-            const int n_a = P.nseg * P.cchunks * P.num_segs;
+            uint32_t accum = 0;
 #pragma unroll 1
-            for (int ai = 0; ai < n_a; ++ai) {
-                const int sg = ai % P.num_segs;
-                mbar_wait(&a_full[as], aph);
+            for (int r = 0; r < n_rounds; ++r) {
+                const int sg = r % P.num_segs;
+                tw = prof ? clock64() : 0;
+                mbar_wait(&full_bar[st], ph);
+                if (prof) t_wfull += clock64() - tw;
                 tc_fence_after();
-                const uint32_t sa = smem_u32(a_ring + as * P.seg_a_bytes);
+                const uint32_t sa = smem_u32(smem + st * P.seg_stage_bytes);
+                const uint32_t sb = sa + P.seg_a_bytes;
+                if (P.debug != 2) {          // (2 = TMA traffic without MMA)
+                    // A descriptor of tap j = stage base + (row0 + j * rstep) rows; B descriptor = base + j weight tiles
+                    const uint64_t da0 = make_smem_desc_sw128(sa, 16, 1024) + (uint64_t)(row0 * 8);
+                    const uint64_t db0 = make_smem_desc_sw128(sb, 16, 1024);
+                    switch (P.seg_taps) {
+                        case 3: issue_row<3, PAIR>(d_tmem, da0, db0, rstep8, bt16, idesc, accum); break;
+                        case 5: issue_row<5, PAIR>(d_tmem, da0, db0, rstep8, bt16, idesc, accum); break;
+                        case 7: issue_row<7, PAIR>(d_tmem, da0, db0, rstep8, bt16, idesc, accum); break;
+                        default:
 #pragma unroll 1
-                for (int j = 0; j < P.seg_taps; ++j) {
-                    const int row = P.tap_row[sg * P.seg_taps + j];
-                    mbar_wait(&b_full[bs], bph);
-                    tc_fence_after();
-                    uint64_t da = make_smem_desc_sw128(sa + row * 128, 16, 1024);
-                    if (P.seg_bo) da = with_base_offset(da, (uint32_t)row);
-                    const uint64_t db = make_smem_desc_sw128(smem_u32(b_ring + bs * P.seg_b_bytes), 16, 1024);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        if (PAIR) umma_bf16_pair(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
-                        else umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+                            for (int j = 0; j < P.seg_taps; ++j) issue_row<1, PAIR>(d_tmem, da0 + (int64_t)j * rstep8, db0 + (uint64_t)j * bt16, 0, 0, idesc, accum);
                     }
-                    first = 0;
-                    if (PAIR) umma_commit_pair(&b_empty[bs], 3); else umma_commit(&b_empty[bs]);
-                    if (++bs == P.seg_nb) { bs = 0; bph ^= 1; }
+                    accum = 1;
                 }
-                if (PAIR) umma_commit_pair(&a_empty[as], 3); else umma_commit(&a_empty[as]);
-                if (++as == P.seg_na) { as = 0; aph ^= 1; }
+                if (PAIR) umma_commit_pair(&empty_bar[st], 3); else umma_commit(&empty_bar[st]);
+                if (++st == P.seg_ns) { st = 0; ph ^= 1; }
             }
             if (PAIR) umma_commit_pair(&tfull_bar[acc], 3); else umma_commit(&tfull_bar[acc]);
+        }
+        if (prof) {
+            P.prof[blockIdx.x * 16 + 2] = clock64() - t_begin; P.prof[blockIdx.x * 16 + 3] = t_wfull; P.prof[blockIdx.x * 16 + 4] = t_wacc;
         }
     } else if (warp >= 4) {
         // ---------------- epilogue (own 128 rows) ----------------
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const aclgan_out_spec& o = P.out;
+        const EpiArgs ea = make_epi_args(P);
         int it = 0;
+        long long t_wt = 0;
+        const long long t_begin = prof ? clock64() : 0;
         for (int item = worker; item < total_items; item += n_workers, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -937,9 +1053,9 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
             if (P.flat) {
                 const int64_t qq = (int64_t)tx * P.box_x + row;
                 rc.z = (int)(qq / P.flat_img);
-                const int rem = (int)(qq % P.flat_img);
+                const int rem = (int)(qq - (int64_t)rc.z * P.flat_img);
                 rc.y = rem / P.flat_w;
-                rc.x = rem % P.flat_w;
+                rc.x = rem - rc.y * P.flat_w;
             } else {
                 rc.x = tx * P.box_x + row % P.box_x;
                 rc.y = ty * P.box_y + (row / P.box_x) % P.box_y;
@@ -949,22 +1065,31 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
             rc.pix0 = o.off + (int64_t)rc.z * o.sn + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
             rc.ny = mirror_coords(rc.y, o.H, o.mirror, rc.ys);
             rc.nx = mirror_coords(rc.x, o.W, o.mirror, rc.xs);
+            const long long tw = prof ? clock64() : 0;
             mbar_wait(&tfull_bar[acc], acc_phase);
+            if (prof) t_wt += clock64() - tw;
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * col_stride + ((uint32_t)(q * 32) << 16);
             const int n0 = nt * P.block_n;
             const int group = (o.kind == ACLGAN_OUT_F32) ? 32 : 64;
-            const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) && (n0 + P.block_n <= o.C);
+            const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) && (n0 + P.block_n <= o.C) &&
+                              (o.act != ACLGAN_ACT_TANH);
             StatCtx sc;
             if (o.stats != 0) sc = make_stat_ctx(P, tx, tz, q, lane, rc);
-            if (fast) epilogue_tile_fast(P, t_row, n0, rc, stage_out + q * 8192, lane, o.stats != 0 ? sc.rb : 32);
-            else epilogue_tile_generic(P, t_row, n0, rc);
-            if (o.stats != 0) stats_tile_end(P, stage_out, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
+            const long long te = prof ? clock64() : 0;
+            if (fast) epilogue_tile_fast(ea, t_row, n0, rc, stage_out + q * 8192, lane, o.stats != 0 ? sc.rb : 32,
+                                         (prof && warp == 4) ? P.prof + blockIdx.x * 16 + 8 : nullptr);
+            else epilogue_tile_generic(ea, t_row, n0, rc);
+            if (o.stats != 0) stats_tile_end(ea, stage_out, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
+            if (prof && warp == 4 && lane == 0) P.prof[blockIdx.x * 16 + 7] += clock64() - te;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 if (PAIR) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
             }
+        }
+        if (prof && warp == 4 && lane == 0) {
+            P.prof[blockIdx.x * 16 + 5] = clock64() - t_begin; P.prof[blockIdx.x * 16 + 6] = t_wt;
         }
     }
 
@@ -992,12 +1117,14 @@ static bool stats_supported(const aclgan_igemm_plan* pl) {
     const aclgan_out_spec& o = pl->out;
     const int group = (o.kind == ACLGAN_OUT_F32) ? 32 : 64;
     if (o.kind != ACLGAN_OUT_BF16 && o.kind != ACLGAN_OUT_F32) return false;
-    if (o.sc != 1 || pl->block_n < group || pl->block_n > 256 || o.C % pl->block_n != 0) return false;
+    if (o.sc != 1 || pl->block_n < group || pl->block_n > 256 || o.C % pl->block_n != 0 || o.act == ACLGAN_ACT_TANH) return false;
     if (pl->n_groups > 1) return false;
     if (pl->flat) return pl->flat_img >= 128;           // a 128-row tile then touches at most two images
     if (pl->box_z != 1 && (pl->box_x * pl->box_y) % 32 != 0) return false;
     return true;
 }
+
+static long long* g_prof = nullptr;      // set by aclgan_igemm_set_prof (perf triage)
 
 static int fill_kparams(const aclgan_igemm_plan* pl, IgemmKParams* kp) {
     if (pl->out.stats != 0 && !stats_supported(pl)) return ACLGAN_ERR_UNSUPPORTED;
@@ -1050,10 +1177,20 @@ static int fill_kparams(const aclgan_igemm_plan* pl, IgemmKParams* kp) {
     kp->seg_rows = pl->seg_rows; kp->num_segs = pl->num_segs; kp->seg_taps = pl->seg_taps;
     for (int i = 0; i < 16; ++i) { kp->seg_dx[i] = pl->seg_dx[i]; kp->seg_dy[i] = pl->seg_dy[i]; }
     for (int t = 0; t < ACLGAN_MAX_TAPS; ++t) kp->tap_row[t] = pl->tap_row[t];
-    kp->seg_a_bytes = kp->seg_b_bytes = kp->seg_na = kp->seg_nb = 0;
+    kp->seg_a_bytes = kp->seg_btile_bytes = kp->seg_stage_bytes = kp->seg_ns = 0;
+    kp->prof = g_prof;
     {
+        const char* ed = getenv("ACLGAN_EPI_DIRECT");
+        kp->epi_direct = ed != nullptr ? atoi(ed) : 1;
+    }
+    {
+        // measured on B200: the 128B swizzle of a UMMA operand is a function of the absolute shared-memory address
+        // bits, so a row-shifted start address needs NO matrix base offset (with it the results are wrong)
         const char* bo = getenv("ACLGAN_SEG_BO");
-        kp->seg_bo = bo != nullptr ? atoi(bo) : 1;
+        kp->seg_bo = bo != nullptr ? atoi(bo) : 0;
+        const char* sd = getenv("ACLGAN_SEG_DEBUG");     // perf triage: 1 = every tap reads rows [0, 128) (aligned start)
+        if (sd != nullptr && atoi(sd) == 1)
+            for (int t = 0; t < ACLGAN_MAX_TAPS; ++t) kp->tap_row[t] = 0;
     }
     return ACLGAN_OK;
 }
@@ -1067,26 +1204,44 @@ static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repea
         return -100;
     const int m_tiles = plan->tiles_x * plan->tiles_y * plan->tiles_z;
     const char* penv = getenv("ACLGAN_IGEMM_PAIR");
-    bool pair = (plan->block_n >= 32) && (((m_tiles + 1) / 2) * plan->n_tiles >= num_sms() / 2);
+    // CTA pairs halve the weight bytes staged per SM; below N = 128 the stage is small anyway and one CTA per tile
+    // issues its (N-independent, ~70-cycle) MMAs at twice the rate per SM
+    bool pair = (plan->block_n >= 128) && (((m_tiles + 1) / 2) * plan->n_tiles >= num_sms() / 2);
     if (penv != nullptr) pair = atoi(penv) != 0 && plan->block_n >= 32;
     const int b_rows = pair ? plan->block_n / 2 : plan->block_n;
+    if (b_rows % 8 != 0) return -100;
     for (int p = 0; p < plan->planes; ++p) {
         int rc = encode_tmap(&plan->a_seg[p], &kp.a_seg[p]);
         if (rc) return rc;
-        aclgan_tmap_spec bs = plan->b[p];
-        bs.box[1] = b_rows;
-        rc = encode_tmap(&bs, &kp.b[p]);
+        // weights of the seg_taps taps of one filter row as ONE box: (64 k-elements, b_rows rows, seg_taps taps)
+        const aclgan_tmap_spec& b2 = plan->b[p];
+        aclgan_tmap_spec b3;
+        memset(&b3, 0, sizeof(b3));
+        const uint64_t tap_elems = (uint64_t)plan->cchunks * 64;          // k elements per tap (tap_bk[t] = t * tap_elems)
+        b3.base = b2.base; b3.rank = 3; b3.elem_bytes = 2;
+        b3.dims[0] = tap_elems;          b3.strides[0] = 2;             b3.box[0] = 64;
+        b3.dims[1] = b2.dims[1];         b3.strides[1] = b2.strides[1]; b3.box[1] = b_rows;
+        b3.dims[2] = plan->num_taps;     b3.strides[2] = tap_elems * 2; b3.box[2] = plan->seg_taps;
+        rc = encode_tmap(&b3, &kp.b_seg[p]);
         if (rc) return rc;
     }
-    if (plan->planes == 1) { kp.a_seg[1] = kp.a_seg[0]; kp.b[1] = kp.b[0]; }
+    for (int t = 0; t < plan->num_taps; ++t) {
+        if (plan->tap_bk[t] != t * plan->cchunks * 64) return -100;
+        const int j = t % plan->seg_taps;
+        const int step = plan->seg_taps > 1 ? plan->tap_row[1] - plan->tap_row[0] : 0;
+        if (plan->tap_row[t] != plan->tap_row[0] + j * step || plan->tap_row[t] < 0 ||
+            plan->tap_row[t] + 128 > plan->seg_rows)
+            return -100;
+    }
+    if (plan->planes == 1) { kp.a_seg[1] = kp.a_seg[0]; kp.b_seg[1] = kp.b_seg[0]; }
     kp.seg_a_bytes = plan->seg_rows * 128;
-    kp.seg_b_bytes = ((b_rows * 128 + 1023) / 1024) * 1024;
+    kp.seg_btile_bytes = b_rows * 128;
+    kp.seg_stage_bytes = kp.seg_a_bytes + plan->seg_taps * kp.seg_btile_bytes;
     const int budget = kSegSmemBytes - 1024 - kStageOutBytes - 512;
-    kp.seg_na = 3;
-    int nb = (budget - kp.seg_na * kp.seg_a_bytes) / kp.seg_b_bytes;
-    if (nb > kSegMaxB) nb = kSegMaxB;
-    if (nb < 2) return -100;
-    kp.seg_nb = nb;
+    int ns = budget / kp.seg_stage_bytes;
+    if (ns > kSegMaxStages) ns = kSegMaxStages;
+    if (ns < 2) return -100;
+    kp.seg_ns = ns;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(igemm_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSegSmemBytes);
@@ -1112,6 +1267,11 @@ static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repea
 }  // namespace aclgan
 
 extern "C" int aclgan_igemm_launch_repeat(const aclgan_igemm_plan* plan, int repeat, void* stream);
+
+// perf triage: device buffer of [grid][8] int64 role timers filled by the segment kernel (0 switches it off):
+// 0 producer total, 1 producer waiting for free stages, 2 MMA thread total, 3 MMA waiting for operands, 4 MMA waiting for
+// a drained accumulator, 5 epilogue warp total, 6 epilogue waiting for a finished accumulator
+extern "C" int aclgan_igemm_set_prof(uint64_t buf) { aclgan::g_prof = reinterpret_cast<long long*>(buf); return 0; }
 
 extern "C" int aclgan_igemm_stats_supported(const aclgan_igemm_plan* plan) { return aclgan::stats_supported(plan) ? 1 : 0; }
 

@@ -60,7 +60,10 @@ class WgradPlan(C.Structure):
                 ("m_dx", C.c_int32 * MAX_TAPS), ("m_dy", C.c_int32 * MAX_TAPS), ("m_var", C.c_int32 * MAX_TAPS),
                 ("n_dx", C.c_int32 * MAX_TAPS), ("n_dy", C.c_int32 * MAX_TAPS), ("n_var", C.c_int32 * MAX_TAPS),
                 ("tap_out", C.c_int32 * MAX_TAPS),
-                ("dw", C.c_uint64), ("dw_sm", C.c_int64), ("dw_st", C.c_int64), ("M", C.c_int32), ("Nn", C.c_int32)]
+                ("dw", C.c_uint64), ("dw_sm", C.c_int64), ("dw_st", C.c_int64), ("M", C.c_int32), ("Nn", C.c_int32),
+                ("seg_mode", C.c_int32), ("seg_rows", C.c_int32), ("seg_taps", C.c_int32), ("seg_on_m", C.c_int32),
+                ("seg_kw0", C.c_int32 * MAX_TAPS), ("seg_cnt", C.c_int32 * MAX_TAPS),
+                ("seg_map", TmapSpec * 2)]
 
 
 class Act(C.Structure):

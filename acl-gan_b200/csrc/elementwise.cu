@@ -238,7 +238,8 @@ __global__ void norm_finalize_kernel(aclgan_norm_finalize_args a) {
 // ------------------------------------------------------------------------------------------ norm_apply
 constexpr int kApplyPix = 4;     // padded pixels per thread (same image, same channel group -> coefficients stay in registers)
 
-__global__ void __launch_bounds__(256, 2) norm_apply_kernel(aclgan_apply_args a) {
+template <int K, int MINB>
+__global__ void __launch_bounds__(256, MINB) norm_apply_kernel(aclgan_apply_args a) {
     const int u = a.upsample, p = a.dst.pad;
     const int hd = a.y.h * u, wd = a.y.w * u, hp = hd + 2 * p, wp = wd + 2 * p;
     const int cg = a.y.c / 8;
@@ -253,13 +254,13 @@ __global__ void __launch_bounds__(256, 2) norm_apply_kernel(aclgan_apply_args a)
         sf = load_coef8(a.shift, (int64_t)n * a.y.c + g * 8);
     }
     const int rp = a.res.pad, rwp = a.res.w + 2 * rp, rhp = a.res.h + 2 * rp;
-    const int batch = lanes * kApplyPix;
+    const int batch = lanes * K;
     // CTAs stride over pixel batches of their image; per batch all loads of the thread's pixels are issued first
     // (memory-level parallelism), then the arithmetic and the stores
     for (int p0 = blockIdx.x * batch + lane; p0 - lane < npix; p0 += gridDim.x * batch) {
-        F8 yv[kApplyPix], rv[kApplyPix];
+        F8 yv[K], rv[K];
 #pragma unroll
-        for (int j = 0; j < kApplyPix; ++j) {
+        for (int j = 0; j < K; ++j) {
             int pix = p0 + j * lanes;
             if (pix >= npix) pix = npix - 1;
             const int Y = pix / wp, X = pix - Y * wp;
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(256, 2) norm_apply_kernel(aclgan_apply_args a)
                 rv[j] = load8_planes(a.res.data, a.res.planes, (((int64_t)n * rhp + y + rp) * rwp + x + rp) * a.res.c + g * 8);
         }
 #pragma unroll
-        for (int j = 0; j < kApplyPix; ++j) {
+        for (int j = 0; j < K; ++j) {
             const int pix = p0 + j * lanes;
             if (pix >= npix) break;
             F8 v = yv[j];
@@ -680,9 +681,9 @@ __device__ __forceinline__ void pix_dz_s(const aclgan_block_bwd_args& a, const f
     }
 }
 
-template <int U, int KIND, int MINB>
+template <int U, int KIND, int MINB, int KP>
 __global__ void __launch_bounds__(kStatThreads, MINB) block_bwd_reduce_fast(aclgan_block_bwd_args a) {
-    constexpr int K = (U == 1) ? kBwdPix1 : kBwdPix2;
+    constexpr int K = (U == 1) ? KP : (KP > 2 ? 2 : 1);
     extern __shared__ float smem_f[];
     float* coef = smem_f;                       // [CF_ROWS][c]
     float* red = smem_f + CF_ROWS * a.c;        // [lanes][c][2]
@@ -721,9 +722,9 @@ __global__ void __launch_bounds__(kStatThreads, MINB) block_bwd_reduce_fast(aclg
                        nullptr, 0);
 }
 
-template <int U, int KIND, int MINB>
+template <int U, int KIND, int MINB, int KP>
 __global__ void __launch_bounds__(kStatThreads, MINB) block_bwd_apply_fast(aclgan_block_bwd_args a) {
-    constexpr int K = (U == 1) ? kBwdPix1 : kBwdPix2;
+    constexpr int K = (U == 1) ? KP : (KP > 2 ? 2 : 1);
     extern __shared__ float smem_f[];
     float* coef = smem_f;
     float* red = smem_f + CF_ROWS * a.c;
@@ -910,8 +911,8 @@ static inline int grid_for(int64_t total, int block) { return (int)((total + blo
 
 // CTAs per image of the grid-stride element-wise kernels: about four CTAs per SM over all images (two resident at a
 // time), so a CTA lives long enough to amortise its prologue and the per-CTA reductions / atomics stay few
-static inline int strided_grid(int batches, int n_images) {
-    int per = (4 * num_sms() + n_images - 1) / n_images;
+static inline int strided_grid(int batches, int n_images, int ctas_per_sm = 4) {
+    int per = (ctas_per_sm * num_sms() + n_images - 1) / n_images;
     if (per < 1) per = 1;
     return batches < per ? batches : per;
 }
@@ -957,20 +958,34 @@ extern "C" int aclgan_norm_apply(const aclgan_apply_args* a, void* stream) {
     const int64_t npix = (int64_t)(a->y.h * u + 2 * p) * (a->y.w * u + 2 * p);
     if (npix >= (1LL << 30)) return ACLGAN_ERR_SHAPE;
     const int lanes = 256 / (a->y.c / 8);
-    dim3 grid(strided_grid(grid_for(npix, lanes * kApplyPix), a->y.n), a->y.n);
-    norm_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+    static int variant = -1;
+    if (variant < 0) {
+        const char* e = getenv("ACLGAN_APPLY_VARIANT");
+        variant = e != nullptr ? atoi(e) : 1;
+    }
+    const int K = variant == 0 ? 4 : 2;
+    dim3 grid(strided_grid(grid_for(npix, lanes * K), a->y.n, variant == 0 ? 4 : 8), a->y.n);
+    if (variant == 0) norm_apply_kernel<4, 2><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+    else if (variant == 1) norm_apply_kernel<2, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+    else norm_apply_kernel<2, 3><<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
 }
 
 // register budget of the fast kernels: 1 = uncapped (about 180 registers, 8 warps / SM), 2 = capped at 128 (some spills,
 // 16 warps / SM); env ACLGAN_BWD_OCC overrides
-static int bwd_minb() {
-    static int v = 0;
-    if (v == 0) {
-        const char* e = getenv("ACLGAN_BWD_OCC");
-        v = (e != nullptr && atoi(e) == 1) ? 1 : 2;
+// variant 0: 4 pixels / thread, 2 CTAs / SM (128 registers); 1: 2 pixels, 3 CTAs (85); 2: 2 pixels, 4 CTAs (64)
+static int bwd_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ACLGAN_BWD_VARIANT");
+        v = e != nullptr ? atoi(e) : 1;
+        if (v < 0 || v > 2) v = 1;
     }
     return v;
+}
+static int bwd_pix(int upsample) {
+    const int kp = bwd_variant() == 0 ? 4 : 2;
+    return upsample == 1 ? kp : (kp > 2 ? 2 : 1);
 }
 
 // fast kernels: at most one reflect image per coordinate, 32-bit pixel indices
@@ -988,20 +1003,24 @@ extern "C" int aclgan_block_bwd_reduce(const aclgan_block_bwd_args* a, void* str
     const int lanes = kStatThreads / (a->c / 8);
     const int64_t hw = (int64_t)a->h * a->w;
     if (bwd_fast_ok(a)) {
-        const int K = a->upsample == 1 ? kBwdPix1 : kBwdPix2;
-        dim3 grid(strided_grid(grid_for(hw, lanes * K), a->n), a->n);
+        const int K = bwd_pix(a->upsample);
+        dim3 grid(strided_grid(grid_for(hw, lanes * K), a->n, 2 * (bwd_variant() + 2)), a->n);
         const size_t smem = ((size_t)lanes * a->c * 2 + (size_t)CF_ROWS * a->c) * sizeof(float);
-        const int sel = (a->upsample == 1 ? 0 : 2) + (a->g_kind ? 1 : 0) + (bwd_minb() == 2 ? 4 : 0);
+        const int sel = (a->upsample == 1 ? 0 : 2) + (a->g_kind ? 1 : 0) + 4 * bwd_variant();
         cudaStream_t st = (cudaStream_t)stream;
         switch (sel) {
-            case 0: block_bwd_reduce_fast<1, 0, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
-            case 1: block_bwd_reduce_fast<1, 1, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
-            case 2: block_bwd_reduce_fast<2, 0, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
-            case 3: block_bwd_reduce_fast<2, 1, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
-            case 4: block_bwd_reduce_fast<1, 0, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
-            case 5: block_bwd_reduce_fast<1, 1, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
-            case 6: block_bwd_reduce_fast<2, 0, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
-            default: block_bwd_reduce_fast<2, 1, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 0: block_bwd_reduce_fast<1, 0, 2, 4><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 1: block_bwd_reduce_fast<1, 1, 2, 4><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 2: block_bwd_reduce_fast<2, 0, 2, 4><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 3: block_bwd_reduce_fast<2, 1, 2, 4><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 4: block_bwd_reduce_fast<1, 0, 3, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 5: block_bwd_reduce_fast<1, 1, 3, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 6: block_bwd_reduce_fast<2, 0, 3, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 7: block_bwd_reduce_fast<2, 1, 3, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 8: block_bwd_reduce_fast<1, 0, 4, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 9: block_bwd_reduce_fast<1, 1, 4, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 10: block_bwd_reduce_fast<2, 0, 4, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            default: block_bwd_reduce_fast<2, 1, 4, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
         }
         return (int)cudaGetLastError();
     }
@@ -1016,20 +1035,24 @@ extern "C" int aclgan_block_bwd_apply(const aclgan_block_bwd_args* a, void* stre
     const int64_t npix = (int64_t)(a->h + 2 * a->dy.pad) * (a->w + 2 * a->dy.pad);
     const int lanes = 256 / (a->c / 8);
     if (bwd_fast_ok(a)) {
-        const int K = a->upsample == 1 ? kBwdPix1 : kBwdPix2;
-        dim3 grid(strided_grid(grid_for(npix, lanes * K), a->n), a->n);
+        const int K = bwd_pix(a->upsample);
+        dim3 grid(strided_grid(grid_for(npix, lanes * K), a->n, 2 * (bwd_variant() + 2)), a->n);
         const size_t smem = ((a->dbias != 0 ? (size_t)lanes * a->c * 2 : 0) + (size_t)CF_ROWS * a->c) * sizeof(float);
-        const int sel = (a->upsample == 1 ? 0 : 2) + (a->g_kind ? 1 : 0) + (bwd_minb() == 2 ? 4 : 0);
+        const int sel = (a->upsample == 1 ? 0 : 2) + (a->g_kind ? 1 : 0) + 4 * bwd_variant();
         cudaStream_t st = (cudaStream_t)stream;
         switch (sel) {
-            case 0: block_bwd_apply_fast<1, 0, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
-            case 1: block_bwd_apply_fast<1, 1, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
-            case 2: block_bwd_apply_fast<2, 0, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
-            case 3: block_bwd_apply_fast<2, 1, 1><<<grid, kStatThreads, smem, st>>>(*a); break;
-            case 4: block_bwd_apply_fast<1, 0, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
-            case 5: block_bwd_apply_fast<1, 1, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
-            case 6: block_bwd_apply_fast<2, 0, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
-            default: block_bwd_apply_fast<2, 1, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 0: block_bwd_apply_fast<1, 0, 2, 4><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 1: block_bwd_apply_fast<1, 1, 2, 4><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 2: block_bwd_apply_fast<2, 0, 2, 4><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 3: block_bwd_apply_fast<2, 1, 2, 4><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 4: block_bwd_apply_fast<1, 0, 3, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 5: block_bwd_apply_fast<1, 1, 3, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 6: block_bwd_apply_fast<2, 0, 3, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 7: block_bwd_apply_fast<2, 1, 3, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 8: block_bwd_apply_fast<1, 0, 4, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 9: block_bwd_apply_fast<1, 1, 4, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            case 10: block_bwd_apply_fast<2, 0, 4, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
+            default: block_bwd_apply_fast<2, 1, 4, 2><<<grid, kStatThreads, smem, st>>>(*a); break;
         }
         return (int)cudaGetLastError();
     }

@@ -79,6 +79,11 @@ static bool seg_enabled() {
     return e == nullptr || atoi(e) != 0;
 }
 
+static bool wgrad_seg_enabled() {
+    const char* e = getenv("ACLGAN_WGRAD_SEG");
+    return e == nullptr || atoi(e) != 0;
+}
+
 static int k_channels(const aclgan_conv_desc* cd, int transposed) {
     return round_up(transposed ? cd->cout : cd->cin, 64);
 }
@@ -139,7 +144,7 @@ extern "C" int aclgan_plan_conv_fwd(const aclgan_conv_desc* cd, const aclgan_act
     aclgan_packed_weight_shape(cd, 0, &rows, &kt);
     for (int pl = 0; pl < x->planes; ++pl) weight_map2(&p->b[pl], w[pl], kt, rows, p->block_n);
 
-    if (cd->window == ACLGAN_WINDOW_NONE && s == 1 && k > 1 && k <= 8 && seg_enabled()) {
+    if (cd->window != ACLGAN_WINDOW_IN && s == 1 && k > 1 && k <= 8 && seg_enabled()) {
         // stride 1: segment mode.  Tiles are 128 consecutive pixels of one output row when the rows are long enough,
         // otherwise 128 consecutive positions of the flattened padded input grid (outputs at the k - 1 right-most
         // columns / bottom rows of that grid are computed and dropped by the epilogue's extent check).
@@ -461,6 +466,49 @@ extern "C" int aclgan_plan_conv_wgrad(const aclgan_conv_desc* cd, const aclgan_a
         p->m_tiles = ceil_div(x->c, 128);
         p->n_chunks = 1; p->n_tiles = 1;
         p->M = cd->cin; p->Nn = 64; p->dw_st = 64;
+    }
+    if (cd->window == ACLGAN_WINDOW_NONE && s == 1 && k > 1 && k <= 7 && wo % 64 == 0 && wgrad_seg_enabled()) {
+        // segment mode: re-plan with 64-pixel row blocks, one CTA-tile per (filter row, m tile, n tile)
+        const int cm = layout == 0 ? dy->c : x->c, cn = layout == 0 ? x->c : dy->c;
+        const int n_chunks = cn / 64 >= 2 ? 2 : 1;     // 128-column accumulators when the operand is wide enough
+        const int per_cta = 512 / (64 * n_chunks);     // taps whose accumulators fit the 512 TMEM columns
+        const int groups = ceil_div(k, per_cta);       // a filter row is split into `groups` entries of ~equal size
+        if (k * groups <= ACLGAN_MAX_TAPS) {
+            p->seg_mode = 1;
+            p->seg_taps = ceil_div(k, groups);
+            p->seg_rows = round_up(64 + k - 1, 8);
+            p->seg_on_m = layout == 0 ? 0 : 1;
+            p->box_x = 64; p->box_y = 1; p->box_z = 1;
+            p->blocks_x = wo / 64; p->blocks_y = ho; p->blocks_z = x->n;
+            p->num_taps = k * groups;
+            p->m_chunks = cm / 64 >= 2 ? 2 : 1;
+            p->m_tiles = ceil_div(cm, 128);
+            p->n_chunks = n_chunks;
+            p->n_tiles = ceil_div(cn / 64, n_chunks);
+            const int64_t px = (int64_t)x->c * 2, row = (int64_t)wp * px, img = (int64_t)hp * row;
+            for (int pl = 0; pl < x->planes; ++pl) {
+                aclgan_tmap_spec* xm = layout == 0 ? &p->nop[pl][0] : &p->mop[pl][0];
+                aclgan_tmap_spec* ym = layout == 0 ? &p->mop[pl][0] : &p->nop[pl][0];
+                plane_map4(xm, x->data[pl], x->c, wp, hp, x->n, px, row, img, 64, 1, 1);
+                plane_map4(&p->seg_map[pl], x->data[pl], x->c, wp, hp, x->n, px, row, img, p->seg_rows, 1, 1);
+                interior_map(ym, dy, pl, dy->c, 64, 1, 1);
+            }
+            p->n_mvariants = 1; p->n_nvariants = 1;
+            int t = 0;
+            for (int kh = 0; kh < k; ++kh) {
+                int kw0 = 0;
+                for (int g = 0; g < groups; ++g, ++t) {
+                    const int cnt = (k - kw0 + (groups - g) - 1) / (groups - g);      // remaining taps spread evenly
+                    p->m_dx[t] = p->m_dy[t] = p->n_dx[t] = p->n_dy[t] = 0;
+                    p->m_var[t] = p->n_var[t] = 0;
+                    if (layout == 0) p->n_dy[t] = kh; else p->m_dy[t] = kh;
+                    p->seg_kw0[t] = kw0;
+                    p->seg_cnt[t] = cnt;
+                    p->tap_out[t] = kh * k + kw0;
+                    kw0 += cnt;
+                }
+            }
+        }
     }
     // split-K so that the grid is ONE wave of CTAs (<= number of SMs): a grid of 162 CTAs on 148 SMs would run two
     // waves and take twice as long as 144

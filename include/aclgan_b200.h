@@ -117,6 +117,16 @@ typedef struct aclgan_wgrad_plan {
     uint64_t dw;                 /* fp32, element (m, tap, n) at m*dw_sm + tap*dw_st + n */
     int64_t dw_sm, dw_st;
     int32_t M, Nn;               /* valid rows / columns */
+    /* segment mode (stride-1 convolutions whose output rows are a multiple of 64 pixels): one CTA reduces ALL seg_taps
+     * taps of one filter ROW (num_taps = filter rows): per 64-pixel block of an output row the dY tile is staged once and
+     * the conv-input pixels once as a segment of seg_rows >= 64 + seg_taps - 1 pixels; tap kw multiplies the dY tile
+     * with rows [kw, kw + 64) of the segment into its own accumulator (seg_taps * 64 * n_chunks <= 512 TMEM columns).
+     * The shifted operand is N when seg_on_m == 0, else M; its box-load map is seg_map.  A filter row may be split into
+     * several entries (so that the accumulators fit TMEM with 128-column tiles): entry t covers the seg_cnt[t] taps
+     * kw = seg_kw0[t] .. of filter row m_dy/n_dy[t]; output tap slot of its j-th tap = tap_out[t] + j. */
+    int32_t seg_mode, seg_rows, seg_taps, seg_on_m;
+    int32_t seg_kw0[ACLGAN_MAX_TAPS], seg_cnt[ACLGAN_MAX_TAPS];
+    aclgan_tmap_spec seg_map[2];
 } aclgan_wgrad_plan;
 
 /* ---- padded NHWC activation handle ---- */

@@ -192,6 +192,8 @@ def run_wgrad(mem, plan):
     segs = [(0, 0)] if plan.nseg == 1 else [(0, 0), (0, 1), (1, 0)]
     ncols = 64 * plan.n_chunks
     pix = plan.box_x * plan.box_y * plan.box_z
+    if plan.seg_mode:
+        return _run_wgrad_seg(mem, plan, dw, dwoff, segs, ncols)
     for tap in range(plan.num_taps):
         for mt in range(plan.m_tiles):
             for nt in range(plan.n_tiles):
@@ -222,6 +224,51 @@ def run_wgrad(mem, plan):
                         continue
                     idx = dwoff + m * plan.dw_sm + plan.tap_out[tap] * plan.dw_st + n0 + torch.arange(cnt)
                     dw[idx] += acc[r, :cnt].to(dw.dtype)
+
+
+def _run_wgrad_seg(mem, plan, dw, dwoff, segs, ncols):
+    """segment mode (wgrad_seg_kernel): per filter row one CTA-tile; the shifted operand is staged once per 64-pixel
+    block as seg_rows pixels and tap kw uses its rows [kw, kw + 64)"""
+    assert plan.box_x == 64 and plan.box_y == 1 and plan.box_z == 1
+    for tap in range(plan.num_taps):
+        for mt in range(plan.m_tiles):
+            for nt in range(plan.n_tiles):
+                kw0, cnt = plan.seg_kw0[tap], plan.seg_cnt[tap]
+                assert 1 <= cnt <= plan.seg_taps and cnt * ncols <= 512
+                acc = torch.zeros(cnt, 128, ncols, dtype=torch.float64)
+                for bz in range(plan.blocks_z):
+                    for by in range(plan.blocks_y):
+                        for bx in range(plan.blocks_x):
+                            x0, y0, z0 = bx * 64, by, bz
+                            for pm, pn in segs:
+                                mm = plan.seg_map[pm] if plan.seg_on_m else plan.mop[pm][0]
+                                nm = plan.nop[pn][0] if plan.seg_on_m else plan.seg_map[pn]
+                                mr = plan.seg_rows if plan.seg_on_m else 64
+                                nr = 64 if plan.seg_on_m else plan.seg_rows
+                                Mt = torch.zeros(mr, 128, dtype=torch.float64)
+                                for c in range(plan.m_chunks):
+                                    Mt[:, c * 64:(c + 1) * 64] = tma_box(
+                                        mem, mm, ((mt * 2 + c) * 64, x0 + plan.m_dx[tap], y0 + plan.m_dy[tap], z0)).reshape(mr, 64)
+                                Nt = torch.zeros(nr, ncols, dtype=torch.float64)
+                                for c in range(plan.n_chunks):
+                                    Nt[:, c * 64:(c + 1) * 64] = tma_box(
+                                        mem, nm, ((nt * plan.n_chunks + c) * 64, x0 + plan.n_dx[tap], y0 + plan.n_dy[tap], z0)).reshape(nr, 64)
+                                for j in range(cnt):
+                                    kw = kw0 + j
+                                    Mw = Mt[kw:kw + 64] if plan.seg_on_m else Mt
+                                    Nw = Nt if plan.seg_on_m else Nt[kw:kw + 64]
+                                    acc[j] += Mw.t() @ Nw
+                for kw in range(cnt):
+                    for r in range(128):
+                        m = mt * 128 + r
+                        if m >= plan.M:
+                            continue
+                        n0 = nt * ncols
+                        cnt = min(ncols, plan.Nn - n0)
+                        if cnt <= 0:
+                            continue
+                        idx = dwoff + m * plan.dw_sm + (plan.tap_out[tap] + kw) * plan.dw_st + n0 + torch.arange(cnt)
+                        dw[idx] += acc[kw, r, :cnt].to(dw.dtype)
 
 
 def unpack_wgrad(desc, dw_flat, shape_oihw):

@@ -178,6 +178,11 @@ WGRAD_CASES = [
     (64, 128, 4, 2, 1, 0, 1, 32, 32, 2),
     (16, 32, 4, 2, 1, 0, 2, 32, 32, 2),
     (64, 128, 4, 2, 1, 0, 1, 16, 16, 1),
+    # segment mode (stride 1, 64-pixel output rows)
+    (128, 128, 3, 1, 1, 0, 2, 16, 64, 1),
+    (256, 128, 5, 1, 2, 0, 1, 8, 128, 1),
+    (128, 64, 5, 1, 2, 0, 1, 8, 64, 1),
+    (64, 128, 3, 1, 1, 0, 2, 4, 64, 2),
     # >= 4096 reduction pixels and narrow operands: 128-pixel pipeline stages
     (64, 64, 3, 1, 1, 0, 2, 64, 64, 1),
     (64, 64, 3, 1, 1, 0, 2, 64, 64, 2),

@@ -83,7 +83,7 @@ def test_conv_fwd_plan(cin, cout, k, s, pad, window, n, h, w, planes):
     o, obuf = out_spec(mem, n, ho, wo, cout, N.OUT_F32, pad=1, act=N.ACT_LRELU, bias=bias, mirror=1)
     plan = N.IgemmPlan()
     N.check(L.aclgan_plan_conv_fwd(C.byref(desc), C.byref(act), wptr, C.byref(o), C.byref(plan)), "plan fwd")
-    assert bool(plan.seg_mode) == (s == 1 and not window and k > 1)
+    assert bool(plan.seg_mode) == (s == 1 and window != 1 and k > 1)
     # the box-per-tap description (plain kernels) and, when present, the segment description (igemm_seg_kernel)
     for use_seg in ([False, True] if plan.seg_mode else [False]):
         obuf.zero_()
@@ -176,6 +176,10 @@ WGRAD_CASES = [
     (64, 64, 3, 1, 1, 0, 2, 32, 64, 1),       # >= 4096 reduction pixels, 2 chunks: 128-pixel stages
     (3, 64, 7, 1, 3, 1, 1, 64, 64, 1),
     (64, 4, 7, 1, 3, 2, 1, 64, 64, 1),
+    # segment mode (stride 1, output rows a multiple of 64 pixels): N-shifted, M-shifted (swapped roles), two planes
+    (128, 128, 3, 1, 1, 0, 1, 3, 64, 1),
+    (128, 64, 5, 1, 2, 0, 1, 3, 128, 1),
+    (64, 128, 3, 1, 1, 0, 2, 2, 64, 2),
 ]
 
 
@@ -200,6 +204,7 @@ def test_conv_wgrad_plan(cin, cout, k, s, pad, window, n, h, w, planes):
     dw = torch.zeros(rows.value * kt.value, dtype=torch.float64)
     plan = N.WgradPlan()
     N.check(L.aclgan_plan_conv_wgrad(C.byref(desc), C.byref(yact), C.byref(xact), mem.add(dw), C.byref(plan)), "plan wgrad")
+    assert bool(plan.seg_mode) == (s == 1 and window == 0 and 1 < k <= 7 and wo % 64 == 0)
     emul.run_wgrad(mem, plan)
     got = emul.unpack_wgrad(desc, dw, (cout, cin, k, k))
     ref = torch.nn.grad.conv2d_weight(xeff, (cout, cin, k, k), yeff, stride=s)

@@ -307,6 +307,24 @@ class Engine:
             tape.push(bwd)
         return out
 
+    def dup_plane(self, tape, x):
+        """two copies of a plane along the batch axis (one content code decoded with two styles in ONE batched pass:
+        trainer.py:109,113 decode c_2 twice); the gradients of both halves are summed back into `x`"""
+        out = ActT(self, 2 * x.n, x.h, x.w, x.c_valid, x.pad)
+        out.buf[:, :x.numel].copy_(x.buf[:, :x.numel])
+        out.buf[:, x.numel:2 * x.numel].copy_(x.buf[:, :x.numel])
+        out.requires_grad = x.requires_grad
+        if tape.enabled and x.requires_grad:
+            def bwd():
+                n = x.n
+                if out.gp is not None:
+                    x.add_gp(out.gp[:n] + out.gp[n:])
+                if out.gr is not None:
+                    x.add_gr(out.gr[:n] + out.gr[n:])
+                out.gp = out.gr = None
+            tape.push(bwd)
+        return out
+
     # ------------------------------------------------------------------------------------------ conv pieces
     def _out_plane(self, dst, act, bias, slope=0.2):
         """OutSpec that makes a conv epilogue write straight into plane `dst` (interior + reflect halo)."""

@@ -62,6 +62,7 @@ class aclgan_Trainer(nn.Module):
         self.use_graphs = bool(int(hp.get("cuda_graphs", os.environ.get("ACLGAN_CUDA_GRAPHS", "1"))))
         self._graphs = {}
         self._launches = {}
+        self.merge_passes = bool(int(hp.get("merge_passes", os.environ.get("ACLGAN_MERGE_PASSES", "1"))))
         self.expose_grads = bool(int(hp.get("expose_grads", 1)))   # keep every param.grad readable after an update
         self._ready = False
         self._noise = None          # optional injected style noise (tests / graph replay): list of 3 tensors
@@ -252,6 +253,20 @@ class aclgan_Trainer(nn.Module):
             tape.push(bwd)
         return res
 
+    def _slice(self, tape, img, lo, hi):
+        """rows [lo, hi) of a batched image node (inverse of _cat)"""
+        res = E.ImgT(img.t[lo:hi], requires_grad=img.requires_grad)
+        if tape.enabled and res.requires_grad:
+            def bwd():
+                if res.grad is None:
+                    return
+                if img.grad is None:
+                    img.grad = torch.zeros_like(img.t)
+                img.grad[lo:hi] += res.grad
+                res.grad = None
+            tape.push(bwd)
+        return res
+
     @staticmethod
     def _lsgan_multi(outs, n, targets, weights):
         """LSGAN terms of several images pushed through a discriminator as one batch: per image group i (rows
@@ -290,16 +305,30 @@ class aclgan_Trainer(nn.Module):
         AB, BA = self.gen_AB, self.gen_BA
         z_1, z_2, z_3 = zs
         r = {}
-        c_1 = AB.enc_content_fwd(tape, x_a)
-        c_2 = BA.enc_content_fwd(tape, x_a)
-        o_b = AB.dec_fwd(tape, c_1, z_1)
-        o_a = BA.dec_fwd(tape, c_2, E.ImgT(self.alpha * z_2.t))
-        if need_recon:
+        if need_recon and self.merge_passes:
+            # passes that share weights and do not depend on each other run as ONE batched pass (every layer on the path
+            # is per-sample, so the results are those of the separate passes): AB encodes [x_a; x_b] and decodes
+            # [(c_1, z_1); (c_4, s_4)], BA decodes c_2 with [alpha z_2; s_2] - half the launches, better-filled grids
+            n = x_a.t.shape[0]
+            c_14 = AB.enc_content_fwd(tape, self._cat(tape, [x_a, x_b]))
+            c_2 = BA.enc_content_fwd(tape, x_a)
             s_2 = BA.enc_style_fwd(tape, x_a)
-            c_4 = AB.enc_content_fwd(tape, x_b)
             s_4 = AB.enc_style_fwd(tape, x_b)
-            r["o_rec_a"] = BA.dec_fwd(tape, c_2, s_2)
-            r["o_rec_b"] = AB.dec_fwd(tape, c_4, s_4)
+            o_14 = AB.dec_fwd(tape, c_14, self._cat(tape, [z_1, s_4]))
+            o_b, r["o_rec_b"] = self._slice(tape, o_14, 0, n), self._slice(tape, o_14, n, 2 * n)
+            o_22 = BA.dec_fwd(tape, self.eng.dup_plane(tape, c_2), self._cat(tape, [E.ImgT(self.alpha * z_2.t), s_2]))
+            o_a, r["o_rec_a"] = self._slice(tape, o_22, 0, n), self._slice(tape, o_22, n, 2 * n)
+        else:
+            c_1 = AB.enc_content_fwd(tape, x_a)
+            c_2 = BA.enc_content_fwd(tape, x_a)
+            o_b = AB.dec_fwd(tape, c_1, z_1)
+            o_a = BA.dec_fwd(tape, c_2, E.ImgT(self.alpha * z_2.t))
+            if need_recon:
+                s_2 = BA.enc_style_fwd(tape, x_a)
+                c_4 = AB.enc_content_fwd(tape, x_b)
+                s_4 = AB.enc_style_fwd(tape, x_b)
+                r["o_rec_a"] = BA.dec_fwd(tape, c_2, s_2)
+                r["o_rec_b"] = AB.dec_fwd(tape, c_4, s_4)
         if focus:
             x_B_fake = self._blend(tape, o_b, x_a)
             x_A_fake = self._blend(tape, o_a, x_a)

@@ -142,8 +142,15 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel from the committed ncu --set full capture
+# (profiles/r1_top_kernels_v5.md): 19.2 MB read (input plane 17.8 MB + packed weights 1.2 MB), the 16.8 MB output stays in L2
+ROOFLINE_TRAFFIC_BYTES = 19.2e6
+
+
 def kernel_roofline(eng_precision, batch, pk):
-    """dominant kernel = the 3x3 256->256 reflect-pad conv of the residual blocks (forward implicit GEMM), timed alone"""
+    """dominant kernel = the 3x3 256->256 reflect-pad conv of the residual blocks (forward implicit GEMM,
+    igemm_seg_pair_kernel: 16 of the 28 generator convs per encode+decode), timed alone with CUDA events, L2 flushed
+    between launches.  Algorithmic work per launch = 2 * (batch*64*64) * 256 * (9*256) FLOP."""
     import ctypes as C
     import torch
     import aclgan_native as N
@@ -157,8 +164,8 @@ def kernel_roofline(eng_precision, batch, pk):
     arena.finalize()
     x = E.ActT(eng, batch, h, h, c, 1, zero=True)
     x.buf.normal_()
-    out = E.ActT(eng, batch, h, h, c, 1)
-    o = eng._out_plane(out, N.ACT_NONE, b)
+    y = eng.new_dense(batch, h, h, c)                   # as in the residual blocks: raw conv output feeding the norm
+    o = eng._out_dense(y, b)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream()
     for _ in range(3):
@@ -176,8 +183,9 @@ def kernel_roofline(eng_precision, batch, pk):
     segs = 3 if eng_precision == "fp32x3" else 1
     flops = 2.0 * batch * h * h * c * c * 9
     achieved = flops / (ms * 1e-3) / 1e12
-    return dict(bound="tensor", kernel="igemm_kernel 3x3 256->256 s1 reflect, %dx64x64 (M=%d N=256 K=2304)" % (batch, batch * h * h),
-                achieved=achieved, peak=pk["burst"], unit="TFLOP/s", frac=achieved / pk["burst"], traffic=None,
+    return dict(bound="tensor", kernel="igemm_seg_pair_kernel 3x3 256->256 s1 reflect, %dx64x64 (M=%d N=256 K=2304)" % (batch, batch * h * h),
+                achieved=achieved, peak=pk["burst"], unit="TFLOP/s", frac=achieved / pk["burst"],
+                traffic=ROOFLINE_TRAFFIC_BYTES if (batch == 8 and eng_precision == "bf16") else None, traffic_unit="bytes of DRAM per launch (ncu)",
                 peak_source=pk["src"] + " bf16_tflops (burst: kernel timed alone)", ms=ms, tensor_passes=segs,
                 note="achieved counts algorithmic conv FLOPs once; fp32x3 executes 3 bf16 tensor-core passes per product")
 

@@ -39,19 +39,44 @@ class Precision:
 
 
 class Tape:
-    """Hand-scheduled reverse pass: forward operators push closures, backward() runs them in reverse."""
+    """Hand-scheduled reverse pass: forward operators push closures, backward() runs them in reverse.
+
+    Closures recorded while `tag` is set (trainer: one tag per discriminator pass) belong to an independent chain; in
+    backward() consecutive chains run on their own side streams (fork from / join into the caller's stream), so the
+    many sub-wave kernels of the small discriminator scales overlap instead of serialising.  Under CUDA-graph capture
+    the fork / join become parallel branches of the graph."""
 
     def __init__(self, enabled=True):
         self.ops = []
         self.enabled = enabled
+        self.tag = None
 
     def push(self, fn):
         if self.enabled:
-            self.ops.append(fn)
+            self.ops.append((fn, self.tag))
 
-    def backward(self):
+    def backward(self, streams=None):
+        main = torch.cuda.current_stream() if (streams and torch.cuda.is_available()) else None
+        cur, used = None, set()
         while self.ops:
-            self.ops.pop()()
+            fn, tag = self.ops.pop()
+            if main is None or tag is None:
+                if main is not None and used:
+                    for t in used:                      # join: everything after this sees the chains' results
+                        main.wait_stream(streams[t])
+                    used.clear()
+                cur = None
+                fn()
+                continue
+            if tag != cur:
+                streams[tag].wait_stream(main)          # fork point = everything the main stream has issued so far
+                used.add(tag)
+                cur = tag
+            with torch.cuda.stream(streams[tag]):
+                fn()
+        if main is not None:
+            for t in used:
+                main.wait_stream(streams[t])
 
 
 class ActT:

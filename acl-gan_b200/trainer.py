@@ -63,6 +63,8 @@ class aclgan_Trainer(nn.Module):
         self._graphs = {}
         self._launches = {}
         self.merge_passes = bool(int(hp.get("merge_passes", os.environ.get("ACLGAN_MERGE_PASSES", "1"))))
+        self.parallel_dis = bool(int(hp.get("parallel_dis", os.environ.get("ACLGAN_PARALLEL_DIS", "1"))))
+        self._side_streams = None
         self.expose_grads = bool(int(hp.get("expose_grads", 1)))   # keep every param.grad readable after an update
         self._ready = False
         self._noise = None          # optional injected style noise (tests / graph replay): list of 3 tensors
@@ -234,6 +236,30 @@ class aclgan_Trainer(nn.Module):
             tape.push(bwd)
         return res
 
+    # ------------------------------------------------------------------------------------------ stream forks
+    def _dis_parallel(self, tape, jobs):
+        """runs the three discriminator passes `jobs` = [callable(tape) -> logits] as independent chains: forward on side
+        streams forked from the current one, and (through the tape tags) backward likewise.  The passes only read shared
+        tensors and write private ones; gradients meet again in the image nodes after the join."""
+        if not self.parallel_dis or not torch.cuda.is_available():
+            return [job(tape) for job in jobs]
+        if self._side_streams is None:
+            self._side_streams = [torch.cuda.Stream() for _ in range(3)]
+        main = torch.cuda.current_stream()
+        outs = []
+        for k, job in enumerate(jobs):
+            st = self._side_streams[k]
+            st.wait_stream(main)
+            tape.tag = k
+            try:
+                with torch.cuda.stream(st):
+                    outs.append(job(tape))
+            finally:
+                tape.tag = None
+        for st in self._side_streams[:len(jobs)]:
+            main.wait_stream(st)
+        return outs
+
     def _cat(self, tape, imgs):
         """batch-concatenates image nodes so a discriminator runs ONCE over all of them (3x fewer, 3x larger launches)"""
         if len(imgs) == 1:
@@ -368,13 +394,15 @@ class aclgan_Trainer(nn.Module):
         r = self._cycle(tape, xa, xb, zs, need_recon=True)
 
         gw, gcw = hp["gan_w"], hp["gan_cw"]
-        la = self._lsgan_multi(self.dis_A.dis(tape, self._cat(tape, [r["x_A_fake"], r["x_A2_fake"]])), n,
-                               [1.0, 1.0], [0.5 * gw, 0.5 * gw])
+        cat_a = self._cat(tape, [r["x_A_fake"], r["x_A2_fake"]])
+        cat_2a, cat_2b = self._cat(tape, [xa, xa]), self._cat(tape, [r["x_A_fake"], r["x_A2_fake"]])
+        out_a, out_b, out_2 = self._dis_parallel(tape, [lambda t: self.dis_A.dis(t, cat_a),
+                                                         lambda t: self.dis_B.dis(t, r["x_B_fake"]),
+                                                         lambda t: self.dis_2.dis(t, cat_2a, cat_2b)])
+        la = self._lsgan_multi(out_a, n, [1.0, 1.0], [0.5 * gw, 0.5 * gw])
         self.loss_gen_adv_A = (la[0] + la[1]) * 0.5
-        self.loss_gen_adv_B = self._lsgan(self.dis_B.dis(tape, r["x_B_fake"]), 1.0, gw)
-        l2 = self._lsgan_multi(self.dis_2.dis(tape, self._cat(tape, [xa, xa]),
-                                              self._cat(tape, [r["x_A_fake"], r["x_A2_fake"]])), n,
-                               [1.0, 0.0], [gcw, gcw])
+        self.loss_gen_adv_B = self._lsgan(out_b, 1.0, gw)
+        l2 = self._lsgan_multi(out_2, n, [1.0, 0.0], [gcw, gcw])
         self.loss_gen_adv_2 = l2[0] + l2[1]
         total = gw * self.loss_gen_adv_A + gw * self.loss_gen_adv_B + gcw * self.loss_gen_adv_2
 
@@ -409,7 +437,7 @@ class aclgan_Trainer(nn.Module):
         rec_b.add_grad(torch.sign(db) * (rw / db.numel()))
         self.loss_gen_total = total + rw * self.loss_idt_A + rw * self.loss_idt_B
 
-        tape.backward()
+        tape.backward(self._side_streams)
         for d in (self.dis_A, self.dis_B, self.dis_2):
             d.train_weights = True
 
@@ -437,16 +465,19 @@ class aclgan_Trainer(nn.Module):
         gw, gcw = hp["gan_w"], hp["gan_cw"]
         # each discriminator runs once over the batch-concatenation of its inputs; dis_A(x_a) is counted twice with
         # weight 1/2 in the reference (trainer.py:283-284) == once with weight 1
-        la = self._lsgan_multi(self.dis_A.dis(tape, self._cat(tape, [xa, fake_a, fake_a2])), n,
-                               [1.0, 0.0, 0.0], [gw, 0.5 * gw, 0.5 * gw])
+        cat_a, cat_b = self._cat(tape, [xa, fake_a, fake_a2]), self._cat(tape, [fake_b, xb])
+        cat_2a, cat_2b = self._cat(tape, [xa, xa]), self._cat(tape, [fake_a, fake_a2])
+        out_a, out_b, out_2 = self._dis_parallel(tape, [lambda t: self.dis_A.dis(t, cat_a),
+                                                         lambda t: self.dis_B.dis(t, cat_b),
+                                                         lambda t: self.dis_2.dis(t, cat_2a, cat_2b)])
+        la = self._lsgan_multi(out_a, n, [1.0, 0.0, 0.0], [gw, 0.5 * gw, 0.5 * gw])
         self.loss_dis_A = (la[1] + la[2] + 2.0 * la[0]) * 0.5
-        lb = self._lsgan_multi(self.dis_B.dis(tape, self._cat(tape, [fake_b, xb])), n, [0.0, 1.0], [gw, gw])
+        lb = self._lsgan_multi(out_b, n, [0.0, 1.0], [gw, gw])
         self.loss_dis_B = lb[0] + lb[1]
-        l2 = self._lsgan_multi(self.dis_2.dis(tape, self._cat(tape, [xa, xa]), self._cat(tape, [fake_a, fake_a2])), n,
-                               [0.0, 1.0], [gcw, gcw])
+        l2 = self._lsgan_multi(out_2, n, [0.0, 1.0], [gcw, gcw])
         self.loss_dis_2 = l2[0] + l2[1]
         self.loss_dis_total = gw * self.loss_dis_A + gw * self.loss_dis_B + gcw * self.loss_dis_2
-        tape.backward()
+        tape.backward(self._side_streams)
 
     @property
     def launches_per_step_pair(self):

@@ -12,12 +12,17 @@ import engine as E  # noqa: E402
 
 eng = E.Engine("bf16")
 L = N.lib()
-SHAPES = [  # cin, cout, k, pad, n, h
+SHAPES = [  # cin, cout, k, pad, n, h[, stride]
     (256, 256, 3, 1, 8, 64),
     (256, 128, 5, 2, 8, 128),
     (128, 64, 5, 2, 8, 256),
     (64, 4, 7, 3, 8, 256),
+    (64, 128, 4, 1, 8, 256, 2),      # content / style encoder down-sampling, D layers (4x4 stride 2)
+    (128, 256, 4, 1, 8, 128, 2),
+    (256, 512, 4, 1, 24, 32, 2),
 ]
+if os.environ.get("ONLY_S2"):
+    SHAPES = [s for s in SHAPES if len(s) > 6]
 CONFIGS = [
     ("box-per-tap plans, plain kernels", dict(ACLGAN_SEG="0")),
     ("segment plans on plain kernels", dict(ACLGAN_SEG="1", ACLGAN_SEGK="0")),
@@ -35,11 +40,13 @@ KEYS = sorted({k for _, c in CONFIGS for k in c})
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 prof = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
 L.aclgan_igemm_set_prof.argtypes = [C.c_uint64]
-for cin, cout, k, pad, n, h in SHAPES:
+for shp in SHAPES:
+    cin, cout, k, pad, n, h = shp[:6]
+    stride = shp[6] if len(shp) > 6 else 1
     w = torch.nn.Parameter(torch.randn(cout, cin, k, k, device="cuda") * 0.02)
     b = torch.nn.Parameter(torch.zeros(cout, device="cuda"))
     arena = E.GradArena(eng.device)
-    layer = E.ConvLayer(eng, arena, w, b, 1, pad, N.WINDOW_OUT if cout <= 8 else N.WINDOW_NONE)
+    layer = E.ConvLayer(eng, arena, w, b, stride, pad, N.WINDOW_OUT if cout <= 8 else N.WINDOW_NONE)
     arena.finalize()
     x = E.ActT(eng, n, h, h, cin, pad, zero=True)
     x.buf.normal_()
@@ -52,10 +59,12 @@ for cin, cout, k, pad, n, h in SHAPES:
         o.N, o.H, o.W, o.C = n, h, h, cout
         o.bias, o.bias_n = b.data_ptr(), cout
     else:
-        y = eng.new_dense(n, h, h, cout)
+        ho = (h + 2 * pad - k) // stride + 1
+        y = eng.new_dense(n, ho, ho, cout)
         o = eng._out_dense(y, b)
-    flops = 2.0 * n * h * h * cin * cout * k * k
-    print("== %dx%d %d->%d, %d x %dx%d  (%.1f GFLOP)" % (k, k, cin, cout, n, h, h, flops / 1e9))
+    ho = (h + 2 * pad - k) // stride + 1
+    flops = 2.0 * n * ho * ho * cin * cout * k * k
+    print("== %dx%d s%d %d->%d, %d x %dx%d  (%.1f GFLOP)" % (k, k, stride, cin, cout, n, h, h, flops / 1e9))
     for name, env in CONFIGS:
         for key in KEYS:
             os.environ.pop(key, None)

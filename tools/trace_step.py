@@ -47,6 +47,20 @@ span = ks[-1][1] - ks[0][0]
 print("kernels %d  span %.2f ms  sum of kernel time %.2f ms  idle gaps %.2f ms" % (len(ks), span / 1e3, busy / 1e3, gaps / 1e3))
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
     print("%6d %9.3f ms %5.1f%%  avg %7.1f us  gap-after %7.3f ms  %s" % (v[0], v[1] / 1e3, 100 * v[1] / span, v[1] / v[0], gap_after[k] / 1e3, k))
+# duration histogram of the heavy kernels: where the launch-bound tail is
+print("-- duration buckets (count / total ms) per kernel")
+edges = [0, 10, 20, 40, 80, 160, 320, 1e9]
+for key in ("igemm_seg_pair", "igemm_seg_kernel", "igemm_pair_kernel", "igemm_kernel", "wgrad_seg", "wgrad_kernel", "block_bwd_apply",
+            "block_bwd_reduce", "norm_apply"):
+    sel = [e - s0 for s0, e, name in ks if key in name]
+    if not sel:
+        continue
+    cells = []
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        b = [d for d in sel if lo <= d < hi]
+        cells.append("%3d/%5.2f" % (len(b), sum(b) / 1e3))
+    print("%-18s %s" % (key, "  ".join(cells)))
+print("   buckets (us): " + "  ".join("[%g,%g)" % (lo, hi) for lo, hi in zip(edges[:-1], edges[1:])))
 # the longest individual kernels
 print("-- longest launches")
 for s, e, name in sorted(ks, key=lambda t: t[0] - t[1])[:25]:

@@ -334,16 +334,29 @@ class aclgan_Trainer(nn.Module):
         if need_recon and self.merge_passes:
             # passes that share weights and do not depend on each other run as ONE batched pass (every layer on the path
             # is per-sample, so the results are those of the separate passes): AB encodes [x_a; x_b] and decodes
-            # [(c_1, z_1); (c_4, s_4)], BA decodes c_2 with [alpha z_2; s_2] - half the launches, better-filled grids
+            # [(c_1, z_1); (c_4, s_4)], BA decodes c_2 with [alpha z_2; s_2] - half the launches, better-filled grids.
+            # The AB and the BA pass are independent chains (own weights, own gradients): forked like the discriminators.
             n = x_a.t.shape[0]
-            c_14 = AB.enc_content_fwd(tape, self._cat(tape, [x_a, x_b]))
-            c_2 = BA.enc_content_fwd(tape, x_a)
-            s_2 = BA.enc_style_fwd(tape, x_a)
-            s_4 = AB.enc_style_fwd(tape, x_b)
-            o_14 = AB.dec_fwd(tape, c_14, self._cat(tape, [z_1, s_4]))
+            xab = self._cat(tape, [x_a, x_b])
+            az_2 = E.ImgT(self.alpha * z_2.t)
+
+            def chain_ab(t):
+                c_14 = AB.enc_content_fwd(t, xab)
+                s_4 = AB.enc_style_fwd(t, x_b)
+                return AB.dec_fwd(t, c_14, self._cat(t, [z_1, s_4]))
+
+            def chain_ba(t):
+                c_2 = BA.enc_content_fwd(t, x_a)
+                s_2 = BA.enc_style_fwd(t, x_a)
+                return BA.dec_fwd(t, self.eng.dup_plane(t, c_2), self._cat(t, [az_2, s_2]))
+
+            o_14, o_22 = self._dis_parallel(tape, [chain_ab, chain_ba])
             o_b, r["o_rec_b"] = self._slice(tape, o_14, 0, n), self._slice(tape, o_14, n, 2 * n)
-            o_22 = BA.dec_fwd(tape, self.eng.dup_plane(tape, c_2), self._cat(tape, [E.ImgT(self.alpha * z_2.t), s_2]))
             o_a, r["o_rec_a"] = self._slice(tape, o_22, 0, n), self._slice(tape, o_22, n, 2 * n)
+        elif not need_recon:
+            az_2 = E.ImgT(self.alpha * z_2.t)
+            o_b, o_a = self._dis_parallel(tape, [lambda t: AB.dec_fwd(t, AB.enc_content_fwd(t, x_a), z_1),
+                                                 lambda t: BA.dec_fwd(t, BA.enc_content_fwd(t, x_a), az_2)])
         else:
             c_1 = AB.enc_content_fwd(tape, x_a)
             c_2 = BA.enc_content_fwd(tape, x_a)

@@ -596,6 +596,8 @@ class Engine:
         def bwd():
             if out.grad is None:
                 return
+            if out.grad.is_cuda:        # assembled on the caller's stream (trainer._slice), consumed on this chain's
+                out.grad.record_stream(torch.cuda.current_stream())
             dy = ActT(self, n, ho, wo, cout, layer.k - 1, cs=8, zero=True)
             a = N.ImgGradPackArgs()
             a.dimg = out.grad.data_ptr()

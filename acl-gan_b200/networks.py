@@ -552,21 +552,31 @@ class MsImageDis(_EngineNet):
     def dis(self, tape, img0, img1=None):
         """forward over all scales; img1 = second image of a channel-concatenated pair (dis_2).
         returns a list of E.ImgT logits [N,1,h,w]"""
+        pyr = self.dis_pyramid(tape, img0, img1)
+        return [self.dis_scale(tape, s, pyr[s]) for s in range(len(self.cnns))]
+
+    def dis_pyramid(self, tape, img0, img1=None):
+        """the input of every scale: the image(s) and their AvgPool2d(3, 2, 1) pyramid (networks.py:33,53)"""
+        self._ensure_bound()
+        imgs = [img0, img1]
+        pyr = [imgs]
+        for _ in range(len(self.cnns) - 1):
+            imgs = [self._pool(tape, im) if im is not None else None for im in imgs]
+            pyr.append(imgs)
+        return pyr
+
+    def dis_scale(self, tape, s, imgs):
+        """one scale's PatchGAN (networks.py:38-47): the scales are independent chains once the pyramid exists"""
         self._ensure_bound()
         eng, tw = self._eng, self.train_weights and tape.enabled
         act = _ACT[self.activ]
-        outs = []
-        imgs = [img0, img1]
-        for s, net in enumerate(self.cnns):
-            x = eng.pack_image(tape, imgs[0], 1, 16, imgs[1])
-            blocks = [b for b in net if isinstance(b, Conv2dBlock)]
-            for i, blk in enumerate(blocks):
-                x = eng.conv_block(tape, blk._layer, x, norm=N.NORM_NONE, act=act,
-                                   out_pad=1 if i + 1 < len(blocks) else 0, train_w=tw)
-            outs.append(self._head(tape, net[-1], x, tw))
-            if s + 1 < len(self.cnns):
-                imgs = [self._pool(tape, im) if im is not None else None for im in imgs]
-        return outs
+        net = self.cnns[s]
+        x = eng.pack_image(tape, imgs[0], 1, 16, imgs[1])
+        blocks = [b for b in net if isinstance(b, Conv2dBlock)]
+        for i, blk in enumerate(blocks):
+            x = eng.conv_block(tape, blk._layer, x, norm=N.NORM_NONE, act=act,
+                               out_pad=1 if i + 1 < len(blocks) else 0, train_w=tw)
+        return self._head(tape, net[-1], x, tw)
 
     def _pool(self, tape, img):
         """AvgPool2d(3, 2, padding 1, count_include_pad=False) on the NCHW image (networks.py:33,53)"""
@@ -593,6 +603,9 @@ class MsImageDis(_EngineNet):
             def bwd():
                 if logit.grad is None:
                     return
+                # (seeded on the caller's stream, consumed on this chain's stream: keep the allocator from reusing it early)
+                if logit.grad.is_cuda:
+                    logit.grad.record_stream(torch.cuda.current_stream())
                 d = logit.grad.view(x.n, x.h, x.w)
                 logit.grad = None
                 if tw:

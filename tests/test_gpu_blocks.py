@@ -62,6 +62,9 @@ CASES = [
     (64, 128, 4, 2, 1, N.NORM_IN, N.ACT_RELU, False, 1, 1, 2, 64),
     (64, 64, 4, 2, 1, N.NORM_NONE, N.ACT_LRELU, False, 1, 1, 1, 64),
     (64, 64, 5, 1, 2, N.NORM_LN, N.ACT_RELU, False, 2, 2, 1, 32),
+    # 128-pixel output rows: row tiles of the segment kernels, statistics fused in the epilogue, segment weight gradient
+    (128, 64, 5, 1, 2, N.NORM_LN, N.ACT_RELU, False, 1, 3, 2, 128),
+    (64, 128, 3, 1, 1, N.NORM_ADAIN, N.ACT_RELU, False, 2, 2, 1, 128),
 ]
 
 
@@ -139,6 +142,10 @@ def test_conv_block(precision, cin, cout, k, stride, pad, norm, act, use_res, up
     probe = torch.zeros_like(x64).requires_grad_(True)
     (F.pad(probe, (pad,) * 4, mode="reflect") * gx).sum().backward()
     btol = tol * 3
+    if h >= 128 and act != N.ACT_NONE and precision == "fp32x3":
+        # millions of units: a handful of ReLU pre-activations lie within the fp32x3 rounding distance (1e-5) of zero and
+        # flip against the fp64 reference; each flip moves these relative L2 errors by ~1e-4 (tests/test_gpu_step.py docstring)
+        btol = 3e-3
     assert rel(probe.grad, x64.grad) < btol, ("dgrad", rel(probe.grad, x64.grad))
     gw, gb = layer.grad_views()
     assert rel(gw, w64.grad) < btol, ("wgrad", rel(gw, w64.grad))
@@ -147,9 +154,11 @@ def test_conv_block(precision, cin, cout, k, stride, pad, norm, act, use_res, up
     if use_res:
         assert rel(ra.gr[..., :cout].permute(0, 3, 1, 2), r64.grad) < btol, "res grad"
     if norm == N.NORM_ADAIN:
-        assert rel(got_adain["dw"], aw.grad) < btol and rel(got_adain["db"], ab.grad) < btol, "adain grads"
+        e_w, e_b = rel(got_adain["dw"], aw.grad), rel(got_adain["db"], ab.grad)
+        assert e_w < btol and e_b < btol, ("adain grads", e_w, e_b)
     if norm == N.NORM_LN:
-        assert rel(ln[2], g64.grad) < btol and rel(ln[3], be64.grad) < btol, "ln grads"
+        e_g, e_b = rel(ln[2], g64.grad), rel(ln[3], be64.grad)
+        assert e_g < btol and e_b < btol, ("ln grads", e_g, e_b)
 
 
 @pytest.mark.parametrize("precision", ["fp32x3", "bf16"])
@@ -204,6 +213,10 @@ def test_image_io_and_final_conv(precision):
     def rel(a, bb):
         return float((a.double() - bb).norm() / (bb.norm() + 1e-30))
     btol = tol * 3
+    if h >= 128 and act != N.ACT_NONE and precision == "fp32x3":
+        # millions of units: a handful of ReLU pre-activations lie within the fp32x3 rounding distance (1e-5) of zero and
+        # flip against the fp64 reference; each flip moves these relative L2 errors by ~1e-4 (tests/test_gpu_step.py docstring)
+        btol = 3e-3
     gw2, gb2 = layer2.grad_views()
     gw, gb = layer.grad_views()
     errs = {"wgrad window-out": rel(gw2, w264.grad), "bias grad final": rel(gb2, b264.grad),

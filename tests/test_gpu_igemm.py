@@ -89,6 +89,10 @@ DGRAD_CASES = [
     (64, 4, 7, 1, 3, 2, 8, 8, 1),
     (64, 4, 7, 1, 3, 2, 8, 8, 2),
     (64, 3, 7, 1, 3, 1, 32, 32, 1),
+    (256, 128, 5, 1, 2, 2, 128, 128, 1),      # cin 256 -> N = 256 pairs, 5 taps per stage
+    (128, 64, 5, 1, 2, 2, 128, 128, 1),       # cin 128 -> N = 128 pairs
+    (128, 64, 5, 1, 2, 2, 128, 128, 2),
+    (64, 64, 3, 1, 1, 2, 128, 128, 2),
 ]
 
 

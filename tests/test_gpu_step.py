@@ -352,3 +352,60 @@ def test_generator_parts_vs_oracle(golden_dir, precision):
     assert vals[len(vals) // 2] < 1e-3, "systematic gradient error"
     bad = {k: "%.2e" % v for k, v in report.items() if v > FLIP_CEIL}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("precision", ["fp32x3", "bf16"])
+def test_schedule_variants_agree(golden_dir, precision):
+    """The scheduling optimisations change WHEN things run, never what is computed: batched same-weight passes, parallel
+    chains on side streams (per discriminator and per scale) and CUDA-graph replay must reproduce the plain sequential
+    eager schedule - losses and every gradient - up to the order of fp32 atomics.  (Guards the cross-stream hand-offs.)"""
+    g32 = _load(golden_dir, "tiny", "fp32")
+    x_a, x_b, zs = _inputs(g32)
+    results = []
+    for variant in (dict(merge_passes=0, parallel_dis=0, cuda_graphs=0), dict(merge_passes=1, parallel_dis=1, cuda_graphs=1),
+                    dict(merge_passes=1, parallel_dis=1, parallel_scales=1, cuda_graphs=1),
+                    dict(merge_passes=1, parallel_dis=1, parallel_scales=1, cuda_graphs=0)):
+        g = dict(g32, cfg=dict(copy.deepcopy(g32["cfg"]), **variant))
+        tr, cfg = _build(g, precision)
+        with torch.no_grad():           # cusp-free operating point (module docstring)
+            for gnet in (tr.gen_AB, tr.gen_BA):
+                list(gnet.dec.model)[-1].conv.bias[3] -= 1.5
+        for opt in (tr.dis_opt, tr.gen_opt):
+            for grp in opt.param_groups:
+                grp["lr"] = 0.0
+        out = {}
+        for rep in range(2):            # second round = graph REPLAY (the first call captures)
+            tr._noise = zs[:3]
+            tr.dis_update(x_a.cuda(), x_b.cuda(), cfg)
+            for n in ("dis_A", "dis_B", "dis_2"):
+                for k, p in getattr(tr, n).named_parameters():
+                    out[(rep, n, k)] = p.grad.detach().double().cpu().clone()
+            out[(rep, "loss_dis_total")] = float(tr.loss_dis_total)
+            tr._noise = zs[3:]
+            tr.gen_update(x_a.cuda(), x_b.cuda(), cfg)
+            for n in ("gen_AB", "gen_BA"):
+                for k, p in getattr(tr, n).named_parameters():
+                    out[(rep, n, k)] = p.grad.detach().double().cpu().clone()
+            out[(rep, "loss_gen_total")] = float(tr.loss_gen_total)
+        results.append(out)
+    base = results[0]
+    # identical kernels on identical operands: only the order of fp32 atomics / partial sums differs (1e-7 on the norm
+    # statistics), which can still flip a ReLU unit (module docstring) - so the bulk must agree to rounding and no tensor
+    # may exceed the flip ceiling; a lost or doubled contribution (stream hazard) shows up as O(1)
+    ltol = 1e-5 if precision == "fp32x3" else 2e-3
+    for vi, other in enumerate(results[1:], 1):
+        errs = []
+        for key, ref in base.items():
+            if isinstance(ref, float):
+                assert abs(other[key] - ref) <= ltol * abs(ref) + 1e-7, (vi, key, other[key], ref)
+                continue
+            nrm = float(ref.norm())
+            if nrm < 1e-7:
+                continue
+            errs.append((float((other[key] - ref).norm()) / nrm, key))
+        errs.sort()
+        med, worst = errs[len(errs) // 2], errs[-1]
+        print("\n[schedule variant %d vs sequential eager, %s] gradient difference median %.2e, worst %.2e at %s" % (
+            vi, precision, med[0], worst[0], worst[1]))
+        assert med[0] < (1e-5 if precision == "fp32x3" else 1e-2), med
+        assert worst[0] < (FLIP_CEIL if precision == "fp32x3" else 0.5), worst

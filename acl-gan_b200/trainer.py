@@ -64,10 +64,11 @@ class aclgan_Trainer(nn.Module):
         self._launches = {}
         self.merge_passes = bool(int(hp.get("merge_passes", os.environ.get("ACLGAN_MERGE_PASSES", "1"))))
         self.parallel_dis = bool(int(hp.get("parallel_dis", os.environ.get("ACLGAN_PARALLEL_DIS", "1"))))
-        # one chain per (discriminator, scale) instead of per discriminator: ~1 % faster.  (It exposed a cross-stream
-        # allocator hazard - a gradient seeded on the caller's stream and released inside a chain's closure was reused
-        # early; fixed with record_stream at the two hand-off points.)  Kept off by default: nine streams for 1 %.
-        self.parallel_scales = bool(int(hp.get("parallel_scales", os.environ.get("ACLGAN_PARALLEL_SCALES", "0"))))
+        # one chain per (discriminator, scale) instead of per discriminator: the sub-wave kernels of the small scales
+        # overlap nine-fold.  (It exposed a cross-stream allocator hazard - a gradient seeded on the caller's stream and
+        # released inside a chain's closure was reused early; fixed with record_stream at the two hand-off points and
+        # guarded by tests/test_gpu_step.py::test_schedule_variants_agree.)
+        self.parallel_scales = bool(int(hp.get("parallel_scales", os.environ.get("ACLGAN_PARALLEL_SCALES", "1"))))
         self._side_streams = None
         self.expose_grads = bool(int(hp.get("expose_grads", 1)))   # keep every param.grad readable after an update
         self._ready = False

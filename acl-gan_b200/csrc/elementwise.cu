@@ -971,8 +971,6 @@ extern "C" int aclgan_norm_apply(const aclgan_apply_args* a, void* stream) {
     return (int)cudaGetLastError();
 }
 
-// register budget of the fast kernels: 1 = uncapped (about 180 registers, 8 warps / SM), 2 = capped at 128 (some spills,
-// 16 warps / SM); env ACLGAN_BWD_OCC overrides
 // variant 0: 4 pixels / thread, 2 CTAs / SM (128 registers); 1: 2 pixels, 3 CTAs (85); 2: 2 pixels, 4 CTAs (64)
 static int bwd_variant() {
     static int v = -1;

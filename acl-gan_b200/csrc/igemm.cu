@@ -50,7 +50,6 @@ struct alignas(64) IgemmKParams {
     CUtensorMap b_seg[2];                           // rank 3 (k element, weight row, tap): box = 64 x rows x seg_taps
     int seg_rows, num_segs, seg_taps;
     int seg_a_bytes, seg_btile_bytes, seg_stage_bytes, seg_ns;   // shared-memory ring geometry chosen by the host
-    int seg_bo;                                     // 1: descriptors carry the matrix base offset of the shifted start row
     int epi_direct;
     long long* prof;                                // perf triage: per-CTA role timers [cta][8] (clock cycles) or null
     int seg_dx[16], seg_dy[16];
@@ -862,10 +861,6 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
 constexpr int kSegMaxStages = 6;
 constexpr int kSegSmemBytes = 232448;   // the whole opt-in budget; the ring is sized from it by the host
 
-__device__ __forceinline__ uint64_t with_base_offset(uint64_t desc, uint32_t rows) {
-    return desc | (static_cast<uint64_t>(rows & 7u) << 49);
-}
-
 // One pipeline stage = one filter row of one 64-channel chunk: the A segment (seg_rows pixels) and the weight tiles of
 // the row's k taps ([tap][b_rows][64], ONE rank-3 TMA box), i.e. two TMA instructions, one barrier round trip and 4*k
 // MMAs per stage - the single-thread producer / issuer loops cost a few hundred cycles per round trip, which a stage of
@@ -1184,10 +1179,9 @@ static int fill_kparams(const aclgan_igemm_plan* pl, IgemmKParams* kp) {
         kp->epi_direct = ed != nullptr ? atoi(ed) : 1;
     }
     {
-        // measured on B200: the 128B swizzle of a UMMA operand is a function of the absolute shared-memory address
-        // bits, so a row-shifted start address needs NO matrix base offset (with it the results are wrong)
-        const char* bo = getenv("ACLGAN_SEG_BO");
-        kp->seg_bo = bo != nullptr ? atoi(bo) : 0;
+        // (measured on B200: the 128B swizzle of a UMMA operand is a function of the absolute shared-memory address
+        // bits, so the row-shifted start addresses of the segment kernel need NO matrix base offset in the descriptor;
+        // with the offset set to (addr >> 7) & 7 the results are wrong)
         const char* sd = getenv("ACLGAN_SEG_DEBUG");     // perf triage: 1 = every tap reads rows [0, 128) (aligned start)
         if (sd != nullptr && atoi(sd) == 1)
             for (int t = 0; t < ACLGAN_MAX_TAPS; ++t) kp->tap_row[t] = 0;

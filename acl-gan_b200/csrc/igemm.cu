@@ -858,6 +858,9 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
 // per filter row and chunk) and B weight tiles (one per tap).
 // Templated on PAIR: cta_group::2 (two CTAs, 256-pixel tile, B split in halves) or one CTA.
 // =====================================================================================================================
+#ifndef ACLGAN_SEG_MAXREG
+#define ACLGAN_SEG_MAXREG 168     // leaves registers for a co-resident element-wise CTA of another chain (see seg_smem_bytes)
+#endif
 constexpr int kSegMaxStages = 6;
 constexpr int kSegSmemBytes = 232448;   // the whole opt-in budget; the ring is sized from it by the host
 
@@ -1096,12 +1099,12 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) igemm_seg_kernel(const __grid_constant__ IgemmKParams P) {
+__global__ void __maxnreg__(ACLGAN_SEG_MAXREG) igemm_seg_kernel(const __grid_constant__ IgemmKParams P) {
     extern __shared__ uint8_t smem_raw[];
     seg_kernel_body<false>(P, smem_raw);
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(ACLGAN_SEG_MAXREG)
 igemm_seg_pair_kernel(const __grid_constant__ IgemmKParams P) {
     extern __shared__ uint8_t smem_raw[];
     seg_kernel_body<true>(P, smem_raw);
@@ -1231,7 +1234,15 @@ static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repea
     kp.seg_a_bytes = plan->seg_rows * 128;
     kp.seg_btile_bytes = b_rows * 128;
     kp.seg_stage_bytes = kp.seg_a_bytes + plan->seg_taps * kp.seg_btile_bytes;
-    const int budget = kSegSmemBytes - 1024 - kStageOutBytes - 512;
+    // shared memory requested per CTA: not all of it, so that an element-wise CTA of another chain (<= 24 KB) can be
+    // co-resident on the SM and run under the tensor pipe's shadow (env ACLGAN_SEG_SMEM_KB overrides)
+    static int seg_smem = 0;
+    if (seg_smem == 0) {
+        const char* e = getenv("ACLGAN_SEG_SMEM_KB");
+        seg_smem = (e != nullptr ? atoi(e) : 196) * 1024;
+        if (seg_smem > kSegSmemBytes || seg_smem < 96 * 1024) seg_smem = kSegSmemBytes;
+    }
+    const int budget = seg_smem - 1024 - kStageOutBytes - 512;
     int ns = budget / kp.seg_stage_bytes;
     if (ns > kSegMaxStages) ns = kSegMaxStages;
     if (ns < 2) return -100;
@@ -1248,12 +1259,12 @@ static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repea
         const int items = ((m_tiles + 1) / 2) * plan->n_tiles;
         int clusters = num_sms() / 2;
         if (items < clusters) clusters = items;
-        for (int i = 0; i < repeat; ++i) igemm_seg_pair_kernel<<<2 * clusters, kThreads, kSegSmemBytes, stream>>>(kp);
+        for (int i = 0; i < repeat; ++i) igemm_seg_pair_kernel<<<2 * clusters, kThreads, seg_smem, stream>>>(kp);
     } else {
         const int items = m_tiles * plan->n_tiles;
         if (items <= 0) return ACLGAN_OK;
         const int grid = items < num_sms() ? items : num_sms();
-        for (int i = 0; i < repeat; ++i) igemm_seg_kernel<<<grid, kThreads, kSegSmemBytes, stream>>>(kp);
+        for (int i = 0; i < repeat; ++i) igemm_seg_kernel<<<grid, kThreads, seg_smem, stream>>>(kp);
     }
     return (int)cudaGetLastError();
 }

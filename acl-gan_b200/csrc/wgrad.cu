@@ -445,11 +445,18 @@ extern "C" int aclgan_wgrad_launch_repeat(const aclgan_wgrad_plan* pl, int repea
         }
         kp.seg_m_bytes = pl->m_chunks * (pl->seg_on_m ? pl->seg_rows : 64) * 128;
         kp.seg_n_bytes = pl->n_chunks * (pl->seg_on_m ? 64 : pl->seg_rows) * 128;
-        int stages = (kWSegSmemBytes - 1024 - kWStageOut - 256) / (kp.seg_m_bytes + kp.seg_n_bytes);
+        // (not the whole shared memory: room for a co-resident element-wise CTA of another chain, see igemm.cu)
+        static int seg_smem = 0;
+        if (seg_smem == 0) {
+            const char* e = getenv("ACLGAN_SEG_SMEM_KB");
+            seg_smem = (e != nullptr ? atoi(e) : 196) * 1024;
+            if (seg_smem > kWSegSmemBytes || seg_smem < 96 * 1024) seg_smem = kWSegSmemBytes;
+        }
+        int stages = (seg_smem - 1024 - kWStageOut - 256) / (kp.seg_m_bytes + kp.seg_n_bytes);
         if (stages > kWSegMaxStages) stages = kWSegMaxStages;
         if (stages < 2) return ACLGAN_ERR_SHAPE;
         kp.seg_stages = stages;
-        for (int i = 0; i < repeat; ++i) wgrad_seg_kernel<<<grid, kWThreads, kWSegSmemBytes, (cudaStream_t)stream>>>(kp);
+        for (int i = 0; i < repeat; ++i) wgrad_seg_kernel<<<grid, kWThreads, seg_smem, (cudaStream_t)stream>>>(kp);
         return (int)cudaGetLastError();
     }
     for (int i = 0; i < repeat; ++i) wgrad_kernel<<<grid, kWThreads, kWSmemBytes, (cudaStream_t)stream>>>(kp);

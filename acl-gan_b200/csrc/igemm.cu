@@ -1239,7 +1239,7 @@ static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repea
     static int seg_smem = 0;
     if (seg_smem == 0) {
         const char* e = getenv("ACLGAN_SEG_SMEM_KB");
-        seg_smem = (e != nullptr ? atoi(e) : 196) * 1024;
+        seg_smem = (e != nullptr ? atoi(e) : 176) * 1024;
         if (seg_smem > kSegSmemBytes || seg_smem < 96 * 1024) seg_smem = kSegSmemBytes;
     }
     const int budget = seg_smem - 1024 - kStageOutBytes - 512;

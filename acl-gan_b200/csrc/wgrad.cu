@@ -449,7 +449,7 @@ extern "C" int aclgan_wgrad_launch_repeat(const aclgan_wgrad_plan* pl, int repea
         static int seg_smem = 0;
         if (seg_smem == 0) {
             const char* e = getenv("ACLGAN_SEG_SMEM_KB");
-            seg_smem = (e != nullptr ? atoi(e) : 196) * 1024;
+            seg_smem = (e != nullptr ? atoi(e) : 176) * 1024;
             if (seg_smem > kWSegSmemBytes || seg_smem < 96 * 1024) seg_smem = kWSegSmemBytes;
         }
         int stages = (seg_smem - 1024 - kWStageOut - 256) / (kp.seg_m_bytes + kp.seg_n_bytes);

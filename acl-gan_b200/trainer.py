@@ -70,6 +70,7 @@ class aclgan_Trainer(nn.Module):
         # guarded by tests/test_gpu_step.py::test_schedule_variants_agree.)
         self.parallel_scales = bool(int(hp.get("parallel_scales", os.environ.get("ACLGAN_PARALLEL_SCALES", "1"))))
         self._side_streams = None
+        self._early_stream = None
         self.expose_grads = bool(int(hp.get("expose_grads", 1)))   # keep every param.grad readable after an update
         self._ready = False
         self._noise = None          # optional injected style noise (tests / graph replay): list of 3 tensors
@@ -349,8 +350,9 @@ class aclgan_Trainer(nn.Module):
                 o.add_grad(diff * (2.0 * weight / diff.numel()))
         return total
 
-    def _cycle(self, tape, x_a, x_b, zs, need_recon):
-        """encode / decode cycle shared by both updates (trainer.py:103-133 and 258-280)"""
+    def _cycle(self, tape, x_a, x_b, zs, need_recon, early=None):
+        """encode / decode cycle shared by both updates (trainer.py:103-133 and 258-280); `early(x_B_fake)` is called as
+        soon as the first translation exists (dis_update starts its dis_B pass there, next to the second translation)"""
         focus = self.focus_lam > 0
         AB, BA = self.gen_AB, self.gen_BA
         z_1, z_2, z_3 = zs
@@ -397,6 +399,8 @@ class aclgan_Trainer(nn.Module):
             x_A_fake = self._blend(tape, o_a, x_a)
         else:
             x_B_fake, x_A_fake = o_b, o_a
+        if early is not None:
+            early(x_B_fake)
         c_3 = BA.enc_content_fwd(tape, x_B_fake)
         o_a2 = BA.dec_fwd(tape, c_3, z_3)
         x_A2_fake = self._blend(tape, o_a2, x_B_fake) if focus else o_a2
@@ -493,22 +497,44 @@ class aclgan_Trainer(nn.Module):
             self.eng.pool.begin()
         n = x_a.size(0)
         xa, xb = E.ImgT(x_a.detach().float()), E.ImgT(x_b.detach().float())
+        gw, gcw = hp["gan_w"], hp["gan_cw"]
+        early_stream = None
+
+        def dis_b_pass(fake_b):
+            tb = E.Tape()
+            (out_b,) = self._dis_all(tb, [(self.dis_B, self._cat(tb, [fake_b, xb]), None)])
+            lb = self._lsgan_multi(out_b, n, [0.0, 1.0], [gw, gw])
+            self.loss_dis_B = lb[0] + lb[1]
+            tb.backward(self._side_streams)
+
+        def early(x_B_fake):
+            # dis_B only needs x_B_fake: its whole forward + backward runs on a side stream while the generators still
+            # compute the second translation (x_A2_fake) on the caller's stream
+            nonlocal early_stream
+            if self._early_stream is None:
+                self._early_stream = torch.cuda.Stream()
+            early_stream = self._early_stream
+            early_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(early_stream):
+                dis_b_pass(E.ImgT(x_B_fake.t))
+
+        use_early = self.parallel_dis and torch.cuda.is_available()
         # the generators only produce the fakes here: no backward pass is recorded for them (trainer.py:91)
-        r = self._cycle(E.Tape(enabled=False), xa, xb, zs, need_recon=False)
+        r = self._cycle(E.Tape(enabled=False), xa, xb, zs, need_recon=False, early=early if use_early else None)
         fake_a, fake_a2, fake_b = (E.ImgT(r[k].t) for k in ("x_A_fake", "x_A2_fake", "x_B_fake"))
+        if early_stream is not None:
+            torch.cuda.current_stream().wait_stream(early_stream)
+        else:
+            dis_b_pass(fake_b)
 
         tape = E.Tape()
-        gw, gcw = hp["gan_w"], hp["gan_cw"]
         # each discriminator runs once over the batch-concatenation of its inputs; dis_A(x_a) is counted twice with
         # weight 1/2 in the reference (trainer.py:283-284) == once with weight 1
-        cat_a, cat_b = self._cat(tape, [xa, fake_a, fake_a2]), self._cat(tape, [fake_b, xb])
+        cat_a = self._cat(tape, [xa, fake_a, fake_a2])
         cat_2a, cat_2b = self._cat(tape, [xa, xa]), self._cat(tape, [fake_a, fake_a2])
-        out_a, out_b, out_2 = self._dis_all(tape, [(self.dis_A, cat_a, None), (self.dis_B, cat_b, None),
-                                                   (self.dis_2, cat_2a, cat_2b)])
+        out_a, out_2 = self._dis_all(tape, [(self.dis_A, cat_a, None), (self.dis_2, cat_2a, cat_2b)])
         la = self._lsgan_multi(out_a, n, [1.0, 0.0, 0.0], [gw, 0.5 * gw, 0.5 * gw])
         self.loss_dis_A = (la[1] + la[2] + 2.0 * la[0]) * 0.5
-        lb = self._lsgan_multi(out_b, n, [0.0, 1.0], [gw, gw])
-        self.loss_dis_B = lb[0] + lb[1]
         l2 = self._lsgan_multi(out_2, n, [0.0, 1.0], [gcw, gcw])
         self.loss_dis_2 = l2[0] + l2[1]
         self.loss_dis_total = gw * self.loss_dis_A + gw * self.loss_dis_B + gcw * self.loss_dis_2

@@ -224,6 +224,7 @@ def _declare(L):
     L.aclgan_pack_weight.argtypes = [C.POINTER(PackWeightArgs), C.c_void_p]
     L.aclgan_adam_step.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_void_p]
     L.aclgan_adam_advance.argtypes = [C.c_uint64, C.c_void_p]
+    L.aclgan_stream_wait_external_event.argtypes = [C.c_void_p, C.c_void_p]
 
 
 launch_count = 0

@@ -68,3 +68,11 @@ extern "C" int aclgan_version(void) { return ACLGAN_ABI_VERSION; }
 extern "C" const char* aclgan_build_info(void) {
     return "aclgan_b200 sm_100a (tcgen05 + TMA implicit GEMM), built " __DATE__ " " __TIME__;
 }
+
+// Makes `stream` wait for an event recorded OUTSIDE a stream capture (cudaEventWaitExternal): inside a capture it becomes
+// an external event-wait node of the graph, outside it is a plain cudaStreamWaitEvent.  Used by trainer.gen_update: its
+// captured graph starts the generator passes while the previous dis_update (graph + Adam on another stream) is still
+// running and only waits for it right before the discriminator passes.
+extern "C" int aclgan_stream_wait_external_event(void* stream, void* event) {
+    return (int)cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, cudaEventWaitExternal);
+}

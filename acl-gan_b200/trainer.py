@@ -71,9 +71,26 @@ class aclgan_Trainer(nn.Module):
         self.parallel_scales = bool(int(hp.get("parallel_scales", os.environ.get("ACLGAN_PARALLEL_SCALES", "1"))))
         self._side_streams = None
         self._early_stream = None
+        # dis_update (graph replay + all-reduce + Adam) runs on its own stream; the next gen_update starts its generator
+        # passes right away and waits for it (an external event-wait node inside its graph) only before the discriminator
+        # passes.  Results of dis_update (loss_dis_*, discriminator gradients / weights) are ordered after
+        # torch.cuda.synchronize(), the next gen_update, or any read of a loss_dis_* attribute.
+        self.overlap_updates = bool(int(hp.get("overlap_updates", os.environ.get("ACLGAN_OVERLAP_UPDATES", "0"))))
+        self._dis_stream = None
+        self._dis_event = None
         self.expose_grads = bool(int(hp.get("expose_grads", 1)))   # keep every param.grad readable after an update
         self._ready = False
         self._noise = None          # optional injected style noise (tests / graph replay): list of 3 tensors
+
+    # ------------------------------------------------------------------------------------------ dis_update ordering
+    def _join_dis(self):
+        """orders the caller's stream after the last dis_update (no-op when nothing is pending)"""
+        if self._dis_event is not None and torch.cuda.is_available():
+            torch.cuda.current_stream().wait_event(self._dis_event)
+
+    def _wait_dis_in_graph(self):
+        if self._dis_event is not None:
+            N.check(N.lib().aclgan_stream_wait_external_event(E._sp(), self._dis_event.cuda_event), "plan:wait_external_event")
 
     # ------------------------------------------------------------------------------------------ engine
     def _setup(self):
@@ -95,6 +112,10 @@ class aclgan_Trainer(nn.Module):
             net.attach_grads()
         self._adam_gen = self._adam_group(self.gen_opt, (self.gen_AB, self.gen_BA), self.gen_arena)
         self._adam_dis = self._adam_group(self.dis_opt, (self.dis_A, self.dis_B, self.dis_2), self.dis_arena)
+        if self.overlap_updates and self.use_graphs and torch.cuda.is_available():
+            self._dis_stream = torch.cuda.Stream()
+            self._dis_event = torch.cuda.Event()
+            self._dis_event.record()            # creates the event handle the gen graph's wait node refers to
         self._ready = True
 
     def _nets(self):
@@ -180,6 +201,7 @@ class aclgan_Trainer(nn.Module):
         """mirror the device-side step counters into the torch optimizer state (before state_dict())"""
         if not self._ready:
             return
+        self._join_dis()
         for grp in (self._adam_gen, self._adam_dis):
             n = float(grp["hyper"][6].item())
             for p in grp["params"]:
@@ -435,6 +457,7 @@ class aclgan_Trainer(nn.Module):
         r = self._cycle(tape, xa, xb, zs, need_recon=True)
 
         gw, gcw = hp["gan_w"], hp["gan_cw"]
+        self._wait_dis_in_graph()           # the discriminators' weights come from the (possibly still running) dis_update
         cat_a = self._cat(tape, [r["x_A_fake"], r["x_A2_fake"]])
         cat_2a, cat_2b = self._cat(tape, [xa, xa]), self._cat(tape, [r["x_A_fake"], r["x_A2_fake"]])
         out_a, out_b, out_2 = self._dis_all(tape, [(self.dis_A, cat_a, None), (self.dis_B, r["x_B_fake"], None),
@@ -483,6 +506,18 @@ class aclgan_Trainer(nn.Module):
 
     def dis_update(self, x_a, x_b, hyperparameters):
         self._setup()
+        if self._dis_stream is not None and self.use_graphs:
+            st = self._dis_stream
+            st.wait_stream(torch.cuda.current_stream())         # inputs and the generators' weights (last gen_update)
+            with torch.cuda.stream(st):
+                self._replay("dis", x_a, x_b, hyperparameters)
+                self._allreduce(self.dis_arena)
+                self._adam_step(self._adam_dis)
+                self._dis_event.record(st)
+            for t in (x_a, x_b):
+                if t.is_cuda:
+                    t.record_stream(st)
+            return
         if self.use_graphs:
             self._replay("dis", x_a, x_b, hyperparameters)
         else:
@@ -499,12 +534,13 @@ class aclgan_Trainer(nn.Module):
         xa, xb = E.ImgT(x_a.detach().float()), E.ImgT(x_b.detach().float())
         gw, gcw = hp["gan_w"], hp["gan_cw"]
         early_stream = None
+        losses = {}
 
         def dis_b_pass(fake_b):
             tb = E.Tape()
             (out_b,) = self._dis_all(tb, [(self.dis_B, self._cat(tb, [fake_b, xb]), None)])
             lb = self._lsgan_multi(out_b, n, [0.0, 1.0], [gw, gw])
-            self.loss_dis_B = lb[0] + lb[1]
+            losses["B"] = lb[0] + lb[1]
             tb.backward(self._side_streams)
 
         def early(x_B_fake):
@@ -534,10 +570,11 @@ class aclgan_Trainer(nn.Module):
         cat_2a, cat_2b = self._cat(tape, [xa, xa]), self._cat(tape, [fake_a, fake_a2])
         out_a, out_2 = self._dis_all(tape, [(self.dis_A, cat_a, None), (self.dis_2, cat_2a, cat_2b)])
         la = self._lsgan_multi(out_a, n, [1.0, 0.0, 0.0], [gw, 0.5 * gw, 0.5 * gw])
-        self.loss_dis_A = (la[1] + la[2] + 2.0 * la[0]) * 0.5
+        losses["A"] = (la[1] + la[2] + 2.0 * la[0]) * 0.5
         l2 = self._lsgan_multi(out_2, n, [0.0, 1.0], [gcw, gcw])
-        self.loss_dis_2 = l2[0] + l2[1]
-        self.loss_dis_total = gw * self.loss_dis_A + gw * self.loss_dis_B + gcw * self.loss_dis_2
+        losses["2"] = l2[0] + l2[1]
+        self.loss_dis_A, self.loss_dis_B, self.loss_dis_2 = losses["A"], losses["B"], losses["2"]
+        self.loss_dis_total = gw * losses["A"] + gw * losses["B"] + gcw * losses["2"]
         tape.backward(self._side_streams)
 
     @property
@@ -609,9 +646,11 @@ class aclgan_Trainer(nn.Module):
         with torch.cuda.graph(graph):
             run()
         self._launches[kind] = N.launch_count - n0 + 2      # + the Adam kernels launched outside the graph
-        names = [k for k in vars(self) if k.startswith("loss_")]
-        prefix = "loss_gen" if kind == "gen" else "loss_dis"
-        ent["losses"] = {k: getattr(self, k) for k in names if k.startswith(prefix) or (kind == "gen" and k.startswith("loss_idt"))}
+        if kind == "gen":
+            names = [k for k in vars(self) if k.startswith("loss_gen") or k.startswith("loss_idt")]
+        else:
+            names = ["loss_dis_A", "loss_dis_B", "loss_dis_2", "loss_dis_total"]
+        ent["losses"] = {k: self.__dict__.get("_dv_" + k[5:], self.__dict__.get(k)) for k in names}
         ent["cycle"] = self._last_cycle
         ent["graph"] = graph
         return ent
@@ -624,6 +663,7 @@ class aclgan_Trainer(nn.Module):
     def sample(self, x_a, x_b):
         """trainer.py:179-245: per-image translations with the fixed display noise"""
         self._setup()
+        self._join_dis()
         self.eval()
         focus = self.focus_lam > 0
         cols = {k: [] for k in ("x_A", "x_B", "x_A_fake", "x_B_fake", "x_A2_fake", "x_A_recon", "x_B_recon",
@@ -673,11 +713,13 @@ class aclgan_Trainer(nn.Module):
             self.dis_scheduler.step()
         if self.gen_scheduler is not None:
             self.gen_scheduler.step()
+        self._join_dis()
         if self._ready:         # the fused Adam kernel reads lr from device memory (outside any captured graph)
             self._adam_gen["hyper"][0:1].fill_(self.gen_opt.param_groups[0]["lr"])
             self._adam_dis["hyper"][0:1].fill_(self.dis_opt.param_groups[0]["lr"])
 
     def resume(self, checkpoint_dir, hyperparameters):
+        self._join_dis()
         last = get_model_list(checkpoint_dir, "gen")
         sd = torch.load(last)
         self.gen_AB.load_state_dict(sd["AB"])
@@ -704,3 +746,23 @@ class aclgan_Trainer(nn.Module):
         torch.save({"AB": self.gen_AB.state_dict(), "BA": self.gen_BA.state_dict()}, gen_name)
         torch.save({"A": self.dis_A.state_dict(), "B": self.dis_B.state_dict(), "2": self.dis_2.state_dict()}, dis_name)
         torch.save({"gen": self.gen_opt.state_dict(), "dis": self.dis_opt.state_dict()}, opt_name)
+
+
+def _dis_loss_property(name):
+    """loss_dis_* are produced on dis_update's own stream: reading one orders the caller's stream after that update"""
+    key = "_dv_" + name[5:]          # (storage name without "loss": utils.write_loss scans attribute names for it)
+
+    def get(self):
+        if key not in self.__dict__:
+            raise AttributeError(name)
+        self._join_dis()
+        return self.__dict__[key]
+
+    def set_(self, value):
+        self.__dict__[key] = value
+
+    return property(get, set_)
+
+
+for _n in ("loss_dis_A", "loss_dis_B", "loss_dis_2", "loss_dis_total"):
+    setattr(aclgan_Trainer, _n, _dis_loss_property(_n))

@@ -328,6 +328,10 @@ typedef struct aclgan_adam_tensor {
 int aclgan_adam_step(uint64_t table, uint64_t chunks, int32_t n_chunks, uint64_t hyper, void* stream);
 int aclgan_adam_advance(uint64_t hyper, void* stream);
 
+/* stream-ordering helper for the host code: wait on an event recorded outside a stream capture (an external event-wait
+ * node when `stream` is capturing); returns the cudaError_t */
+int aclgan_stream_wait_external_event(void* stream, void* event);
+
 #ifdef __cplusplus
 }
 #endif

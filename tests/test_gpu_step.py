@@ -193,6 +193,7 @@ def test_gradients_vs_live_oracle(golden_dir, precision, point):
             grp["weight_decay"] = 0.0
     tr._noise = zs[:3]
     tr.dis_update(x_a.cuda(), x_b.cuda(), cfg)
+    torch.cuda.synchronize()            # dis_update runs on its own stream (ordered by synchronize / the next gen_update)
     mine_d = {(n, k): p.grad.detach().double().cpu().clone() for n in ("dis_A", "dis_B", "dis_2")
               for k, p in getattr(tr, n).named_parameters()}
     tr._noise = zs[3:]
@@ -377,12 +378,14 @@ def test_schedule_variants_agree(golden_dir, precision):
         for rep in range(2):            # second round = graph REPLAY (the first call captures)
             tr._noise = zs[:3]
             tr.dis_update(x_a.cuda(), x_b.cuda(), cfg)
+            torch.cuda.synchronize()
             for n in ("dis_A", "dis_B", "dis_2"):
                 for k, p in getattr(tr, n).named_parameters():
                     out[(rep, n, k)] = p.grad.detach().double().cpu().clone()
             out[(rep, "loss_dis_total")] = float(tr.loss_dis_total)
             tr._noise = zs[3:]
             tr.gen_update(x_a.cuda(), x_b.cuda(), cfg)
+            torch.cuda.synchronize()
             for n in ("gen_AB", "gen_BA"):
                 for k, p in getattr(tr, n).named_parameters():
                     out[(rep, n, k)] = p.grad.detach().double().cpu().clone()

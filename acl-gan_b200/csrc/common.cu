@@ -74,5 +74,10 @@ extern "C" const char* aclgan_build_info(void) {
 // captured graph starts the generator passes while the previous dis_update (graph + Adam on another stream) is still
 // running and only waits for it right before the discriminator passes.
 extern "C" int aclgan_stream_wait_external_event(void* stream, void* event) {
-    return (int)cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, cudaEventWaitExternal);
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaError_t e = cudaStreamIsCapturing((cudaStream_t)stream, &st);
+    if (e != cudaSuccess) return (int)e;
+    // (the external flag is only valid while capturing)
+    const unsigned flags = st == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : cudaEventWaitDefault;
+    return (int)cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, flags);
 }

@@ -75,7 +75,7 @@ class aclgan_Trainer(nn.Module):
         # passes right away and waits for it (an external event-wait node inside its graph) only before the discriminator
         # passes.  Results of dis_update (loss_dis_*, discriminator gradients / weights) are ordered after
         # torch.cuda.synchronize(), the next gen_update, or any read of a loss_dis_* attribute.
-        self.overlap_updates = bool(int(hp.get("overlap_updates", os.environ.get("ACLGAN_OVERLAP_UPDATES", "0"))))
+        self.overlap_updates = bool(int(hp.get("overlap_updates", os.environ.get("ACLGAN_OVERLAP_UPDATES", "1"))))
         self._dis_stream = None
         self._dis_event = None
         self.expose_grads = bool(int(hp.get("expose_grads", 1)))   # keep every param.grad readable after an update

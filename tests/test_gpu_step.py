@@ -363,7 +363,8 @@ def test_schedule_variants_agree(golden_dir, precision):
     g32 = _load(golden_dir, "tiny", "fp32")
     x_a, x_b, zs = _inputs(g32)
     results = []
-    for variant in (dict(merge_passes=0, parallel_dis=0, cuda_graphs=0), dict(merge_passes=1, parallel_dis=1, cuda_graphs=1),
+    for variant in (dict(merge_passes=0, parallel_dis=0, cuda_graphs=0, overlap_updates=0),
+                    dict(merge_passes=1, parallel_dis=1, cuda_graphs=1, overlap_updates=0),
                     dict(merge_passes=1, parallel_dis=1, parallel_scales=1, cuda_graphs=1),
                     dict(merge_passes=1, parallel_dis=1, parallel_scales=1, cuda_graphs=0)):
         g = dict(g32, cfg=dict(copy.deepcopy(g32["cfg"]), **variant))

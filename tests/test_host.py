@@ -107,3 +107,55 @@ def test_no_cpu_fallback():
     gen = networks.AdaINGen(3, _cfg()["gen"])
     with pytest.raises(N.NativeError):
         gen.encode(torch.zeros(1, 3, 64, 64))
+
+
+def test_tape_runs_in_reverse_and_keeps_tags():
+    """the hand-scheduled reverse pass: closures run last-in-first-out; tags only matter with side streams (GPU)"""
+    import engine as E
+    tape = E.Tape()
+    order = []
+    tape.push(lambda: order.append("a"))
+    tape.tag = 3
+    tape.push(lambda: order.append("b"))
+    tape.push(lambda: order.append("c"))
+    tape.tag = None
+    tape.push(lambda: order.append("d"))
+    assert [t for _, t in tape.ops] == [None, 3, 3, None]
+    tape.backward()                 # no streams: plain sequential reverse order
+    assert order == ["d", "c", "b", "a"] and not tape.ops
+    off = E.Tape(enabled=False)
+    off.push(lambda: order.append("x"))
+    assert not off.ops
+
+
+def test_sums_pool_counts_then_serves_slices():
+    """statistics workspace: counting mode measures the update, the sized pool hands out disjoint zeroed slices"""
+    import engine as E
+    count = E.SumsPool("cpu")
+    count.begin()
+    a = count.take((2, 64, 2))
+    b = count.take((1, 3, 2))
+    assert a.shape == (2, 64, 2) and float(a.abs().sum()) == 0 and count.off == 256 + 6
+    pool = E.SumsPool("cpu", count.off)
+    pool.begin()
+    a, b = pool.take((2, 64, 2)), pool.take((1, 3, 2))
+    a.fill_(1.0)
+    assert float(b.abs().sum()) == 0 and a.data_ptr() != b.data_ptr()
+    c = pool.take((4, 64, 2))       # beyond the measured size: falls back to a fresh tensor, never overlaps
+    assert c.shape == (4, 64, 2) and float(c.abs().sum()) == 0
+    pool.begin()
+    assert float(pool.take((2, 64, 2)).abs().sum()) == 0      # one memset per update
+
+
+def test_dis_loss_attributes_are_plain_attributes_until_set():
+    """loss_dis_* behave like the reference's attributes: absent before the first update (utils.write_loss reflects over
+    the trainer), readable after; stored under names without 'loss' so the reflection does not log them twice"""
+    import trainer as T
+    cfg = _cfg()
+    cfg["gen"].update(dim=8, mlp_dim=8, n_res=1)
+    cfg["dis"].update(dim=8)
+    tr = T.aclgan_Trainer(copy.deepcopy(cfg))
+    assert not hasattr(tr, "loss_dis_total")
+    tr.loss_dis_total = torch.tensor(1.5)
+    assert float(tr.loss_dis_total) == 1.5
+    assert not [k for k in vars(tr) if "loss" in k and k.startswith("_")]

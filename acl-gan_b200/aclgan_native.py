@@ -45,7 +45,7 @@ class IgemmPlan(C.Structure):
                 ("n_groups", C.c_int32), ("group_taps", C.c_int32), ("group_off", C.c_int64 * 4),
                 ("seg_mode", C.c_int32), ("seg_rows", C.c_int32), ("num_segs", C.c_int32), ("seg_taps", C.c_int32),
                 ("seg_dx", C.c_int32 * 16), ("seg_dy", C.c_int32 * 16), ("tap_row", C.c_int32 * MAX_TAPS),
-                ("a_seg", TmapSpec * 2),
+                ("a_seg", TmapSpec * 2), ("fold", C.c_int32), ("tile_step", C.c_int32),
                 ("out", OutSpec)]
 
 
@@ -206,6 +206,7 @@ def _declare(L):
     L.aclgan_packed_weight_index.restype = C.c_int64
     L.aclgan_igemm_launch.argtypes = [C.POINTER(IgemmPlan), C.c_void_p]
     L.aclgan_igemm_stats_supported.argtypes = [C.POINTER(IgemmPlan)]
+    L.aclgan_fold_launch.argtypes = [C.POINTER(IgemmPlan), C.c_int, C.c_void_p]
     L.aclgan_plan_conv_wgrad.argtypes = [C.POINTER(ConvDesc), C.POINTER(Act), C.POINTER(Act), C.c_uint64,
                                          C.POINTER(WgradPlan)]
     L.aclgan_wgrad_layout.argtypes = [C.POINTER(ConvDesc)]

@@ -1288,6 +1288,7 @@ extern "C" int aclgan_igemm_launch(const aclgan_igemm_plan* plan, void* stream) 
 // without per-launch host work (bench.py roofline leg, tools/triage_igemm.py)
 extern "C" int aclgan_igemm_launch_repeat(const aclgan_igemm_plan* plan, int repeat, void* stream) {
     using namespace aclgan;
+    if (plan->fold) return aclgan_fold_launch(plan, repeat, stream);      // (experimental fold-mode plans, csrc/fold.cu)
     static bool attr_set = false;
     IgemmKParams kp;
     int rc = fill_kparams(plan, &kp);

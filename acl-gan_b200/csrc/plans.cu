@@ -79,6 +79,12 @@ static bool seg_enabled() {
     return e == nullptr || atoi(e) != 0;
 }
 
+// fold mode of the few-output-channel final conv's forward (experimental, off by default)
+static bool fold_enabled(const aclgan_conv_desc* cd) {
+    const char* e = getenv("ACLGAN_FOLD");
+    return e != nullptr && atoi(e) != 0 && cd->window == ACLGAN_WINDOW_OUT && cd->stride == 1 && cd->k <= 8 && cd->cout <= 8;
+}
+
 static bool wgrad_seg_enabled() {
     const char* e = getenv("ACLGAN_WGRAD_SEG");
     return e == nullptr || atoi(e) != 0;
@@ -102,6 +108,11 @@ extern "C" int aclgan_packed_weight_shape(const aclgan_conv_desc* cd, int transp
     int bn, nt;
     choose_block_n(transposed ? cd->cin : cd->cout, &bn, &nt);
     *rows = (int64_t)bn * nt;
+    if (!transposed && fold_enabled(cd)) {          // rows n = kw * 8 + co, k = kh * Cs + ci
+        *rows = 64;
+        *k_total = (int64_t)cd->k * k_channels(cd, 0);
+        return ACLGAN_OK;
+    }
     if (uses_window(cd, transposed)) *k_total = (int64_t)cd->k * 64;
     else *k_total = (int64_t)cd->k * cd->k * k_channels(cd, transposed);
     return ACLGAN_OK;
@@ -111,6 +122,7 @@ extern "C" int64_t aclgan_packed_weight_index(const aclgan_conv_desc* cd, int tr
                                               int kw) {
     int64_t rows, kt;
     aclgan_packed_weight_shape(cd, transposed, &rows, &kt);
+    if (!transposed && fold_enabled(cd)) return (int64_t)(kw * 8 + co) * kt + (int64_t)kh * k_channels(cd, 0) + ci;
     if (!uses_window(cd, transposed)) {
         if (!transposed) return (int64_t)co * kt + (int64_t)(kh * cd->k + kw) * k_channels(cd, 0) + ci;
         return (int64_t)ci * kt + (int64_t)(kh * cd->k + kw) * k_channels(cd, 1) + co;
@@ -144,7 +156,28 @@ extern "C" int aclgan_plan_conv_fwd(const aclgan_conv_desc* cd, const aclgan_act
     aclgan_packed_weight_shape(cd, 0, &rows, &kt);
     for (int pl = 0; pl < x->planes; ++pl) weight_map2(&p->b[pl], w[pl], kt, rows, p->block_n);
 
-    if (cd->window != ACLGAN_WINDOW_IN && s == 1 && k > 1 && k <= 8 && seg_enabled()) {
+    if (fold_enabled(cd)) {
+        // filter columns folded into N: one tap per filter row over the flattened padded grid, overlapping 128-row tiles
+        if (cs % 64 != 0 || cs != k_channels(cd, 0)) return ACLGAN_ERR_SHAPE;
+        const int64_t total = (int64_t)x->n * hp * wp;
+        p->block_n = 64; p->n_tiles = 1;
+        p->fold = k;
+        p->tile_step = 120;
+        p->box_x = 128; p->box_y = 1; p->box_z = 1;
+        p->tiles_x = (int)((total + p->tile_step - 1) / p->tile_step); p->tiles_y = 1; p->tiles_z = 1;
+        p->flat = 1; p->flat_w = wp; p->flat_img = hp * wp;
+        p->cchunks = cs / 64;
+        p->num_taps = k;
+        p->n_avariants = 1;
+        for (int pl = 0; pl < x->planes; ++pl) {
+            plane_map4(&p->a[pl][0], x->data[pl], cs, total, 1, 1, px, total * px, total * px, 128, 1, 1);
+            weight_map2(&p->b[pl], w[pl], kt, rows, 64);
+        }
+        for (int kh = 0; kh < k; ++kh) {
+            p->tap_dx[kh] = kh * wp;
+            p->tap_bk[kh] = kh * cs;
+        }
+    } else if (cd->window != ACLGAN_WINDOW_IN && s == 1 && k > 1 && k <= 8 && seg_enabled()) {
         // stride 1: segment mode.  Tiles are 128 consecutive pixels of one output row when the rows are long enough,
         // otherwise 128 consecutive positions of the flattened padded input grid (outputs at the k - 1 right-most
         // columns / bottom rows of that grid are computed and dropped by the epilogue's extent check).

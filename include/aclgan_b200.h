@@ -94,6 +94,11 @@ typedef struct aclgan_igemm_plan {
     int32_t seg_dx[16], seg_dy[16]; /* box offset of segment s relative to the tile origin (like tap_dx / tap_dy) */
     int32_t tap_row[ACLGAN_MAX_TAPS]; /* first segment row of tap t */
     aclgan_tmap_spec a_seg[2];        /* [plane] the variant-0 map with a seg_rows-pixel box */
+    /* fold mode (forward of the few-output-channel final conv, EXPERIMENTAL, env ACLGAN_FOLD=1): the k taps of a filter row
+     * are folded into the N dimension (weight row n = kw*8 + co, one tap per filter ROW), tiles are 128 flattened positions
+     * stepping by tile_step = 128 - 8, and the epilogue sums the diagonal out[q][co] = sum_kw P[q + kw][kw*8 + co]. */
+    int32_t fold;        /* 0, or the filter width k */
+    int32_t tile_step;   /* flattened positions between consecutive tiles (fold mode) */
     aclgan_out_spec out;
 } aclgan_igemm_plan;
 
@@ -170,6 +175,7 @@ int aclgan_wgrad_layout(const aclgan_conv_desc* cd);
 
 /* launches (networks.py:363,366 Conv2d forward; autograd of it for dgrad / wgrad) */
 int aclgan_igemm_launch(const aclgan_igemm_plan* plan, void* stream);
+int aclgan_fold_launch(const aclgan_igemm_plan* plan, int repeat, void* stream);   /* fold-mode plans (igemm_launch forwards them) */
 /* 1 when the epilogue of this plan can accumulate out.stats (otherwise run aclgan_norm_stats on the output) */
 int aclgan_igemm_stats_supported(const aclgan_igemm_plan* plan);
 int aclgan_wgrad_launch(const aclgan_wgrad_plan* plan, void* stream);

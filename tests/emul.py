@@ -92,6 +92,8 @@ def run_igemm(mem, plan, use_seg=None):
         bias = bt.reshape(-1)[boff:].double()
     segs = [(0, 0)] if plan.nseg == 1 else [(0, 0), (0, 1), (1, 0)]
     bn = plan.block_n
+    if plan.fold:
+        return _run_igemm_fold(mem, plan, outs, bias, segs)
     n_groups = plan.n_groups if plan.n_groups > 1 else 1
     gtaps = plan.group_taps if plan.n_groups > 1 else plan.num_taps
     for grp in range(n_groups):
@@ -156,6 +158,37 @@ def run_igemm(mem, plan, use_seg=None):
                                         flat[idx] += val.to(flat.dtype)
                                     else:
                                         flat[idx] = val.to(flat.dtype)
+
+
+def _run_igemm_fold(mem, plan, outs, bias, segs):
+    """fold mode: P[r][kw*8 + co] per 128-row tile (tiles step by tile_step), out[q][co] = sum_kw P[q + kw][kw*8 + co]"""
+    o = plan.out
+    k = plan.fold
+    assert plan.flat and plan.block_n == 64 and plan.tile_step + k - 1 <= 128 and o.kind in (N.OUT_F32, N.OUT_BF16)
+    for tx in range(plan.tiles_x):
+        x0 = tx * plan.tile_step
+        acc = torch.zeros(128, 64, dtype=torch.float64)
+        for pa, pb in segs:
+            for t in range(plan.num_taps):
+                for cc in range(plan.cchunks):
+                    A = tma_box(mem, plan.a[pa][0], (cc * 64, x0 + plan.tap_dx[t], 0, 0)).reshape(128, 64)
+                    B = tma_box(mem, plan.b[pb], (plan.tap_bk[t] + cc * 64, 0)).reshape(64, 64)
+                    acc += A @ B.t()
+        for r in range(plan.tile_step):
+            q = x0 + r
+            z, rem = divmod(q, plan.flat_img)
+            y, x = divmod(rem, plan.flat_w)
+            if not (x < o.W and y < o.H and z < o.N):
+                continue
+            v = torch.stack([sum(acc[r + kw, kw * 8 + co] for kw in range(k)) for co in range(o.C)])
+            if bias is not None:
+                nb = min(o.C, o.bias_n)
+                v[:nb] = v[:nb] + bias[:nb]
+            v = _act(v, o.act, o.slope)
+            t_, toff = outs[0]
+            flat = t_.reshape(-1)
+            idx = toff + o.off + z * o.sn + y * o.sy + x * o.sx + torch.arange(o.C) * o.sc
+            flat[idx] = v.to(flat.dtype)
 
 
 def pack_weight(desc, w_oihw, transposed, dtype=torch.bfloat16):

@@ -210,3 +210,40 @@ def test_conv_wgrad_plan(cin, cout, k, s, pad, window, n, h, w, planes):
     ref = torch.nn.grad.conv2d_weight(xeff, (cout, cin, k, k), yeff, stride=s)
     tol = 1e-6 if planes == 1 else 3e-4
     assert torch.allclose(got, ref, rtol=tol, atol=tol * float(ref.abs().max())), float((got - ref).abs().max())
+
+
+@pytest.mark.parametrize("cout,n,h,w,planes", [(4, 1, 8, 16, 1), (3, 2, 12, 8, 2)])
+def test_conv_fwd_fold_plan(monkeypatch, cout, n, h, w, planes):
+    """experimental fold mode of the final 7x7 conv (ACLGAN_FOLD=1): filter columns folded into N, diagonal sum in the
+    epilogue - packing, plan geometry and epilogue rule validated by CPU emulation"""
+    monkeypatch.setenv("ACLGAN_FOLD", "1")
+    L = N.lib()
+    torch.manual_seed(3)
+    mem = emul.Memory()
+    cin, k, pad = 64, 7, 3
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, k, k) * 0.05
+    bias = torch.randn(cout)
+    desc = N.ConvDesc(cin, cout, k, 1, pad, N.WINDOW_OUT)
+    act, abuf, xeff = make_act(mem, x, pad, 64, planes)
+    wts = [emul.pack_weight(desc, wt, False)]
+    weff = wt.bfloat16().double()
+    if planes == 2:
+        wts.append(emul.pack_weight(desc, wt - wt.bfloat16().float(), False))
+        weff = weff + (wt - wt.bfloat16().float()).bfloat16().double()
+    assert tuple(wts[0].shape) == (64, k * 64)
+    wptr = (C.c_uint64 * 2)(*[mem.add(t) for t in wts] + [0] * (2 - len(wts)))
+    img = torch.zeros(n, cout, h, w, dtype=torch.float32)
+    o = N.OutSpec()
+    o.ptr[0] = mem.add(img)
+    o.kind, o.act, o.slope, o.mirror, o.off = N.OUT_F32, N.ACT_TANH, 0.2, 0, 0
+    o.sn, o.sy, o.sx, o.sc = cout * h * w, w, 1, h * w
+    o.N, o.H, o.W, o.C = n, h, w, cout
+    o.bias, o.bias_n = mem.add(bias), cout
+    plan = N.IgemmPlan()
+    N.check(L.aclgan_plan_conv_fwd(C.byref(desc), C.byref(act), wptr, C.byref(o), C.byref(plan)), "plan fwd")
+    assert plan.fold == k and plan.tile_step == 120 and plan.num_taps == k and not plan.seg_mode
+    emul.run_igemm(mem, plan)
+    ref = torch.tanh(F.conv2d(xeff, weff, bias.double()))
+    tol = 1e-6 if planes == 1 else 2e-4
+    assert torch.allclose(img.double(), ref, rtol=tol, atol=tol), float((img.double() - ref).abs().max())

@@ -23,6 +23,9 @@ SHAPES = [  # cin, cout, k, pad, n, h[, stride]
 ]
 if os.environ.get("ONLY_S2"):
     SHAPES = [s for s in SHAPES if len(s) > 6]
+if os.environ.get("ONLY7"):
+    SHAPES = [s for s in SHAPES if s[2] == 7]
+    CONFIGS = CONFIGS[2:3]
 CONFIGS = [
     ("box-per-tap plans, plain kernels", dict(ACLGAN_SEG="0")),
     ("segment plans on plain kernels", dict(ACLGAN_SEG="1", ACLGAN_SEGK="0")),

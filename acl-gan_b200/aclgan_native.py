@@ -116,7 +116,8 @@ class NormBwdFinalizeArgs(C.Structure):
     _fields_ = [("mode", C.c_int32), ("n", C.c_int32), ("c", C.c_int32), ("hw", C.c_int32),
                 ("c_valid", C.c_int32), ("sums", C.c_uint64), ("inv", C.c_uint64), ("sigma", C.c_uint64),
                 ("w", C.c_uint64), ("ca", C.c_uint64), ("cb", C.c_uint64), ("cc", C.c_uint64),
-                ("dw", C.c_uint64), ("db", C.c_uint64), ("wb_stride", C.c_int64)]
+                ("dw", C.c_uint64), ("db", C.c_uint64), ("wb_stride", C.c_int64),
+                ("fsums", C.c_uint64), ("mean", C.c_uint64), ("dbias", C.c_uint64)]
 
 
 class ImgGradPackArgs(C.Structure):
@@ -140,6 +141,55 @@ class AdamTensor(C.Structure):
     _fields_ = [("p", C.c_uint64), ("m", C.c_uint64), ("v", C.c_uint64), ("g", C.c_uint64),
                 ("d", C.c_int32 * 4), ("gs", C.c_int64 * 4), ("goff", C.c_int64),
                 ("pk", (C.c_uint64 * 2) * 2), ("aff", (C.c_int64 * 5) * 2), ("planes", C.c_int32), ("pad_", C.c_int32)]
+
+
+class AvgPoolArgs(C.Structure):
+    _fields_ = [("src", C.c_uint64), ("dst", C.c_uint64), ("planes", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("accumulate", C.c_int32)]
+
+
+class StyleHeadArgs(C.Structure):
+    _fields_ = [("x", Act), ("c_valid", C.c_int32), ("style_dim", C.c_int32), ("weight", C.c_uint64), ("bias", C.c_uint64),
+                ("pooled", C.c_uint64), ("style", C.c_uint64), ("dstyle", C.c_uint64), ("dweight", C.c_uint64),
+                ("dbias", C.c_uint64), ("gr", C.c_uint64), ("g_kind", C.c_int32), ("pad_", C.c_int32)]
+
+
+class MlpArgs(C.Structure):
+    _fields_ = [("n", C.c_int32), ("n_layers", C.c_int32), ("dims", C.c_int32 * 5), ("pad_", C.c_int32),
+                ("w", C.c_uint64 * 4), ("b", C.c_uint64 * 4), ("h", C.c_uint64 * 5), ("h0_stride", C.c_int64),
+                ("dh", C.c_uint64 * 5), ("dw", C.c_uint64 * 4), ("db", C.c_uint64 * 4)]
+
+
+class DisHeadArgs(C.Structure):
+    _fields_ = [("x", Act), ("c_valid", C.c_int32), ("groups", C.c_int32), ("weight", C.c_uint64), ("bias", C.c_uint64),
+                ("logits", C.c_uint64), ("dlogits", C.c_uint64), ("loss", C.c_uint64), ("target", C.c_float * 4),
+                ("gweight", C.c_float * 4), ("loss_slot", C.c_int32 * 4)]
+
+
+class DisHeadBwdArgs(C.Structure):
+    _fields_ = [("x", Act), ("c_valid", C.c_int32), ("g_kind", C.c_int32), ("weight", C.c_uint64), ("dlogits", C.c_uint64),
+                ("dweight", C.c_uint64), ("dbias", C.c_uint64), ("gr", C.c_uint64)]
+
+
+class BlendArgs(C.Structure):
+    _fields_ = [("out4", C.c_uint64), ("bg", C.c_uint64), ("dst", C.c_uint64), ("n", C.c_int32), ("h", C.c_int32),
+                ("w", C.c_int32), ("acc_out4", C.c_int32), ("acc_bg", C.c_int32), ("pad_", C.c_int32),
+                ("ddst", C.c_uint64), ("dout4", C.c_uint64), ("dbg", C.c_uint64)]
+
+
+LOSS_L1, LOSS_FOCUS = 0, 1
+
+
+class LossReduceArgs(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("n", C.c_int32), ("ca", C.c_int32), ("c", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("a", C.c_uint64), ("b", C.c_uint64), ("acc", C.c_uint64), ("slot", C.c_int32), ("acc_da", C.c_int32),
+                ("da", C.c_uint64), ("gscale", C.c_float), ("upper", C.c_float), ("lower", C.c_float), ("eps", C.c_float)]
+
+
+class FocusGradArgs(C.Structure):
+    _fields_ = [("out4", C.c_uint64), ("dout4", C.c_uint64), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("slot", C.c_int32), ("size_slot", C.c_int32), ("acc", C.c_int32), ("sums", C.c_uint64),
+                ("delta", C.c_float), ("eps", C.c_float), ("gscale", C.c_float), ("pad_", C.c_int32)]
 
 
 class NativeError(RuntimeError):
@@ -226,6 +276,22 @@ def _declare(L):
     L.aclgan_adam_step.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_void_p]
     L.aclgan_adam_advance.argtypes = [C.c_uint64, C.c_void_p]
     L.aclgan_stream_wait_external_event.argtypes = [C.c_void_p, C.c_void_p]
+    L.aclgan_avgpool3x3s2_fwd.argtypes = [C.POINTER(AvgPoolArgs), C.c_void_p]
+    L.aclgan_avgpool3x3s2_bwd.argtypes = [C.POINTER(AvgPoolArgs), C.c_void_p]
+    L.aclgan_style_head_fwd.argtypes = [C.POINTER(StyleHeadArgs), C.c_void_p]
+    L.aclgan_style_head_bwd.argtypes = [C.POINTER(StyleHeadArgs), C.c_void_p]
+    L.aclgan_mlp_fwd.argtypes = [C.POINTER(MlpArgs), C.c_void_p]
+    L.aclgan_mlp_bwd.argtypes = [C.POINTER(MlpArgs), C.c_void_p]
+    L.aclgan_dis_head_fwd.argtypes = [C.POINTER(DisHeadArgs), C.c_void_p]
+    L.aclgan_dis_head_bwd.argtypes = [C.POINTER(DisHeadBwdArgs), C.c_void_p]
+    L.aclgan_focus_blend_fwd.argtypes = [C.POINTER(BlendArgs), C.c_void_p]
+    L.aclgan_focus_blend_bwd.argtypes = [C.POINTER(BlendArgs), C.c_void_p]
+    L.aclgan_loss_reduce.argtypes = [C.POINTER(LossReduceArgs), C.c_void_p]
+    L.aclgan_focus_grad.argtypes = [C.POINTER(FocusGradArgs), C.c_void_p]
+    L.aclgan_loss_combine.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]
+    L.aclgan_axpby.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_int64, C.c_int32, C.c_void_p]
+    L.aclgan_zero.argtypes = [C.c_uint64, C.c_int64, C.c_void_p]
+    L.aclgan_copy.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p]
 
 
 launch_count = 0

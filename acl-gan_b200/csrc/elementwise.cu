@@ -808,6 +808,14 @@ __global__ void norm_bwd_finalize_kernel(aclgan_norm_bwd_finalize_args a) {
             cc[c] = (float)(-r * s1 / M);
             atomicAdd(reinterpret_cast<float*>(a.dw) + c, (float)sums[2 * c + 1]);
             atomicAdd(reinterpret_cast<float*>(a.db) + c, (float)sums[2 * c]);
+            if (a.dbias != 0) {
+                // conv bias in front of LayerNorm: db[c] = sum over (n, hw) of dy = ca*T1 + cb*sum_hw(yhat) + cc*HW
+                const double mu = reinterpret_cast<const float*>(a.mean)[(int64_t)n * a.c + c];
+                const double s1f = reinterpret_cast<const double*>(a.fsums)[((int64_t)n * a.c + c) * 2];
+                const double syh = (s1f - (double)a.hw * mu) * r;
+                const double dbv = (double)ca[c] * sums[2 * c] + (double)cb[c] * syh + (double)cc[c] * (double)a.hw;
+                atomicAdd(reinterpret_cast<float*>(a.dbias) + c, (float)dbv);
+            }
         }
         return;
     }

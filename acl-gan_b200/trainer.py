@@ -121,6 +121,14 @@ class aclgan_Trainer(nn.Module):
     def _nets(self):
         return (self.gen_AB, self.gen_BA, self.dis_A, self.dis_B, self.dis_2)
 
+    def _repack_dirty(self):
+        """re-derives the packed bf16 weights of every layer whose fp32 master was replaced outside the fused Adam kernel
+        (load_state_dict hook, or a manual edit followed by net.mark_dirty()); cheap no-op otherwise"""
+        for net in self._nets():
+            for l in net.conv_layers():
+                if l.dirty:
+                    l.repack()
+
     # ------------------------------------------------------------------------------------------ optimizer
     def _adam_group(self, opt, nets, arena):
         """device tables for the fused Adam kernel; the torch.optim.Adam object keeps owning the state tensors
@@ -436,6 +444,7 @@ class aclgan_Trainer(nn.Module):
         if self.use_graphs:
             self._replay("gen", x_a, x_b, hyperparameters)
         else:
+            self._repack_dirty()
             self._gen_fwd_bwd(x_a, x_b, hyperparameters, self._draw_noise(x_a.size(0)))
         self._allreduce(self.gen_arena)
         self._adam_step(self._adam_gen)
@@ -521,6 +530,7 @@ class aclgan_Trainer(nn.Module):
         if self.use_graphs:
             self._replay("dis", x_a, x_b, hyperparameters)
         else:
+            self._repack_dirty()
             self._dis_fwd_bwd(x_a, x_b, hyperparameters, self._draw_noise(x_a.size(0)))
         self._allreduce(self.dis_arena)
         self._adam_step(self._adam_dis)
@@ -594,15 +604,25 @@ class aclgan_Trainer(nn.Module):
         if ent is None:
             ent = self._capture(kind, x_a, x_b, hp)
             self._graphs[key] = ent
+        self._repack_dirty()
         ent["xa"].copy_(x_a, non_blocking=True)
         ent["xb"].copy_(x_b, non_blocking=True)
+        # pinned noise staging is double-buffered: the H2D copy of the previous replay may still be queued behind tens of
+        # milliseconds of GPU work, so a buffer is only rewritten after the copy that last read it has completed
+        slot = ent["zslot"] = 1 - ent.get("zslot", 1)
+        zpin = ent["zpin"][slot]
+        if ent["zev"][slot] is not None:
+            ent["zev"][slot].synchronize()
         if self._noise is not None:
             zs, self._noise = self._noise, None
-            ent["zpin"].copy_(torch.stack([z.reshape(n, self.style_dim).float().cpu() for z in zs]))
+            zpin.copy_(torch.stack([z.reshape(n, self.style_dim).float().cpu() for z in zs]))
         else:       # three CPU randn draws in the reference's order (trainer.py:99-101 / 254-256)
             for i in range(3):
-                ent["zpin"][i].copy_(torch.randn(n, self.style_dim, 1, 1).view(n, self.style_dim))
-        ent["z"].copy_(ent["zpin"], non_blocking=True)
+                zpin[i].copy_(torch.randn(n, self.style_dim, 1, 1).view(n, self.style_dim))
+        ent["z"].copy_(zpin, non_blocking=True)
+        if ent["zev"][slot] is None:
+            ent["zev"][slot] = torch.cuda.Event()
+        ent["zev"][slot].record()
         ent["graph"].replay()
         for k, v in ent["losses"].items():
             setattr(self, k, v)
@@ -614,7 +634,8 @@ class aclgan_Trainer(nn.Module):
         ent = dict(xa=torch.empty(x_a.shape, dtype=torch.float32, device=dev),
                    xb=torch.empty(x_b.shape, dtype=torch.float32, device=dev),
                    z=torch.zeros((3, n, self.style_dim), dtype=torch.float32, device=dev),
-                   zpin=torch.zeros((3, n, self.style_dim), dtype=torch.float32).pin_memory())
+                   zpin=[torch.zeros((3, n, self.style_dim), dtype=torch.float32).pin_memory() for _ in range(2)],
+                   zev=[None, None])
         ent["xa"].copy_(x_a)
         ent["xb"].copy_(x_b)
         impl = self._gen_fwd_bwd if kind == "gen" else self._dis_fwd_bwd
@@ -628,10 +649,7 @@ class aclgan_Trainer(nn.Module):
 
         # warm-up off the capture stream (lazy initialisation of kernels / cuBLAS); forward + backward only,
         # so no parameter, optimizer or RNG state is touched
-        for net in self._nets():
-            for l in net.conv_layers():
-                if l.dirty:
-                    l.repack()
+        self._repack_dirty()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         ent["pool"] = E.SumsPool(dev)           # counting mode: the warm-up run measures the statistics workspace
@@ -734,7 +752,13 @@ class aclgan_Trainer(nn.Module):
         self.gen_opt.load_state_dict(sd["gen"])
         self.dis_scheduler = get_scheduler(self.dis_opt, hyperparameters, iterations)
         self.gen_scheduler = get_scheduler(self.gen_opt, hyperparameters, iterations)
-        self._ready = False      # optimizer state tensors were replaced: rebuild the device tables lazily
+        if self._ready:
+            # the networks keep their engine layers, gradient arenas and captured graphs (load_state_dict copied into the
+            # same parameter tensors); only the optimizer state tensors were replaced: rebuild the Adam device tables
+            # around them and re-derive the packed bf16 weights from the restored masters
+            self._adam_gen = self._adam_group(self.gen_opt, (self.gen_AB, self.gen_BA), self.gen_arena)
+            self._adam_dis = self._adam_group(self.dis_opt, (self.dis_A, self.dis_B, self.dis_2), self.dis_arena)
+            self._repack_dirty()
         print("Resume from iteration %d" % iterations)
         return iterations
 

@@ -186,9 +186,12 @@ def get_all_data_loaders(conf):
     h, w = conf["crop_image_height"], conf["crop_image_width"]
     if "data_root" in conf:
         root = conf["data_root"]
-        mk = lambda sub, train, size: get_data_loader_folder(os.path.join(root, sub), bs, train, size, h, w, nw, True)
+        # test loaders crop to new_size x new_size (reference utils.py:57-60), train loaders to the configured crop
+        mk = lambda sub, train, size: get_data_loader_folder(os.path.join(root, sub), bs, train, size,
+                                                             h if train else size, w if train else size, nw, True)
         return mk("trainA", True, size_a), mk("trainB", True, size_b), mk("testA", False, size_a), mk("testB", False, size_b)
-    mk = lambda folder, lst, train, size: get_data_loader_list(conf[folder], conf[lst], bs, train, size, h, w, nw, True)
+    mk = lambda folder, lst, train, size: get_data_loader_list(conf[folder], conf[lst], bs, train, size,
+                                                               h if train else size, w if train else size, nw, True)
     return (mk("data_folder_train_a", "data_list_train_a", True, size_a),
             mk("data_folder_train_b", "data_list_train_b", True, size_b),
             mk("data_folder_test_a", "data_list_test_a", False, size_a),

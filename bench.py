@@ -1,7 +1,7 @@
 """Benchmark of the ACL-GAN convolutional training step (BASELINE.json metric: training images/s at 256x256).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's B200 path (one rank per GPU under torchrun)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm's CPU path (oracle port) on host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference's CPU path (oracle/_ref) on host cores
 
 One "step" = one step-pair (dis_update + gen_update on the same batch, what the reference's train.py:71-74 executes on
 even iterations) on synthetic uniform[-1,1] 256x256 RGB batches, batch 8 per GPU (BASELINE.json configs[1]; weak scaling).
@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-bar", action="store_true",
+                    help="skip the extra leg that times the unmodified reference as eager PyTorch/cuDNN on this GPU")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
                     help="after warm-up run ONE step-pair between cudaProfilerStart/Stop and exit (for ncu "
@@ -98,31 +100,79 @@ class ClockSampler:
                     power_w_max=max(float(r[3]) for r in rows))
 
 
-def cpu_baseline(cfg, size, steps=1, warmup=0):
-    """the reference algorithm on the host cores: oracle port (plain torch CPU fp32), bs=1 step-pairs at `size`^2"""
-    import torch
-    import aclgan_oracle as O
+def _host_threads():
     # intra-op threads: all host cores up to 32 (beyond that torch's CPU convolutions on these small per-image
     # shapes slow down from oversubscription: 128 threads measured 34x slower than 8)
-    cores = min(os.cpu_count() or 1, 32)
+    return min(os.cpu_count() or 1, 32)
+
+
+def _reference_available():
+    try:
+        import ref_shim
+        return ref_shim.available()
+    except Exception:
+        return False
+
+
+def cpu_baseline(cfg, size, steps=1, warmup=0, budget_s=200.0):
+    """the reference's CPU path on the host cores, bs=1 step-pairs at `size`^2 (a bounded sample of the bs=8 workload).
+    kind "reference": the UNMODIFIED reference modules (oracle/_ref, verbatim copy made by oracle/make_ref.py) under the
+    CPU shim of oracle/ref_shim.py, driven through its own aclgan_Trainer.dis_update / gen_update; kind "port": the
+    oracle restatement (oracle/aclgan_oracle.py), used only when the reference copy is absent."""
+    import torch
+    cores = _host_threads()
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    ot = O.OracleTrainer(copy.deepcopy(cfg))
     g = torch.Generator().manual_seed(1234)
     x_a = torch.rand(1, 3, size, size, generator=g) * 2 - 1
     x_b = torch.rand(1, 3, size, size, generator=g) * 2 - 1
+    if _reference_available():
+        import contextlib
+        import ref_shim
+        _, trainer_mod, _ = ref_shim.import_reference()
+        shim, kind = ref_shim.cpu_shim, "reference"
+        with shim():
+            torch.manual_seed(0)
+            tr = trainer_mod.aclgan_Trainer(copy.deepcopy(cfg))
+
+        def pair():
+            with shim():
+                tr.dis_update(x_a, x_b, cfg)
+                tr.gen_update(x_a, x_b, cfg)
+        what = "the UNMODIFIED reference (oracle/_ref: trainer.py dis_update + gen_update under the CPU shim)"
+    else:
+        import aclgan_oracle as O
+        torch.manual_seed(0)
+        ot = O.OracleTrainer(copy.deepcopy(cfg))
+        kind = "port"
+
+        def pair():
+            ot.dis_update(x_a, x_b)
+            ot.gen_update(x_a, x_b)
+        what = "the oracle port (oracle/aclgan_oracle.py)"
+    done_warm = 0
+    t_first = None
     for _ in range(warmup):
-        ot.dis_update(x_a, x_b)
-        ot.gen_update(x_a, x_b)
+        t0 = time.time()
+        pair()
+        t_first = time.time() - t0 if t_first is None else t_first
+        done_warm += 1
+    if t_first is not None and steps * t_first > budget_s:      # keep the whole run within a few minutes
+        steps = max(1, int(budget_s / t_first))
     t0 = time.time()
     for _ in range(steps):
-        ot.dis_update(x_a, x_b)
-        ot.gen_update(x_a, x_b)
+        pair()
     dt = (time.time() - t0) / steps
-    return dict(value=1.0 / dt, unit="images/s", cores=cores, kind="port",
-                sample="%d step-pair(s) of the oracle port (oracle/aclgan_oracle.py, torch CPU fp32, %d threads of %d host "
-                       "cores) at %dx%d bs=1 after %d warm-up" % (steps, cores, os.cpu_count() or 1, size, size, warmup),
+    return dict(value=1.0 / dt, unit="images/s", cores=cores, kind=kind, steps=steps, warmup=done_warm,
+                sample="%d step-pair(s) of %s, torch CPU fp32, %d threads of %d host cores, at %dx%d bs=1 after %d warm-up" % (
+                    steps, what, cores, os.cpu_count() or 1, size, size, done_warm),
                 s_per_step_pair=dt)
+
+
+def workload_config(args, world):
+    B, S = args.batch, args.size
+    return dict(workload="%s %dx%d synthetic RGB, bs=%d per GPU, step-pair = dis_update + gen_update" % (args.config, S, S, B),
+                global_batch=B * world, parallelism="dp%d" % world, cuda_graphs=not args.no_graphs,
+                l2="per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush")
 
 
 def run_reference(args):
@@ -131,15 +181,55 @@ def run_reference(args):
         return
     cfg = load_cfg(args.config)
     steps = max(1, args.steps)
-    cb = cpu_baseline(cfg, args.size, steps=steps, warmup=min(args.warmup, 1))
+    cb = cpu_baseline(cfg, args.size, steps=steps, warmup=max(1, args.warmup))
     line = dict(metric="training images/sec @256x256 (dis_update + gen_update step-pair)", value=cb["value"],
-                unit="images/s", n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 1),
+                unit="images/s", n_gpus=args.gpus, steps=cb["steps"], warmup=cb["warmup"],
                 ms_per_step=cb["s_per_step_pair"] * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="%s %dx%d synthetic, bs=1 per step (bounded CPU sample of the bs=%d workload)" % (
-                    args.config, args.size, args.size, args.batch)),
+                config=workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
                 cpu_baseline=cb, e2e=dict(value=cb["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
+
+
+def library_bar(cfg, batch, size, steps=3, warmup=2):
+    """extra leg (not the reference arm): the UNMODIFIED reference (oracle/_ref) as eager PyTorch -> cuDNN / ATen on the same
+    B200 - "the Blackwell kernel to beat" of SURVEY.md 2.2.  cudnn.benchmark = True as train.py:29; (a) stock settings
+    (conv TF32 allowed, the torch default) and (b) the same under torch.autocast(bfloat16)."""
+    import torch
+    if not _reference_available():
+        return dict(unavailable="oracle/_ref not present on this box (run __graft_entry__.build() where /root/reference exists)")
+    import ref_shim
+    _, trainer_mod, _ = ref_shim.import_reference()
+    torch.backends.cudnn.benchmark = True
+    out = dict(what="unmodified reference trainer.py dis_update + gen_update, eager PyTorch %s + cuDNN on cuda:0, bs=%d %dx%d, "
+                    "%d step-pairs after %d warm-up" % (torch.__version__, batch, size, size, steps, warmup))
+    g = torch.Generator().manual_seed(1234)
+    x_a = (torch.rand(batch, 3, size, size, generator=g) * 2 - 1).cuda()
+    x_b = (torch.rand(batch, 3, size, size, generator=g) * 2 - 1).cuda()
+    import contextlib
+    for tag, ctx in (("tf32_default", contextlib.nullcontext), ("bf16_autocast", lambda: torch.autocast("cuda", dtype=torch.bfloat16))):
+        try:
+            torch.manual_seed(0)
+            tr = trainer_mod.aclgan_Trainer(copy.deepcopy(cfg)).cuda()
+            with ctx():
+                for _ in range(warmup):
+                    tr.dis_update(x_a, x_b, cfg)
+                    tr.gen_update(x_a, x_b, cfg)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    tr.dis_update(x_a, x_b, cfg)
+                    tr.gen_update(x_a, x_b, cfg)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[tag] = dict(images_per_s=batch / (ms * 1e-3), ms_per_step_pair=ms)
+            del tr
+            torch.cuda.empty_cache()
+        except Exception as ex:      # noqa: BLE001 - a measurement leg must never take the bench line down
+            out[tag] = dict(error="%s: %s" % (type(ex).__name__, str(ex)[:200]))
+    return out
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel from the committed ncu --set full capture
@@ -270,6 +360,13 @@ def run_b200(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     loss_val = [float(v) for v in loss_host]
+
+    def step_2to1():        # the shipped schedule (D_update 1, G_update 2: train.py:71-74): two iterations = 2 x dis + 1 x gen
+        tr.dis_update(dev_a, dev_b, cfg)
+        tr.gen_update(dev_a, dev_b, cfg)
+        tr.dis_update(dev_a, dev_b, cfg)
+    step_2to1()
+    ms_2to1 = timed(step_2to1, max(2, args.steps // 2))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -285,9 +382,7 @@ def run_b200(args):
         metric="training images/sec @256x256 (dis_update + gen_update step-pair)", value=img_s, unit="images/s",
         n_gpus=world, steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_res, higher_is_better=True,
         scaling="weak", vs_baseline=None, dtype="bf16" if args.precision == "bf16" else "bf16x3(~f32)", data="synthetic",
-        config=dict(workload="%s %dx%d synthetic RGB, bs=%d per GPU, step-pair = dis_update + gen_update" % (args.config, S, S, B),
-                    global_batch=B * world, parallelism="dp%d" % world, cuda_graphs=not args.no_graphs,
-                    l2="per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush"),
+        config=workload_config(args, world),
         e2e=dict(value=img_s_e2e, unit="images/s", h2d_bytes_per_step=2 * host_a.numel() * 4 + 3 * 2 * B * 8 * 4,
                  d2h_bytes_per_step=8, ms_per_step=ms_e2e, losses=loss_val),
         gpu_launches=launches if launches is not None else -1,
@@ -296,7 +391,13 @@ def run_b200(args):
                               peak=pk["sustained"], frac=f_alg * img_s / world / pk["sustained"],
                               peak_source=pk["src"] + " bf16_tflops_sustained (kernel inside a long step)"),
     )
+    line["schedule_2to1"] = dict(value=2 * B * world / (ms_2to1 * 1e-3), unit="images/s (iterations x batch; D_update 1, G_update 2 "
+                                 "as shipped in the YAML: 2 dis_update + 1 gen_update per 2 iterations)", ms_per_2_iterations=ms_2to1)
     line["roofline"] = kernel_roofline(args.precision, B, pk)
+    del tr
+    torch.cuda.empty_cache()
+    if not args.no_library_bar and world == 1:
+        line["library_bar"] = library_bar(load_cfg(args.config), B, S)
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(load_cfg(args.config), S, steps=1, warmup=0)
     print(json.dumps(line))

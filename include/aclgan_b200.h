@@ -280,6 +280,11 @@ typedef struct aclgan_norm_bwd_finalize_args {
     uint64_t ca, cb, cc;    /* out fp32 [n][c] */
     uint64_t dw, db;        /* out: ADAIN fp32 [n][c] (assigned); LN fp32 [c] (accumulated: +=) ; IN unused */
     int64_t wb_stride;      /* ADAIN: sample stride of w, dw and db in elements (0 = c_valid) */
+    /* LN only: gradient of the conv bias in front of the LayerNorm (NOT cancelled: the statistics span all channels):
+     * dbias[c] += sum_n ca*T1 + cb*sum_hw(yhat) + cc*HW with sum_hw(yhat) = (S1fwd - HW*mean)*inv; 0 = skip */
+    uint64_t fsums;         /* double [n][c][2]: the FORWARD statistics (S1 = sum of y) */
+    uint64_t mean;          /* fp32 [n][c] forward mean */
+    uint64_t dbias;         /* fp32 [c_valid] accumulated with atomics, or 0 */
 } aclgan_norm_bwd_finalize_args;
 int aclgan_norm_bwd_finalize(const aclgan_norm_bwd_finalize_args* a, void* stream);
 
@@ -333,6 +338,129 @@ typedef struct aclgan_adam_tensor {
  * chunks (device, int32[2*n_chunks]): (tensor id, first element / 1024) per CTA. */
 int aclgan_adam_step(uint64_t table, uint64_t chunks, int32_t n_chunks, uint64_t hyper, void* stream);
 int aclgan_adam_advance(uint64_t hyper, void* stream);
+
+/* ================= small operators: csrc/smallops.cu ================= */
+
+/* AvgPool2d(3, stride 2, padding 1, count_include_pad=False) of the multi-scale discriminator's image pyramid on NCHW fp32
+ * images (reference networks.py:33,53).  Output extent (h - 1) / 2 + 1.  Bit-identical to the ATen kernel: the window is
+ * summed row-major in fp32 and divided once by the number of valid elements (4 | 6 | 9). */
+typedef struct aclgan_avgpool_args {
+    uint64_t src, dst;   /* fwd: src [planes][h][w] -> dst [planes][ho][wo];  bwd: src = d(dst) [planes][ho][wo] -> dst = d(src) [planes][h][w] */
+    int32_t planes;      /* n * c */
+    int32_t h, w;        /* extent of the un-pooled image */
+    int32_t accumulate;  /* bwd: dst += */
+} aclgan_avgpool_args;
+int aclgan_avgpool3x3s2_fwd(const aclgan_avgpool_args* a, void* stream);
+int aclgan_avgpool3x3s2_bwd(const aclgan_avgpool_args* a, void* stream);
+
+/* style head: AdaptiveAvgPool2d(1) + Conv2d(C, style_dim, 1) (networks.py:222-223) and its backward */
+typedef struct aclgan_style_head_args {
+    aclgan_act x;             /* last style-encoder plane */
+    int32_t c_valid, style_dim;
+    uint64_t weight, bias;    /* fp32 [style_dim][c_valid], [style_dim] */
+    uint64_t pooled;          /* fp32 [n][c_valid]: written by fwd, read by bwd */
+    uint64_t style;           /* fwd out: fp32 [n][style_dim] */
+    uint64_t dstyle;          /* bwd in:  fp32 [n][style_dim] */
+    uint64_t dweight, dbias;  /* bwd: accumulated (+=), or 0 */
+    uint64_t gr;              /* bwd out: dense gradient of the plane [n][h][w][x.c] (assigned) */
+    int32_t g_kind;           /* 0 bf16, 1 fp32 */
+    int32_t pad_;
+} aclgan_style_head_args;
+int aclgan_style_head_fwd(const aclgan_style_head_args* a, void* stream);
+int aclgan_style_head_bwd(const aclgan_style_head_args* a, void* stream);
+
+/* MLP of Linear(+ReLU) layers, ReLU on all but the last (networks.py:280-292: 8 -> 256 -> 256 -> n_adain) */
+typedef struct aclgan_mlp_args {
+    int32_t n, n_layers;      /* samples, layers (<= 4) */
+    int32_t dims[5];          /* in, hidden ..., out */
+    int32_t pad_;
+    uint64_t w[4], b[4];      /* fp32 [dims[l+1]][dims[l]], [dims[l+1]] */
+    uint64_t h[5];            /* fp32 activations [n][dims[l]]: h[0] input, h[n_layers] output (post-ReLU values for hidden layers) */
+    int64_t h0_stride;        /* row stride of h[0] in elements (0 = dims[0]) */
+    uint64_t dh[5];           /* bwd: dh[n_layers] = gradient of the output (in); dh[l] scratch [n][dims[l]] for 0 < l < n_layers;
+                                 dh[0] = gradient of the input (out) or 0 */
+    uint64_t dw[4], db[4];    /* bwd: accumulated (+=), or 0 */
+} aclgan_mlp_args;
+int aclgan_mlp_fwd(const aclgan_mlp_args* a, void* stream);
+int aclgan_mlp_bwd(const aclgan_mlp_args* a, void* stream);
+
+/* discriminator head Conv2d(C, 1, 1) (networks.py:45) fused with the LSGAN terms mean((o - t)^2) of networks.py:67,83,98 and
+ * their gradient seed.  The batch holds `groups` image groups of equal size (one discriminator evaluated once over the
+ * concatenation of its inputs); group g has target[g], loss weight gweight[g] and loss accumulator slot loss_slot[g]. */
+typedef struct aclgan_dis_head_args {
+    aclgan_act x;             /* last feature plane */
+    int32_t c_valid, groups;  /* groups <= 4 */
+    uint64_t weight, bias;    /* fp32 [c_valid], [1] */
+    uint64_t logits;          /* out fp32 [N][h][w] */
+    uint64_t dlogits;         /* out fp32 [N][h][w] = gweight[g] * 2 (o - target[g]) / (n_per * h * w), or 0 */
+    uint64_t loss;            /* double accumulators: loss[loss_slot[g]] += mean over the group of (o - target[g])^2, or 0 */
+    float target[4], gweight[4];
+    int32_t loss_slot[4];
+} aclgan_dis_head_args;
+int aclgan_dis_head_fwd(const aclgan_dis_head_args* a, void* stream);
+typedef struct aclgan_dis_head_bwd_args {
+    aclgan_act x;
+    int32_t c_valid, g_kind;
+    uint64_t weight, dlogits;
+    uint64_t dweight, dbias;  /* accumulated with atomics, or 0 (generator update: no discriminator weight gradients) */
+    uint64_t gr;              /* out: dense gradient of the plane [N][h][w][x.c] (assigned), or 0 */
+} aclgan_dis_head_bwd_args;
+int aclgan_dis_head_bwd(const aclgan_dis_head_bwd_args* a, void* stream);
+
+/* focus_translation (trainer.py:85-88): dst = fg * m + bg * (1 - m), m = (mask + 1) / 2, fg / mask = channels 0-2 / 3 of the
+ * decoder output; same rounding sequence as the reference's fp32 expression.  bwd: adjoint into d(out4) and d(bg). */
+typedef struct aclgan_blend_args {
+    uint64_t out4;            /* fp32 [n][4][h][w] */
+    uint64_t bg;              /* fp32 [n][3][h][w] */
+    uint64_t dst;             /* fwd out fp32 [n][3][h][w] */
+    int32_t n, h, w;
+    int32_t acc_out4, acc_bg; /* bwd: 1 = accumulate (+=), 0 = assign */
+    int32_t pad_;
+    uint64_t ddst;            /* bwd in  [n][3][h][w] */
+    uint64_t dout4;           /* bwd out [n][4][h][w] or 0 */
+    uint64_t dbg;             /* bwd out [n][3][h][w] or 0 */
+} aclgan_blend_args;
+int aclgan_focus_blend_fwd(const aclgan_blend_args* a, void* stream);
+int aclgan_focus_blend_bwd(const aclgan_blend_args* a, void* stream);
+
+/* loss reductions into double accumulators (zeroed by the caller once per update) */
+enum { ACLGAN_LOSS_L1 = 0, ACLGAN_LOSS_FOCUS = 1 };
+typedef struct aclgan_loss_reduce_args {
+    int32_t mode;
+    int32_t n, ca, c, h, w;   /* a is [n][ca][h][w]; L1 compares its first c channels with b [n][c][h][w]; FOCUS reads channel 3 */
+    uint64_t a, b;
+    uint64_t acc;             /* double[]: L1: acc[slot] += mean|a - b| (trainer.py:61-62);
+                                 FOCUS: acc[slot] += sum(m - upper), acc[slot+1] += sum(lower - m), acc[slot+2] += sum 1/(|m-.5|+eps)
+                                 over the WHOLE batch, m = (a[:,3] + 1)/2 (trainer.py:146-151) */
+    int32_t slot;
+    int32_t acc_da;           /* L1: da (+)= */
+    uint64_t da;              /* L1: [n][ca][h][w], channels < c get sign(a - b) * gscale, or 0 */
+    float gscale, upper, lower, eps;
+} aclgan_loss_reduce_args;
+int aclgan_loss_reduce(const aclgan_loss_reduce_args* a, void* stream);
+
+/* second pass of the focus losses: size = delta * (relu(S1)^2 + relu(S2)^2) -> sums[size_slot]; channel 3 of d(out4) (+)=
+ * gscale * (2 delta (relu(S1) - relu(S2)) - sign(m - .5) / (|m - .5| + eps)^2)   (trainer.py:149-161) */
+typedef struct aclgan_focus_grad_args {
+    uint64_t out4, dout4;     /* fp32 [n][4][h][w] */
+    int32_t n, h, w;
+    int32_t slot, size_slot;  /* sums[slot], sums[slot+1] = S1, S2 (from ACLGAN_LOSS_FOCUS) */
+    int32_t acc;
+    uint64_t sums;            /* double[] */
+    float delta, eps, gscale;
+    int32_t pad_;
+} aclgan_focus_grad_args;
+int aclgan_focus_grad(const aclgan_focus_grad_args* a, void* stream);
+
+/* out[j] = sum_k M[j][k] * acc[k]: every loss_* scalar and weighted total of trainer.py:142-165 / 288-290 in one launch */
+int aclgan_loss_combine(uint64_t acc /* double[K] */, uint64_t M /* fp32 [J][K] */, uint64_t out /* fp32 [J] */, int32_t J,
+                        int32_t K, void* stream);
+
+/* dst = alpha * a + beta * b (b may be 0; dst may alias a or b); kind 0 bf16, 1 fp32: gradient accumulation / alpha * z_2 */
+int aclgan_axpby(uint64_t dst, uint64_t a, uint64_t b, float alpha, float beta, int64_t n, int32_t kind, void* stream);
+/* cudaMemsetAsync(0) / device-to-device cudaMemcpyAsync on the caller's stream (memset / memcpy nodes under graph capture) */
+int aclgan_zero(uint64_t ptr, int64_t bytes, void* stream);
+int aclgan_copy(uint64_t dst, uint64_t src, int64_t bytes, void* stream);
 
 /* stream-ordering helper for the host code: wait on an event recorded outside a stream capture (an external event-wait
  * node when `stream` is capturing); returns the cudaError_t */

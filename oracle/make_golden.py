@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
 
-    python oracle/make_golden.py            # writes tests/golden/p0_fp32.pt, p0_fp64.pt, tiny_fp32.pt, tiny_fp64.pt
+    python oracle/make_golden.py            # writes tests/golden/{tiny,p0,p0nf,p1_256,p2_256}_{fp32,fp64}.pt
+                                            # (the two 256x256 cases take ~4 minutes each in fp64 on 8 cores)
 
 Recipe: torch.manual_seed(0) -> aclgan_Trainer(cfg); manual_seed(1) ->
 x_a, x_b = rand(B,3,H,H)*2-1; manual_seed(2) -> 6 style-noise draws (3 for dis_update,
@@ -48,6 +49,10 @@ def case_config(case):
         cfg["dis"].update(dim=16)
         cfg["display_size"] = 2
         return cfg, 2, 64
+    if case == "p1_256":       # BASELINE.json configs[1] geometry (male2female 256x256), batch 2 to bound the CPU fp64 run
+        return load_cfg("male2female.yaml"), 2, 256
+    if case == "p2_256":       # BASELINE.json configs[2] geometry (selfie2anime := focus branch off, 256x256), batch 2
+        return load_cfg("selfie2anime.yaml"), 2, 256
     raise ValueError(case)
 
 
@@ -130,12 +135,27 @@ def run_case(case, dtype):
                     sigs.append(tensor_sig(gr))
             return dict(keys=keys, norm=torch.stack(norms), head=torch.stack(heads), sig=torch.stack(sigs))
 
-        def params_sig(names):
+        def snapshot(names):
+            return {"%s.%s" % (n, k): p.detach().double().clone() for n in names for k, p in getattr(tr, n).named_parameters()}
+
+        def params_sig(names, before):
+            """post-step parameters: sig [P,3] of p_after, and of the UPDATE dp = p_after - p_before: dsig [P,3] (sum, abs-sum,
+            sum of squares) + dhead [P,8] (first 8 elements) - an optimizer that does nothing, or steps the wrong way, shows
+            up in the update even though it is invisible in sig (|dp| ~ lr = 1e-4 of |p|)"""
             keys = ["%s.%s" % (n, k) for n in names for k, p in getattr(tr, n).named_parameters()]
-            sig = torch.stack([tensor_sig(p) for n in names for k, p in getattr(tr, n).named_parameters()])
-            return dict(keys=keys, sig=sig)
+            ps = [p for n in names for k, p in getattr(tr, n).named_parameters()]
+            sig = torch.stack([tensor_sig(p) for p in ps])
+            dsig, dhead = [], []
+            for key, p in zip(keys, ps):
+                d = (p.detach().double() - before[key]).reshape(-1)
+                dsig.append(tensor_sig(d))
+                h = torch.zeros(8, dtype=torch.float64)
+                h[:min(8, d.numel())] = d[:8]
+                dhead.append(h)
+            return dict(keys=keys, sig=sig, dsig=torch.stack(dsig), dhead=torch.stack(dhead))
 
         out["dis_forward"] = forward_images(queue[:3])
+        before_d = snapshot(("dis_A", "dis_B", "dis_2"))
         torch.randn = fake_randn
         try:
             tr.dis_update(x_a, x_b, cfg)
@@ -144,9 +164,10 @@ def run_case(case, dtype):
         out["dis_losses"] = {k: getattr(tr, k).detach().double() for k in
                              ("loss_dis_A", "loss_dis_B", "loss_dis_2", "loss_dis_total")}
         out["dis_grads"] = grads_of(("dis_A", "dis_B", "dis_2"))
-        out["dis_params_after"] = params_sig(("dis_A", "dis_B", "dis_2"))
+        out["dis_params_after"] = params_sig(("dis_A", "dis_B", "dis_2"), before_d)
 
         out["gen_forward"] = forward_images(queue[:3])
+        before_g = snapshot(("gen_AB", "gen_BA"))
         torch.randn = fake_randn
         try:
             tr.gen_update(x_a, x_b, cfg)
@@ -155,22 +176,32 @@ def run_case(case, dtype):
         out["gen_losses"] = {k: v.detach().double() for k, v in vars(tr).items()
                              if k.startswith("loss_gen") or k.startswith("loss_idt")}
         out["gen_grads"] = grads_of(("gen_AB", "gen_BA"))
-        out["gen_params_after"] = params_sig(("gen_AB", "gen_BA"))
+        out["gen_params_after"] = params_sig(("gen_AB", "gen_BA"), before_g)
         # keep the fixture small: images are 64x64; D maps / contents are stored in fp32
         for grp in ("dis_forward", "gen_forward"):
             if dtype == torch.float64:
                 # fp64 fixtures pin losses / gradients / post-step parameters; the forward
                 # tensors live in the fp32 fixture (fp32-vs-fp64 forward differs by ~1e-6)
                 out[grp] = {k: v.float() for k, v in out[grp].items() if k in ("x_A2_fake",)}
-                continue
-            for k, v in out[grp].items():
-                out[grp][k] = [t.float() for t in v] if isinstance(v, list) else v.float()
+            else:
+                for k, v in out[grp].items():
+                    out[grp][k] = [t.float() for t in v] if isinstance(v, list) else v.float()
+            if size > 64:
+                # 256x256 fixtures stay small: full-resolution tensors are replaced by their signature (sum, abs-sum, sum of
+                # squares in fp64) and an 8x-strided sub-sample (the -m gpu test also compares full tensors with the live oracle)
+                comp = {}
+                for k, v in out[grp].items():
+                    if isinstance(v, list) or v.dim() != 4 or v.numel() <= 32768:
+                        comp[k] = v
+                    else:
+                        comp[k] = dict(sig=tensor_sig(v), sub=v[:, :, 3::8, 5::8].contiguous(), shape=tuple(v.shape))
+                out[grp] = comp
     return out
 
 
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    cases = sys.argv[1:] or ["tiny", "p0", "p0nf"]
+    cases = sys.argv[1:] or ["tiny", "p0", "p0nf", "p1_256", "p2_256"]
     for case in cases:
         for dtype, tag in ((torch.float32, "fp32"), (torch.float64, "fp64")):
             res = run_case(case, dtype)

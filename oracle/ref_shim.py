@@ -8,8 +8,9 @@ CPU-only box WITHOUT touching the reference sources:
 * ``torch.Tensor.cuda`` / ``nn.Module.cuda`` become identity while the shim is active,
 * ``yaml.load`` defaults to ``SafeLoader``.
 
-Only usable where ``/root/reference`` exists (the build container); the GPU box does not
-have it, so nothing imported at run time by ``-m gpu`` tests / smoke / bench may use this.
+Usable where ``/root/reference`` exists (the build container) or where ``oracle/make_ref.py`` left its verbatim,
+git-ignored copy in ``oracle/_ref/`` (it travels to the GPU box with the snapshot).  ``/root/reference`` itself is never
+read on the GPU box; callers must check ``available()`` and degrade (skip / fall back to the port) when neither exists.
 """
 import contextlib
 import importlib
@@ -19,7 +20,19 @@ import sys
 import torch
 import yaml
 
-REF_DIR = os.environ.get("ACLGAN_REFERENCE_DIR", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _default_ref_dir():
+    """/root/reference in the build container; on the GPU box the verbatim copy oracle/make_ref.py left in
+    oracle/_ref/ (git-ignored, travels with the gpurun snapshot)"""
+    for d in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isfile(os.path.join(d, "trainer.py")):
+            return d
+    return "/root/reference"
+
+
+REF_DIR = os.environ.get("ACLGAN_REFERENCE_DIR") or _default_ref_dir()
 
 
 def available() -> bool:

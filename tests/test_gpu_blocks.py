@@ -65,6 +65,11 @@ CASES = [
     # 128-pixel output rows: row tiles of the segment kernels, statistics fused in the epilogue, segment weight gradient
     (128, 64, 5, 1, 2, N.NORM_LN, N.ACT_RELU, False, 1, 3, 2, 128),
     (64, 128, 3, 1, 1, N.NORM_ADAIN, N.ACT_RELU, False, 2, 2, 1, 128),
+    # the benchmarked 256x256 decoder tail: 5x5 256->128 (output upsampled to 256, pad 2) and 5x5 128->64 on the 256^2 plane
+    # (out_pad 3 = the final 7x7's reflect width), 4x4 s2 64->128 from 256 wide
+    (256, 128, 5, 1, 2, N.NORM_LN, N.ACT_RELU, False, 2, 2, 1, 128),
+    (128, 64, 5, 1, 2, N.NORM_LN, N.ACT_RELU, False, 1, 3, 1, 256),
+    (64, 128, 4, 2, 1, N.NORM_IN, N.ACT_RELU, False, 1, 1, 1, 256),
 ]
 
 
@@ -213,8 +218,8 @@ def test_image_io_and_final_conv(precision):
     def rel(a, bb):
         return float((a.double() - bb).norm() / (bb.norm() + 1e-30))
     btol = tol * 3
-    if h >= 128 and act != N.ACT_NONE and precision == "fp32x3":
-        # millions of units: a handful of ReLU pre-activations lie within the fp32x3 rounding distance (1e-5) of zero and
+    if h >= 128 and precision == "fp32x3":
+        # millions of LeakyReLU units: a handful of pre-activations lie within the fp32x3 rounding distance (1e-5) of zero and
         # flip against the fp64 reference; each flip moves these relative L2 errors by ~1e-4 (tests/test_gpu_step.py docstring)
         btol = 3e-3
     gw2, gb2 = layer2.grad_views()

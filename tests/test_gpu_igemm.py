@@ -23,6 +23,14 @@ FWD_CASES = [
     (6, 64, 4, 2, 1, 1, 2, 32, 32, 1),
     (64, 4, 7, 1, 3, 0, 1, 32, 32, 1),
     (64, 48, 4, 2, 1, 0, 1, 2, 2, 1),
+    # W = 256 (the benchmarked geometry): two 128-pixel tiles per output row, 258/260/262-wide padded planes
+    (128, 64, 5, 1, 2, 0, 1, 8, 256, 1),       # 5x5 128->64: one-CTA N = 64 segment path
+    (128, 64, 5, 1, 2, 0, 1, 4, 256, 2),
+    (64, 4, 7, 1, 3, 0, 1, 8, 256, 1),         # final 7x7 64->4
+    (64, 4, 7, 1, 3, 0, 1, 4, 256, 2),
+    (3, 64, 7, 1, 3, 1, 1, 8, 256, 1),         # first 7x7 3->64: pixel windows at W = 256
+    (6, 64, 4, 2, 1, 1, 1, 16, 256, 1),        # discriminator first conv on a 256-wide pair
+    (256, 256, 3, 1, 1, 0, 1, 4, 256, 1),
 ]
 
 
@@ -93,6 +101,12 @@ DGRAD_CASES = [
     (128, 64, 5, 1, 2, 2, 128, 128, 1),       # cin 128 -> N = 128 pairs
     (128, 64, 5, 1, 2, 2, 128, 128, 2),
     (64, 64, 3, 1, 1, 2, 128, 128, 2),
+    # 256-wide output rows (benchmarked geometry)
+    (128, 64, 5, 1, 2, 1, 8, 256, 1),
+    (64, 4, 7, 1, 3, 1, 8, 256, 1),
+    (64, 4, 7, 1, 3, 1, 4, 256, 2),
+    (3, 64, 7, 1, 3, 1, 8, 256, 1),
+    (64, 128, 4, 2, 1, 1, 8, 128, 1),          # stride-2 data gradient of a 256-wide input
 ]
 
 
@@ -194,6 +208,13 @@ WGRAD_CASES = [
     (3, 64, 7, 1, 3, 1, 2, 64, 64, 1),
     (6, 64, 4, 2, 1, 1, 2, 128, 128, 1),
     (64, 4, 7, 1, 3, 2, 2, 64, 64, 1),
+    # W = 256 (benchmarked geometry)
+    (128, 64, 5, 1, 2, 0, 1, 8, 256, 1),
+    (64, 4, 7, 1, 3, 2, 1, 8, 256, 1),
+    (64, 4, 7, 1, 3, 2, 1, 4, 256, 2),
+    (3, 64, 7, 1, 3, 1, 1, 8, 256, 1),
+    (6, 64, 4, 2, 1, 1, 1, 16, 256, 1),
+    (64, 128, 4, 2, 1, 0, 1, 16, 256, 1),
 ]
 
 

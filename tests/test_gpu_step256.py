@@ -1,0 +1,191 @@
+"""-m gpu: the BENCHMARKED geometry (256x256; BASELINE.json configs[1] male2female bf16 = P1, configs[2] selfie2anime fp32
+parity = P2) through the drop-in trainer, batch 2, checked against
+
+ (a) golden fixtures generated from the UNMODIFIED reference at 256x256 (oracle/make_golden.py cases p1_256 / p2_256, fp32 and
+     fp64): every loss_*, the generated images (fp64 signatures + an 8x-strided sub-sample), discriminator / generator gradient
+     norms and leading elements, and the optimizer UPDATE dp = p_after - p_before per tensor;
+ (b) the CPU oracle run live on this box in fp32 with shared weights / inputs / noise: the five images in full, every
+     discriminator gradient tensor in full, generator gradients under the statistical rule of tests/test_gpu_step.py.
+
+At 256x256 the stride-1 plans use two 128-pixel tiles per row, 258^2 / 260^2 / 262^2 padded planes, the one-CTA N = 64 path of the
+5x5 128->64 conv and the pixel-window 7x7 at W = 256 - geometries the 64x64 step tests never reach.
+(The fp64 oracle needs ~200 s per step-pair at this size, so the fp64 numbers come from the fixtures only.)"""
+import copy
+import os
+
+import pytest
+import torch
+
+import aclgan_oracle as O
+import trainer as T
+from test_gpu_step import CUSP_CEIL, FLIP_CEIL, _build, _cancelled_bias_keys, _check_updates, _inputs, _load, _rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_image(name, mine, fix, tol):
+    """fixture entry = dict(sig, sub, shape) at 256x256 (full tensor at 64x64)"""
+    if not isinstance(fix, dict):
+        e = _rel(mine, fix)
+        assert e < tol, (name, e)
+        return e
+    assert tuple(mine.shape) == tuple(fix["shape"]), (name, mine.shape, fix["shape"])
+    e = _rel(mine[:, :, 3::8, 5::8], fix["sub"])
+    assert e < tol, (name, "sub-sample", e)
+    t = mine.detach().double().reshape(-1).cpu()
+    sig = torch.stack([t.sum(), t.abs().sum(), (t * t).sum()])
+    for i in (1, 2):       # abs-sum and sum of squares over the FULL tensor (the plain sum cancels to ~0 on images)
+        assert abs(float(sig[i]) - float(fix["sig"][i])) <= tol * abs(float(fix["sig"][i])), (name, "sig", i, sig, fix["sig"])
+    return e
+
+
+@pytest.mark.parametrize("case,precision", [("p2_256", "fp32x3"), ("p1_256", "fp32x3"), ("p1_256", "bf16")])
+def test_step_256_vs_reference_fixture(golden_dir, case, precision):
+    g32, g64 = _load(golden_dir, case, "fp32"), _load(golden_dir, case, "fp64")
+    tr, cfg = _build(g32, precision)
+    x_a, x_b, zs = _inputs(g32)
+    xa, xb = x_a.cuda(), x_b.cuda()
+    par = precision == "fp32x3"
+    ltol = 1e-3 if par else 5e-2
+    report = []
+    names_d, names_g = ("dis_A", "dis_B", "dis_2"), ("gen_AB", "gen_BA")
+    before = {"%s.%s" % (n, k): p.detach().double().cpu().clone() for n in names_d + names_g
+              for k, p in getattr(tr, n).named_parameters()}
+    cancelled = _cancelled_bias_keys(tr)
+
+    tr._noise = zs[:3]
+    tr.dis_update(xa, xb, cfg)
+    torch.cuda.synchronize()
+    for k, v in g32["dis_losses"].items():
+        e = abs(float(getattr(tr, k)) - float(v)) / abs(float(v))
+        report.append((k, e))
+        assert e < ltol, (k, float(getattr(tr, k)), float(v))
+    for k in ("x_B_fake", "x_A_fake", "x_A2_fake"):
+        report.append(("dis " + k, _check_image(k, tr._last_cycle[k].t, g32["dis_forward"][k], ltol)))
+    if par:
+        gg32, gg64 = g32["dis_grads"], g64["dis_grads"]
+        errs = []
+        for i, key in enumerate(gg64["keys"]):
+            n, k = key.split(".", 1)
+            gr = dict(getattr(tr, n).named_parameters())[k].grad.double().cpu().reshape(-1)
+            ref64, ref32 = float(gg64["norm"][i]), float(gg32["norm"][i])
+            allow = max(1e-3, 2 * abs(ref32 - ref64) / ref64)
+            e = abs(float(gr.norm()) - ref64) / ref64
+            errs.append(e)
+            hd = gg64["head"][i][:min(8, gr.numel())]
+            rms = ref64 / max(1.0, gr.numel()) ** 0.5
+            assert e < allow, ("dis grad norm", key, float(gr.norm()), ref64, ref32)
+            assert float((gr[:hd.numel()] - hd).norm()) <= 10 * allow * max(float(hd.norm()), 3 * rms) + 1e-12, ("dis grad head", key)
+        errs.sort()
+        report.append(("dis grad-norm err median", errs[len(errs) // 2]))
+        report.append(("max", errs[-1]))
+        _check_updates(tr, g32["dis_params_after"], before, report, "dis")
+
+    tr._noise = zs[3:]
+    tr.gen_update(xa, xb, cfg)
+    torch.cuda.synchronize()
+    for k, v in g32["gen_losses"].items():
+        e = abs(float(getattr(tr, k)) - float(v)) / max(abs(float(v)), 1e-12)
+        report.append((k, e))
+        assert e < (ltol if "focus" not in k else 5 * ltol), (k, float(getattr(tr, k)), float(v))
+    r = tr._last_cycle
+    for k in ("x_B_fake", "x_A_fake", "x_A2_fake"):
+        report.append(("gen " + k, _check_image(k, r[k].t, g32["gen_forward"][k], ltol)))
+    report.append(("x_A_recon", _check_image("x_A_recon", r["o_rec_a"].t[:, :3], g32["gen_forward"]["x_A_recon"], ltol)))
+    report.append(("x_B_recon", _check_image("x_B_recon", r["o_rec_b"].t[:, :3], g32["gen_forward"]["x_B_recon"], ltol)))
+    if par:
+        gg32, gg64 = g32["gen_grads"], g64["gen_grads"]
+        errs, bad = [], []
+        ceil = CUSP_CEIL if cfg["focus_loss"] > 0 else FLIP_CEIL
+        for i, key in enumerate(gg64["keys"]):
+            n, k = key.split(".", 1)
+            ref64, ref32 = float(gg64["norm"][i]), float(gg32["norm"][i])
+            if ref64 < 1e-6:
+                continue
+            gr = dict(getattr(tr, n).named_parameters())[k].grad.double().cpu().reshape(-1)
+            allow = max(1e-3, 2 * abs(ref32 - ref64) / ref64)
+            e = abs(float(gr.norm()) - ref64) / ref64
+            errs.append(e)
+            if not e < max(allow, ceil):
+                bad.append((key, "%.4e" % float(gr.norm()), "%.4e" % ref64, "%.4e" % ref32))
+        assert not bad, ("gen grads", bad[:40])
+        errs.sort()
+        report.append(("gen grad-norm err median", errs[len(errs) // 2]))
+        report.append(("max", errs[-1]))
+        if cfg["focus_loss"] == 0:
+            assert errs[len(errs) // 2] < 5e-3, ("median gen grad-norm error", errs[len(errs) // 2])
+            _check_updates(tr, g32["gen_params_after"], before, report, "gen", cancelled)
+    else:
+        for n in names_g + names_d:
+            for k, p in getattr(tr, n).named_parameters():
+                assert bool(torch.isfinite(p).all()) and bool(torch.isfinite(p.grad).all()), (n, k)
+    print("\n[step parity 256x256 %s %s] " % (case, precision) + "  ".join("%s=%.2e" % kv for kv in report))
+
+
+@pytest.mark.parametrize("case", ["p2_256", "p1_256"])
+def test_step_256_vs_live_oracle(golden_dir, case):
+    """fp32x3 vs the CPU oracle (fp32) on shared weights at 256x256, batch 2: the five images and every discriminator gradient
+    in full (<= 1e-3), generator gradients tensor by tensor under the statistical rule (median <= 5e-3, max <= FLIP_CEIL).
+    male2female runs at the cusp-free operating point (mask bias - 1.5, tests/test_gpu_step.py docstring)."""
+    g32 = _load(golden_dir, case, "fp32")
+    tr, cfg = _build(g32, "fp32x3")
+    if cfg["focus_loss"] > 0:
+        with torch.no_grad():
+            for gnet in (tr.gen_AB, tr.gen_BA):
+                list(gnet.dec.model)[-1].conv.bias[3] -= 1.5
+    x_a, x_b, zs = _inputs(g32)
+    sds = {n: {k: v.detach().cpu().clone() for k, v in getattr(tr, n).state_dict().items()} for n in O.OracleTrainer.NETS}
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+    ot = O.OracleTrainer(copy.deepcopy(g32["cfg"]), construct=False)
+    ot.load_state_dicts(sds)
+    ld, td = ot.dis_update(x_a, x_b, zs[:3], step=False)
+    gd = {(n, k): v.grad.clone() for n in ("dis_A", "dis_B", "dis_2") for k, v in ot.nets[n].items() if v.grad is not None}
+    lg, tg = ot.gen_update(x_a, x_b, zs[3:], step=False)
+    gg = {(n, k): v.grad.clone() for n in ("gen_AB", "gen_BA") for k, v in ot.nets[n].items() if v.grad is not None}
+    for opt in (tr.dis_opt, tr.gen_opt):
+        for grp in opt.param_groups:
+            grp["lr"] = 0.0
+            grp["weight_decay"] = 0.0
+    tr._noise = zs[:3]
+    tr.dis_update(x_a.cuda(), x_b.cuda(), cfg)
+    torch.cuda.synchronize()
+    rep = []
+    for k, v in ld.items():
+        e = abs(float(getattr(tr, k)) - float(v)) / abs(float(v))
+        rep.append((k, e))
+        assert e < 1e-3, (k, e)
+    for k in ("x_B_fake", "x_A_fake", "x_A2_fake"):
+        e = _rel(tr._last_cycle[k].t, td[k])
+        rep.append(("dis " + k, e))
+        assert e < 1e-3, (k, e)
+    errs_d = []
+    for (n, k), ref in gd.items():
+        e = _rel(dict(getattr(tr, n).named_parameters())[k].grad, ref)
+        errs_d.append((e, n + "." + k))
+    errs_d.sort()
+    assert errs_d[-1][0] < 1e-3, errs_d[-5:]
+    tr._noise = zs[3:]
+    tr.gen_update(x_a.cuda(), x_b.cuda(), cfg)
+    torch.cuda.synchronize()
+    for k, v in lg.items():
+        e = abs(float(getattr(tr, k)) - float(v)) / max(abs(float(v)), 1e-12)
+        rep.append((k, e))
+        assert e < (1e-3 if "focus" not in k else 5e-3), (k, float(getattr(tr, k)), float(v))
+    r = tr._last_cycle
+    for k, mine in (("x_B_fake", r["x_B_fake"].t), ("x_A_fake", r["x_A_fake"].t), ("x_A2_fake", r["x_A2_fake"].t),
+                    ("x_A_recon", r["o_rec_a"].t[:, :3]), ("x_B_recon", r["o_rec_b"].t[:, :3])):
+        e = _rel(mine, tg[k])
+        rep.append(("gen " + k, e))
+        assert e < 1e-3, (k, e)
+    errs_g = []
+    for (n, k), ref in gg.items():
+        if float(ref.norm()) < 1e-7:
+            continue
+        errs_g.append((_rel(dict(getattr(tr, n).named_parameters())[k].grad, ref), n + "." + k))
+    errs_g.sort()
+    print("\n[256x256 %s vs live fp32 oracle] %s ; dis grads (%d tensors, full): median %.2e max %.2e ; gen grads (%d): median %.2e "
+          "90%% %.2e max %.2e at %s" % (case, "  ".join("%s=%.1e" % kv for kv in rep), len(errs_d), errs_d[len(errs_d) // 2][0],
+                                       errs_d[-1][0], len(errs_g), errs_g[len(errs_g) // 2][0], errs_g[int(len(errs_g) * 0.9)][0],
+                                       errs_g[-1][0], errs_g[-1][1]))
+    assert errs_g[len(errs_g) // 2][0] < 5e-3, "systematic generator gradient error"
+    assert errs_g[-1][0] < FLIP_CEIL, errs_g[-5:]

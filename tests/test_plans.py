@@ -58,6 +58,11 @@ FWD_CASES = [
     (64, 48, 4, 2, 1, 0, 1, 2, 2, 1),
     (64, 64, 5, 1, 2, 0, 1, 3, 128, 1),        # row tiles (128-pixel output rows) in segment mode
     (128, 16, 3, 1, 1, 0, 2, 3, 128, 2),
+    # W = 256 (benchmarked geometry): two row tiles per output row; pixel windows / small cout at 256 wide
+    (64, 64, 5, 1, 2, 0, 1, 3, 256, 1),
+    (3, 64, 7, 1, 3, 1, 1, 4, 256, 1),
+    (64, 4, 7, 1, 3, 0, 1, 4, 256, 1),
+    (6, 16, 4, 2, 1, 1, 1, 4, 256, 1),
 ]
 
 
@@ -108,6 +113,8 @@ DGRAD_CASES = [
     (64, 64, 4, 2, 1, 2, 2, 2, 2),
     (64, 4, 7, 1, 3, 2, 4, 4, 1),
     (64, 4, 7, 1, 3, 1, 8, 8, 2),
+    (64, 64, 5, 1, 2, 1, 2, 256, 1),          # 256-wide output rows (benchmarked geometry)
+    (64, 4, 7, 1, 3, 1, 2, 256, 1),
 ]
 
 
@@ -180,6 +187,8 @@ WGRAD_CASES = [
     (128, 128, 3, 1, 1, 0, 1, 3, 64, 1),
     (128, 64, 5, 1, 2, 0, 1, 3, 128, 1),
     (64, 128, 3, 1, 1, 0, 2, 2, 64, 2),
+    (64, 64, 5, 1, 2, 0, 1, 3, 256, 1),       # W = 256 (benchmarked geometry)
+    (64, 4, 7, 1, 3, 2, 1, 4, 256, 1),
 ]
 
 

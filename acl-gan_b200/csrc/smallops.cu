@@ -424,6 +424,15 @@ __global__ void axpby_kernel<__nv_bfloat16>(__nv_bfloat16* dst, const __nv_bfloa
         dst[i] = __float2bfloat16_rn(alpha * __bfloat162float(a[i]) + (b != nullptr ? beta * __bfloat162float(b[i]) : 0.f));
 }
 
+// dst[c] += sum_n sums[n][c][0] (fp64 per-(n, c) sums of the generic backward-reduce kernel -> fp32 conv-bias gradient)
+__global__ void stats_to_bias_kernel(const double* __restrict__ sums, float* __restrict__ dst, int n, int c, int c_valid) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c_valid) return;
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += sums[((int64_t)i * c + ch) * 2];
+    dst[ch] += (float)s;
+}
+
 static inline int grid1d(int64_t total, int block, int cap = 148 * 8) {
     int64_t g = (total + block - 1) / block;
     if (g > cap) g = cap;
@@ -584,4 +593,11 @@ extern "C" int aclgan_copy(uint64_t dst, uint64_t src, int64_t bytes, void* stre
     if (bytes <= 0) return ACLGAN_OK;
     return (int)cudaMemcpyAsync(reinterpret_cast<void*>(dst), reinterpret_cast<const void*>(src), (size_t)bytes,
                                 cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+}
+
+extern "C" int aclgan_stats_to_bias(uint64_t sums, uint64_t dst, int32_t n, int32_t c, int32_t c_valid, void* stream) {
+    if (n < 1 || c_valid < 1 || c_valid > c) return ACLGAN_ERR_SHAPE;
+    stats_to_bias_kernel<<<(c_valid + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(sums),
+                                                                                reinterpret_cast<float*>(dst), n, c, c_valid);
+    return (int)cudaGetLastError();
 }

@@ -26,6 +26,60 @@ def round_up(a, b):
     return (a + b - 1) // b * b
 
 
+def _rc(rc, what):
+    """status check of a C-ABI call that launches no kernel (memset / memcpy nodes)"""
+    if rc != 0:
+        raise N.NativeError("%s failed with status %d" % (what, rc))
+
+
+def zero_(t):
+    """cudaMemsetAsync on the current stream (a memset node under graph capture) instead of an ATen fill kernel"""
+    if not t.is_cuda:           # host-side bookkeeping objects in the CPU unit tests (the compute path is CUDA only)
+        return t.zero_()
+    _rc(N.lib().aclgan_zero(t.data_ptr(), t.numel() * t.element_size(), _sp()), "zero")
+    return t
+
+
+def zeros(shape, dtype, device):
+    return zero_(torch.empty(shape, dtype=dtype, device=device))
+
+
+def copy_(dst, src):
+    """contiguous device-to-device copy as a memcpy node"""
+    assert dst.is_contiguous() and src.is_contiguous() and dst.dtype == src.dtype and dst.numel() == src.numel()
+    _rc(N.lib().aclgan_copy(dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size(), _sp()), "copy")
+    return dst
+
+
+def axpby(dst, a, b, alpha=1.0, beta=1.0):
+    """dst = alpha * a + beta * b (b may be None) on bf16 / fp32 contiguous tensors: gradient accumulation without ATen"""
+    assert dst.is_contiguous() and a.is_contiguous() and dst.dtype == a.dtype and dst.numel() == a.numel()
+    assert dst.dtype in (torch.float32, torch.bfloat16)
+    if b is not None:
+        assert b.is_contiguous() and b.dtype == a.dtype and b.numel() == a.numel()
+    N.check(N.lib().aclgan_axpby(dst.data_ptr(), a.data_ptr(), b.data_ptr() if b is not None else 0, float(alpha), float(beta),
+                                 dst.numel(), 1 if dst.dtype == torch.float32 else 0, _sp()), "axpby")
+    return dst
+
+
+def acc_(dst, src):
+    """dst += src"""
+    return axpby(dst, dst, src, 1.0, 1.0)
+
+
+def cat0(tensors):
+    """torch.cat along dim 0 of contiguous tensors as memcpy nodes"""
+    if len(tensors) == 1:
+        return tensors[0]
+    out = torch.empty((sum(t.shape[0] for t in tensors),) + tuple(tensors[0].shape[1:]), dtype=tensors[0].dtype,
+                      device=tensors[0].device)
+    off = 0
+    for t in tensors:
+        copy_(out[off:off + t.shape[0]], t.contiguous())
+        off += t.shape[0]
+    return out
+
+
 class Precision:
     """bf16: one bf16 plane, bf16 raw conv outputs and gradients (throughput mode).
     fp32x3: hi/lo bf16 planes (3 tensor-core passes ~ fp32 products), fp32 raw outputs and gradients (parity mode)."""
@@ -90,8 +144,9 @@ class ActT:
         self.numel = n * (h + 2 * pad) * (w + 2 * pad) * self.c
         # planes with fewer than 64 channels are read through pixel-window tensor maps that overrun the plane by up to
         # 64 elements (zeroed slack); full-width planes are only ever read inside their extent (TMA zero-fills beyond)
-        alloc = torch.zeros if (zero or self.c < 64 or self.c != c_valid) else torch.empty
-        self.buf = alloc((self.planes, self.numel + 64), dtype=torch.bfloat16, device=eng.device)
+        self.buf = torch.empty((self.planes, self.numel + 64), dtype=torch.bfloat16, device=eng.device)
+        if zero or self.c < 64 or self.c != c_valid:
+            zero_(self.buf)
         self.gp = None            # gradient of the padded plane [n, h+2p, w+2p, c] (engine gradient dtype)
         self.gr = None            # dense gradient [n, h, w, c] (residual branches / heads)
         self.requires_grad = False
@@ -104,10 +159,10 @@ class ActT:
         return a
 
     def add_gp(self, g):
-        self.gp = g if self.gp is None else self.gp.add_(g)
+        self.gp = g if self.gp is None else acc_(self.gp, g)
 
     def add_gr(self, g):
-        self.gr = g if self.gr is None else self.gr.add_(g)
+        self.gr = g if self.gr is None else acc_(self.gr, g)
 
     def value_nchw(self):
         """fp32 NCHW copy of the logical (un-padded, valid-channel) content - for tests / API boundaries."""
@@ -127,7 +182,20 @@ class ImgT:
         self.grad = None
 
     def add_grad(self, g):
-        self.grad = g if self.grad is None else self.grad.add_(g)
+        self.grad = g if self.grad is None else acc_(self.grad, g.contiguous())
+
+    def grad_buffer(self):
+        """(tensor to write d/d(self.t) into, accumulate flag): the existing gradient (accumulate) or a fresh one (assign)"""
+        if self.grad is None:
+            self.grad = torch.empty_like(self.t)
+            return self.grad, 0
+        return self.grad, 1
+
+    def zero_grad_buffer(self):
+        """gradient buffer that may be accumulated into channel-wise: zero-filled (memset) when it does not exist yet"""
+        if self.grad is None:
+            self.grad = zeros(self.t.shape, self.t.dtype, self.t.device)
+        return self.grad
 
 
 class SumsPool:
@@ -142,7 +210,7 @@ class SumsPool:
     def begin(self):
         self.off = 0
         if self.buf is not None:
-            self.buf.zero_()
+            zero_(self.buf)
 
     def take(self, shape):
         numel = 1
@@ -151,7 +219,7 @@ class SumsPool:
         numel = round_up(numel, 2)
         if self.buf is None or self.off + numel > self.buf.numel():
             self.off += numel
-            return torch.zeros(shape, dtype=torch.float64, device=self.device)
+            return zeros(shape, torch.float64, self.device)
         t = self.buf[self.off:self.off + numel].view(shape)
         self.off += numel
         return t
@@ -178,7 +246,7 @@ class GradArena:
         return self.flat[off:off + numel]
 
     def zero_(self):
-        self.flat.zero_()
+        zero_(self.flat)
 
 
 def _affine_index(desc, transposed, shape):
@@ -284,7 +352,7 @@ class Engine:
     def sums(self, n, cs):
         if self.pool is not None:
             return self.pool.take((n, cs, 2))
-        return torch.zeros((n, cs, 2), dtype=torch.float64, device=self.device)
+        return zeros((n, cs, 2), torch.float64, self.device)
 
     def _check_device(self):
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -292,8 +360,8 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------ helpers
     def new_dense(self, n, h, w, c, zero=False):
-        f = torch.zeros if zero else torch.empty
-        return f((n, h, w, c), dtype=self.prec.dtype, device=self.device)
+        t = torch.empty((n, h, w, c), dtype=self.prec.dtype, device=self.device)
+        return zero_(t) if zero else t
 
     def t4(self, t):
         n, h, w, c = t.shape
@@ -321,13 +389,12 @@ class Engine:
                     if img is None or not img.requires_grad:
                         continue
                     u = N.ImgGradUnpackArgs()
-                    g = torch.empty_like(img.t)
+                    g, acc = img.grad_buffer()
                     u.src = out.gp.data_ptr()
                     u.n, u.c, u.h, u.w = n, img.t.shape[1], h, w
                     u.cs, u.pad, u.c_off = out.gp.shape[-1], pad, off
-                    u.dst, u.accumulate = g.data_ptr(), 0
+                    u.dst, u.accumulate = g.data_ptr(), acc
                     N.check(N.lib().aclgan_img_grad_unpack(C.byref(u), _sp()), "img_grad_unpack")
-                    img.add_grad(g)
                 out.gp = None
             tape.push(bwd)
         return out
@@ -336,16 +403,17 @@ class Engine:
         """two copies of a plane along the batch axis (one content code decoded with two styles in ONE batched pass:
         trainer.py:109,113 decode c_2 twice); the gradients of both halves are summed back into `x`"""
         out = ActT(self, 2 * x.n, x.h, x.w, x.c_valid, x.pad)
-        out.buf[:, :x.numel].copy_(x.buf[:, :x.numel])
-        out.buf[:, x.numel:2 * x.numel].copy_(x.buf[:, :x.numel])
+        for p in range(x.planes):
+            copy_(out.buf[p, :x.numel], x.buf[p, :x.numel])
+            copy_(out.buf[p, x.numel:2 * x.numel], x.buf[p, :x.numel])
         out.requires_grad = x.requires_grad
         if tape.enabled and x.requires_grad:
             def bwd():
                 n = x.n
                 if out.gp is not None:
-                    x.add_gp(out.gp[:n] + out.gp[n:])
+                    x.add_gp(axpby(torch.empty_like(out.gp[:n]), out.gp[:n], out.gp[n:]))
                 if out.gr is not None:
-                    x.add_gr(out.gr[:n] + out.gr[n:])
+                    x.add_gr(axpby(torch.empty_like(out.gr[:n]), out.gr[:n], out.gr[n:]))
                 out.gp = out.gr = None
             tape.push(bwd)
         return out
@@ -401,7 +469,7 @@ class Engine:
         hp, wp = x.h + 2 * x.pad, x.w + 2 * x.pad
         cs = x.c if x.c >= 64 else 16           # image planes: 3|6 channels -> one 16-wide UMMA column block
         if x.c < 64:
-            g = torch.zeros((x.n, hp, wp, cs), dtype=torch.float32, device=self.device)
+            g = zeros((x.n, hp, wp, cs), torch.float32, self.device)
         else:
             g = self.new_dense(x.n, hp, wp, cs, zero=(cs != round_up(layer.cin, 16)))
         dys = dy.struct()
@@ -473,7 +541,7 @@ class Engine:
                 a.res = res.struct()
             a.upsample, a.dst = upsample, out.struct()
             N.check(L.aclgan_norm_apply(C.byref(a), _sp()), "norm_apply")
-            saved = (y, coef, sigma, sums[:, :, 0].clone() if norm == N.NORM_LN else None)
+            saved = (y, coef, sigma, sums if norm == N.NORM_LN else None)     # (pool slices live until the update ends)
         need_x_grad = x.requires_grad
         out.requires_grad = need_x_grad or train_w or (res is not None and res.requires_grad) or adain is not None
         if not tape.enabled or not out.requires_grad:
@@ -503,7 +571,7 @@ class Engine:
                 if train_w:         # conv bias gradient = sum of dz: fused into the apply pass below
                     b.dbias, b.dbias_n = layer.db().data_ptr(), cout
             else:
-                y, coef, sigma, fwd_s1 = saved
+                y, coef, sigma, fwd_sums = saved
                 sums = self.sums(n, cs)
                 b.sums = sums.data_ptr()
                 b.norm = 1
@@ -522,16 +590,11 @@ class Engine:
                 elif norm == N.NORM_LN:
                     f.w, f.dw, f.db = ln[0].data_ptr(), ln[2].data_ptr(), ln[3].data_ptr()
                 f.ca, f.cb, f.cc = (cf[i].data_ptr() for i in range(3))
-                N.check(L.aclgan_norm_bwd_finalize(C.byref(f), _sp()), "norm_bwd_finalize")
                 if norm == N.NORM_LN and train_w:
-                    # a conv bias in front of LayerNorm is NOT cancelled (statistics span all channels):
-                    # db[c] = sum_{n,hw} dy with dy = ca*dz + cb*yhat + cc:
-                    #        = sum_n ca*T1 + cb*sum_hw(yhat) + cc*HW,   sum_hw(yhat) = (S1 - HW*mean) * inv
-                    hw = float(ho * wo)
-                    syh = (fwd_s1[:, :cout] - hw * coef[2, :, :cout].double()) * coef[3, :, :cout].double()
-                    db = (cf[0, :, :cout].double() * sums[:, :cout, 0] + cf[1, :, :cout].double() * syh +
-                          cf[2, :, :cout].double() * hw).sum(0)
-                    layer.db().add_(db.float())
+                    # a conv bias in front of LayerNorm is NOT cancelled (statistics span all channels): the finalize kernel
+                    # adds db[c] = sum_n ca*T1 + cb*sum_hw(yhat) + cc*HW with sum_hw(yhat) = (S1 - HW*mean) * inv
+                    f.fsums, f.mean, f.dbias = fwd_sums.data_ptr(), coef[2].data_ptr(), layer.db().data_ptr()
+                N.check(L.aclgan_norm_bwd_finalize(C.byref(f), _sp()), "norm_bwd_finalize")
                 b.ca, b.cb, b.cc = (cf[i].data_ptr() for i in range(3))
             rc = L.aclgan_block_bwd_apply(C.byref(b), _sp())
             if rc == -3 and b.dbias:
@@ -540,7 +603,7 @@ class Engine:
                 sums = self.sums(n, cs)
                 b.sums = sums.data_ptr()
                 N.check(L.aclgan_block_bwd_reduce(C.byref(b), _sp()), "block_bwd_reduce")
-                layer.db().add_(sums[:, :cout, 0].sum(0).float())
+                N.check(L.aclgan_stats_to_bias(sums.data_ptr(), layer.db().data_ptr(), n, cs, cout, _sp()), "stats_to_bias")
                 rc = L.aclgan_block_bwd_apply(C.byref(b), _sp())
             N.check(rc, "block_bwd_apply")
             if self.debug is not None:
@@ -559,7 +622,7 @@ class Engine:
     def _fold_only(self, gp, gr, out, upsample):
         """dense gradient of the logical block output (fold of the padded / upsampled plane gradient)"""
         if gp is None:
-            return gr.clone()
+            return copy_(torch.empty_like(gr), gr)
         b = N.BlockBwdArgs()
         cs = gp.shape[-1]
         h, w = out.h // upsample, out.w // upsample

@@ -12,6 +12,8 @@ Two call levels:
   * engine API (`enc(...)`, `dec(...)`, `dis(...)`) used by trainer.py, which records the hand-scheduled
     backward pass on an `engine.Tape`.
 """
+import ctypes as C
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -368,23 +370,27 @@ class AdaINGen(_EngineNet):
             nxt_pad = convs[i + 1].spec["pad"] if i + 1 < len(convs) else 0
             x = eng.conv_block(tape, blk._layer, x, norm=N.NORM_NONE, act=act, out_pad=nxt_pad, train_w=tw)
         head = m[-1]
-        c = x.c_valid
-        xf = x.buf[:, :x.numel].float().sum(0).view(x.n, x.h * x.w, x.c)[:, :, :c]
-        pooled = xf.mean(1)                                              # AdaptiveAvgPool2d(1)
-        w2 = head.weight.detach().view(head.weight.shape[0], c)
-        style = E.ImgT(torch.addmm(head.bias.detach(), pooled, w2.t()), requires_grad=tape.enabled)
+        c, sd = x.c_valid, head.weight.shape[0]
+        L = N.lib()
+        a = N.StyleHeadArgs()
+        a.x, a.c_valid, a.style_dim = x.struct(), c, sd
+        a.weight, a.bias = head.weight.data_ptr(), head.bias.data_ptr()
+        pooled = torch.empty((x.n, c), dtype=torch.float32, device=eng.device)
+        st = torch.empty((x.n, sd), dtype=torch.float32, device=eng.device)
+        a.pooled, a.style = pooled.data_ptr(), st.data_ptr()
+        N.check(L.aclgan_style_head_fwd(C.byref(a), E._sp()), "style_head_fwd")      # AdaptiveAvgPool2d(1) + Conv2d 1x1
+        style = E.ImgT(st, requires_grad=tape.enabled)
         if tape.enabled:
             def bwd():
                 if style.grad is None:
                     return
-                ds = style.grad
+                ds = style.grad.contiguous()
                 style.grad = None
+                g = torch.empty((x.n, x.h, x.w, x.c), dtype=eng.prec.dtype, device=eng.device)
+                a.dstyle, a.gr, a.g_kind = ds.data_ptr(), g.data_ptr(), eng.prec.kind
                 if tw:
-                    self._grad_of(head.weight).view(-1, c).add_(ds.t() @ pooled)
-                    self._grad_of(head.bias).add_(ds.sum(0))
-                dp = (ds @ w2) / float(x.h * x.w)                        # [n, c]
-                g = torch.zeros((x.n, x.h, x.w, x.c), dtype=eng.prec.dtype, device=eng.device)
-                g[..., :c] = dp.view(x.n, 1, 1, c).to(eng.prec.dtype)
+                    a.dweight, a.dbias = self._grad_of(head.weight).data_ptr(), self._grad_of(head.bias).data_ptr()
+                N.check(L.aclgan_style_head_bwd(C.byref(a), E._sp()), "style_head_bwd")
                 x.add_gr(g)
             tape.push(bwd)
         return style
@@ -393,27 +399,42 @@ class AdaINGen(_EngineNet):
         """MLP (networks.py:280-292) on an E.ImgT [N, style_dim] -> E.ImgT [N, n_adain]"""
         self._ensure_bound()
         tw = self.train_weights and tape.enabled
+        eng = self._eng
         fcs = [lb.fc for lb in self.mlp.model]
-        hs = [style.t.reshape(style.t.shape[0], -1)]
+        x0 = style.t.reshape(style.t.shape[0], -1).contiguous()
+        n = x0.shape[0]
+        a = N.MlpArgs()
+        a.n, a.n_layers = n, len(fcs)
+        hs = [x0]
         for i, fc in enumerate(fcs):
-            z = torch.addmm(fc.bias.detach(), hs[-1], fc.weight.detach().t())
-            hs.append(torch.relu(z) if i + 1 < len(fcs) else z)
+            a.dims[i], a.dims[i + 1] = fc.weight.shape[1], fc.weight.shape[0]
+            a.w[i], a.b[i] = fc.weight.data_ptr(), fc.bias.data_ptr()
+            hs.append(torch.empty((n, fc.weight.shape[0]), dtype=torch.float32, device=eng.device))
+        for i, h in enumerate(hs):
+            a.h[i] = h.data_ptr()
+        a.h0_stride = x0.shape[1]
+        N.check(N.lib().aclgan_mlp_fwd(C.byref(a), E._sp()), "mlp_fwd")
         out = E.ImgT(hs[-1], requires_grad=tape.enabled)
         if tape.enabled:
             def bwd():
                 if out.grad is None:
                     return
-                g = out.grad
+                g = out.grad.contiguous()
                 out.grad = None
-                for i in reversed(range(len(fcs))):
-                    if i + 1 < len(fcs):
-                        g = g * (hs[i + 1] > 0).to(g.dtype)
-                    if tw:
-                        self._grad_of(fcs[i].weight).add_(g.t() @ hs[i])
-                        self._grad_of(fcs[i].bias).add_(g.sum(0))
-                    g = g @ fcs[i].weight.detach()
+                scratch = [torch.empty_like(h) for h in hs[1:-1]]
+                a.dh[len(fcs)] = g.data_ptr()
+                for i, t in enumerate(scratch):
+                    a.dh[i + 1] = t.data_ptr()
+                d0 = None
                 if style.requires_grad:
-                    style.add_grad(g.view_as(style.t))
+                    d0 = torch.empty_like(x0)
+                    a.dh[0] = d0.data_ptr()
+                if tw:
+                    for i, fc in enumerate(fcs):
+                        a.dw[i], a.db[i] = self._grad_of(fc.weight).data_ptr(), self._grad_of(fc.bias).data_ptr()
+                N.check(N.lib().aclgan_mlp_bwd(C.byref(a), E._sp()), "mlp_bwd")
+                if d0 is not None:
+                    style.add_grad(d0.view_as(style.t))
             tape.push(bwd)
         return out
 
@@ -428,7 +449,7 @@ class AdaINGen(_EngineNet):
         n = content.n
         d_ap = None
         if tape.enabled:
-            d_ap = torch.zeros_like(ap.t)
+            d_ap = E.zeros(ap.t.shape, ap.t.dtype, ap.t.device)
 
             def bwd_ap():
                 ap.add_grad(d_ap)
@@ -549,11 +570,11 @@ class MsImageDis(_EngineNet):
                     self._reserve_dense(blk.bias)
 
     # ---- engine API ---------------------------------------------------------------------------------
-    def dis(self, tape, img0, img1=None):
+    def dis(self, tape, img0, img1=None, lsgan=None):
         """forward over all scales; img1 = second image of a channel-concatenated pair (dis_2).
         returns a list of E.ImgT logits [N,1,h,w]"""
         pyr = self.dis_pyramid(tape, img0, img1)
-        return [self.dis_scale(tape, s, pyr[s]) for s in range(len(self.cnns))]
+        return [self.dis_scale(tape, s, pyr[s], lsgan) for s in range(len(self.cnns))]
 
     def dis_pyramid(self, tape, img0, img1=None):
         """the input of every scale: the image(s) and their AvgPool2d(3, 2, 1) pyramid (networks.py:33,53)"""
@@ -565,8 +586,10 @@ class MsImageDis(_EngineNet):
             pyr.append(imgs)
         return pyr
 
-    def dis_scale(self, tape, s, imgs):
-        """one scale's PatchGAN (networks.py:38-47): the scales are independent chains once the pyramid exists"""
+    def dis_scale(self, tape, s, imgs, lsgan=None):
+        """one scale's PatchGAN (networks.py:38-47): the scales are independent chains once the pyramid exists.
+        lsgan = dict(acc=<double accumulators>, targets, weights, slots): the LSGAN terms of networks.py:67,83,98 and their
+        gradient seed are fused into the head kernel (image groups along the batch, one entry per group)"""
         self._ensure_bound()
         eng, tw = self._eng, self.train_weights and tape.enabled
         act = _ACT[self.activ]
@@ -576,44 +599,75 @@ class MsImageDis(_EngineNet):
         for i, blk in enumerate(blocks):
             x = eng.conv_block(tape, blk._layer, x, norm=N.NORM_NONE, act=act,
                                out_pad=1 if i + 1 < len(blocks) else 0, train_w=tw)
-        return self._head(tape, net[-1], x, tw)
+        return self._head(tape, net[-1], x, tw, lsgan)
 
     def _pool(self, tape, img):
         """AvgPool2d(3, 2, padding 1, count_include_pad=False) on the NCHW image (networks.py:33,53)"""
-        t = F.avg_pool2d(img.t, 3, stride=2, padding=1, count_include_pad=False)
+        n, c, h, w = img.t.shape
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        src = img.t.contiguous()
+        t = torch.empty((n, c, ho, wo), dtype=torch.float32, device=src.device)
+        a = N.AvgPoolArgs(src.data_ptr(), t.data_ptr(), n * c, h, w, 0)
+        N.check(N.lib().aclgan_avgpool3x3s2_fwd(C.byref(a), E._sp()), "avgpool_fwd")
         out = E.ImgT(t, requires_grad=img.requires_grad)
         if tape.enabled and img.requires_grad:
             def bwd():
                 if out.grad is None:
                     return
-                g = torch.ops.aten.avg_pool2d_backward(out.grad, img.t, [3, 3], [2, 2], [1, 1], False, False, None)
+                go = out.grad.contiguous()
                 out.grad = None
-                img.add_grad(g)
+                g, acc = img.grad_buffer()
+                b = N.AvgPoolArgs(go.data_ptr(), g.data_ptr(), n * c, h, w, acc)
+                N.check(N.lib().aclgan_avgpool3x3s2_bwd(C.byref(b), E._sp()), "avgpool_bwd")
             tape.push(bwd)
         return out
 
-    def _head(self, tape, conv, x, tw):
-        """1x1 conv dim*8 -> 1 (networks.py:45): per-pixel dot product on the un-padded plane"""
+    def _head(self, tape, conv, x, tw, lsgan=None):
+        """1x1 conv dim*8 -> 1 (networks.py:45) as a warp-per-pixel dot product on the un-padded plane, fused with the LSGAN
+        terms (per image group) and d loss / d logits when `lsgan` is given"""
         eng = self._eng
+        L = N.lib()
         c = x.c_valid
-        xf = x.buf[:, :x.numel].float().sum(0).view(x.n, x.h, x.w, x.c)[..., :c]
-        wv = conv.weight.detach().view(c)
-        logit = E.ImgT((xf @ wv + conv.bias.detach()).view(x.n, 1, x.h, x.w), requires_grad=tape.enabled)
+        a = N.DisHeadArgs()
+        a.x, a.c_valid = x.struct(), c
+        a.weight, a.bias = conv.weight.data_ptr(), conv.bias.data_ptr()
+        lt = torch.empty((x.n, 1, x.h, x.w), dtype=torch.float32, device=eng.device)
+        a.logits = lt.data_ptr()
+        dl = None
+        a.groups = 1
+        if lsgan is not None:
+            k = len(lsgan["targets"])
+            a.groups = k
+            for i in range(k):
+                a.target[i], a.gweight[i], a.loss_slot[i] = lsgan["targets"][i], lsgan["weights"][i], lsgan["slots"][i]
+            a.loss = lsgan["acc"].data_ptr()
+            if tape.enabled:
+                dl = torch.empty((x.n, 1, x.h, x.w), dtype=torch.float32, device=eng.device)
+                a.dlogits = dl.data_ptr()
+        N.check(L.aclgan_dis_head_fwd(C.byref(a), E._sp()), "dis_head_fwd")
+        logit = E.ImgT(lt, requires_grad=tape.enabled)
         if tape.enabled:
             def bwd():
-                if logit.grad is None:
+                d = dl
+                if logit.grad is not None:       # a gradient seeded by the caller (tests / custom losses) adds to the fused seed
+                    # (seeded on the caller's stream, consumed on this chain's stream: keep the allocator from reusing it early)
+                    if logit.grad.is_cuda:
+                        logit.grad.record_stream(torch.cuda.current_stream())
+                    d = logit.grad.contiguous() if d is None else E.acc_(d, logit.grad.contiguous())
+                    logit.grad = None
+                if d is None:
                     return
-                # (seeded on the caller's stream, consumed on this chain's stream: keep the allocator from reusing it early)
-                if logit.grad.is_cuda:
-                    logit.grad.record_stream(torch.cuda.current_stream())
-                d = logit.grad.view(x.n, x.h, x.w)
-                logit.grad = None
+                b = N.DisHeadBwdArgs()
+                b.x, b.c_valid, b.g_kind = x.struct(), c, eng.prec.kind
+                b.weight, b.dlogits = conv.weight.data_ptr(), d.data_ptr()
                 if tw:
-                    self._grad_of(conv.weight).view(c).add_(torch.einsum("nhw,nhwc->c", d, xf))
-                    self._grad_of(conv.bias).add_(d.sum().view(1))
+                    b.dweight, b.dbias = self._grad_of(conv.weight).data_ptr(), self._grad_of(conv.bias).data_ptr()
+                g = None
                 if x.requires_grad:
-                    g = torch.zeros((x.n, x.h, x.w, x.c), dtype=eng.prec.dtype, device=eng.device)
-                    g[..., :c] = (d.unsqueeze(-1) * wv).to(eng.prec.dtype)
+                    g = torch.empty((x.n, x.h, x.w, x.c), dtype=eng.prec.dtype, device=eng.device)
+                    b.gr = g.data_ptr()
+                N.check(L.aclgan_dis_head_bwd(C.byref(b), E._sp()), "dis_head_bwd")
+                if g is not None:
                     x.add_gr(g)
             tape.push(bwd)
         return logit

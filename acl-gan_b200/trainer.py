@@ -62,6 +62,7 @@ class aclgan_Trainer(nn.Module):
         self.use_graphs = bool(int(hp.get("cuda_graphs", os.environ.get("ACLGAN_CUDA_GRAPHS", "1"))))
         self._graphs = {}
         self._launches = {}
+        self._lplans = {}
         self.merge_passes = bool(int(hp.get("merge_passes", os.environ.get("ACLGAN_MERGE_PASSES", "1"))))
         self.parallel_dis = bool(int(hp.get("parallel_dis", os.environ.get("ACLGAN_PARALLEL_DIS", "1"))))
         # one chain per (discriminator, scale) instead of per discriminator: the sub-wave kernels of the small scales
@@ -238,37 +239,30 @@ class aclgan_Trainer(nn.Module):
         return x_fg * x_map + x_bg * (1 - x_map)
 
     def _blend(self, tape, out, bg):
-        """decoder output [N,4,H,W] -> focus-blended RGB (trainer.py:85-88,108-111); returns (image, raw mask)"""
-        fg, f = out.t[:, :3], out.t[:, 3:4]
-        m = (f + 1) / 2
-        res = E.ImgT(fg * m + bg.t * (1 - m), requires_grad=out.requires_grad or bg.requires_grad)
+        """decoder output [N,4,H,W] -> focus-blended RGB (trainer.py:85-88,108-111) by the blend kernel; the raw mask stays
+        channel 3 of `out`"""
+        import ctypes as C
+        n, _, h, w = out.t.shape
+        o4, bgt = out.t.contiguous(), bg.t.contiguous()
+        dst = torch.empty((n, 3, h, w), dtype=torch.float32, device=o4.device)
+        a = N.BlendArgs()
+        a.out4, a.bg, a.dst, a.n, a.h, a.w = o4.data_ptr(), bgt.data_ptr(), dst.data_ptr(), n, h, w
+        N.check(N.lib().aclgan_focus_blend_fwd(C.byref(a), E._sp()), "focus_blend_fwd")
+        res = E.ImgT(dst, requires_grad=out.requires_grad or bg.requires_grad)
         if tape.enabled and res.requires_grad:
             def bwd():
                 if res.grad is None:
                     return
-                d = res.grad
+                d = res.grad.contiguous()
                 res.grad = None
+                a.ddst = d.data_ptr()
                 if out.requires_grad:
-                    do = torch.cat((d * m, (d * (fg - bg.t)).sum(1, keepdim=True) * 0.5), 1)
-                    out.add_grad(do)
+                    g, a.acc_out4 = out.grad_buffer()
+                    a.dout4 = g.data_ptr()
                 if bg.requires_grad:
-                    bg.add_grad(d * (1 - m))
-            tape.push(bwd)
-        return res
-
-    def _rgb(self, tape, out):
-        """first three channels of a decoder output as an image node (the .split(3, 1)[0] of trainer.py:113-114)"""
-        if out.t.shape[1] == 3:
-            return out
-        res = E.ImgT(out.t[:, :3], requires_grad=out.requires_grad)
-        if tape.enabled and res.requires_grad:
-            def bwd():
-                if res.grad is None:
-                    return
-                do = torch.zeros_like(out.t)
-                do[:, :3] = res.grad
-                res.grad = None
-                out.add_grad(do)
+                    g, a.acc_bg = bg.grad_buffer()
+                    a.dbg = g.data_ptr()
+                N.check(N.lib().aclgan_focus_blend_bwd(C.byref(a), E._sp()), "focus_blend_bwd")
             tape.push(bwd)
         return res
 
@@ -299,15 +293,16 @@ class aclgan_Trainer(nn.Module):
         return outs
 
     def _dis_all(self, tape, inputs):
-        """inputs: [(discriminator, img0, img1 | None)] -> list of per-discriminator logit lists.  The pooling pyramids
-        are built first; then every (discriminator, scale) PatchGAN runs as its own parallel chain."""
+        """inputs: [(discriminator, img0, img1 | None, lsgan spec | None)] -> list of per-discriminator logit lists.  The
+        pooling pyramids are built first; then every (discriminator, scale) PatchGAN runs as its own parallel chain.  The
+        LSGAN terms and their gradient seeds are computed by the head kernel of every scale (networks._head)."""
         if not self.parallel_scales:
-            return self._dis_parallel(tape, [lambda t, d=d, a=a, b=b: d.dis(t, a, b) for d, a, b in inputs])
-        pyrs = [d.dis_pyramid(tape, a, b) for d, a, b in inputs]
+            return self._dis_parallel(tape, [lambda t, d=d, a=a, b=b, ls=ls: d.dis(t, a, b, ls) for d, a, b, ls in inputs])
+        pyrs = [d.dis_pyramid(tape, a, b) for d, a, b, _ in inputs]
         jobs, index = [], []
-        for i, (d, _, _) in enumerate(inputs):
+        for i, (d, _, _, ls) in enumerate(inputs):
             for sc in range(len(d.cnns)):
-                jobs.append(lambda t, d=d, sc=sc, imgs=pyrs[i][sc]: d.dis_scale(t, sc, imgs))
+                jobs.append(lambda t, d=d, sc=sc, imgs=pyrs[i][sc], ls=ls: d.dis_scale(t, sc, imgs, ls))
                 index.append(i)
         flat = self._dis_parallel(tape, jobs)
         outs = [[] for _ in inputs]
@@ -319,7 +314,7 @@ class aclgan_Trainer(nn.Module):
         """batch-concatenates image nodes so a discriminator runs ONCE over all of them (3x fewer, 3x larger launches)"""
         if len(imgs) == 1:
             return imgs[0]
-        res = E.ImgT(torch.cat([i.t for i in imgs], 0), requires_grad=any(i.requires_grad for i in imgs))
+        res = E.ImgT(E.cat0([i.t for i in imgs]), requires_grad=any(i.requires_grad for i in imgs))
         if tape.enabled and res.requires_grad:
             def bwd():
                 if res.grad is None:
@@ -341,37 +336,15 @@ class aclgan_Trainer(nn.Module):
             def bwd():
                 if res.grad is None:
                     return
-                if img.grad is None:
-                    img.grad = torch.zeros_like(img.t)
-                img.grad[lo:hi] += res.grad
+                E.acc_(img.zero_grad_buffer()[lo:hi], res.grad.contiguous())
                 res.grad = None
             tape.push(bwd)
         return res
 
     @staticmethod
-    def _lsgan_multi(outs, n, targets, weights):
-        """LSGAN terms of several images pushed through a discriminator as one batch: per image group i (rows
-        [i*n, (i+1)*n) of every scale's logits) sum_scales mean((o - t_i)^2); seeds d loss / d logits with weight w_i"""
-        k = len(targets)
-        totals = [0] * k
-        for o in outs:
-            t = o.t
-            shape = [k * n] + [1] * (t.dim() - 1)
-            # (fill kernels only: a host->device copy of a Python list would break CUDA-graph capture)
-            tv = torch.cat([torch.full((n,), float(v), dtype=t.dtype, device=t.device) for v in targets]).view(shape)
-            diff = t - tv
-            sq = (diff * diff).view(k, -1)
-            per = sq.mean(1)
-            for i in range(k):
-                totals[i] = totals[i] + per[i]
-            if o.requires_grad:
-                wv = torch.cat([torch.full((n,), float(v), dtype=t.dtype, device=t.device) for v in weights]).view(shape)
-                o.add_grad(diff * wv * (2.0 / sq.shape[1]))
-        return totals
-
-    @staticmethod
     def _lsgan(outs, target, weight):
-        """sum over scales of mean((o - t)^2) (networks.py:67,83,98); seeds d loss / d logits scaled by `weight`"""
+        """sum over scales of mean((o - t)^2) (networks.py:67,83,98); seeds d loss / d logits scaled by `weight`.
+        Plain-torch helper for tests / custom losses on top of MsImageDis.dis(); the updates use the fused head kernel."""
         total = 0
         for o in outs:
             diff = o.t - target
@@ -379,6 +352,12 @@ class aclgan_Trainer(nn.Module):
             if o.requires_grad and weight != 0:
                 o.add_grad(diff * (2.0 * weight / diff.numel()))
         return total
+
+    @staticmethod
+    def _scaled(z, alpha):
+        """alpha * z as an image node (trainer.py:109,119,264,269: alpha multiplies only z_2)"""
+        t = z.t.contiguous()
+        return E.ImgT(E.axpby(torch.empty_like(t), t, None, alpha, 0.0))
 
     def _cycle(self, tape, x_a, x_b, zs, need_recon, early=None):
         """encode / decode cycle shared by both updates (trainer.py:103-133 and 258-280); `early(x_B_fake)` is called as
@@ -394,7 +373,7 @@ class aclgan_Trainer(nn.Module):
             # The AB and the BA pass are independent chains (own weights, own gradients): forked like the discriminators.
             n = x_a.t.shape[0]
             xab = self._cat(tape, [x_a, x_b])
-            az_2 = E.ImgT(self.alpha * z_2.t)
+            az_2 = self._scaled(z_2, self.alpha)
 
             def chain_ab(t):
                 c_14 = AB.enc_content_fwd(t, xab)
@@ -410,14 +389,14 @@ class aclgan_Trainer(nn.Module):
             o_b, r["o_rec_b"] = self._slice(tape, o_14, 0, n), self._slice(tape, o_14, n, 2 * n)
             o_a, r["o_rec_a"] = self._slice(tape, o_22, 0, n), self._slice(tape, o_22, n, 2 * n)
         elif not need_recon:
-            az_2 = E.ImgT(self.alpha * z_2.t)
+            az_2 = self._scaled(z_2, self.alpha)
             o_b, o_a = self._dis_parallel(tape, [lambda t: AB.dec_fwd(t, AB.enc_content_fwd(t, x_a), z_1),
                                                  lambda t: BA.dec_fwd(t, BA.enc_content_fwd(t, x_a), az_2)])
         else:
             c_1 = AB.enc_content_fwd(tape, x_a)
             c_2 = BA.enc_content_fwd(tape, x_a)
             o_b = AB.dec_fwd(tape, c_1, z_1)
-            o_a = BA.dec_fwd(tape, c_2, E.ImgT(self.alpha * z_2.t))
+            o_a = BA.dec_fwd(tape, c_2, self._scaled(z_2, self.alpha))
             if need_recon:
                 s_2 = BA.enc_style_fwd(tape, x_a)
                 c_4 = AB.enc_content_fwd(tape, x_b)
@@ -452,62 +431,120 @@ class aclgan_Trainer(nn.Module):
             self.gen_AB.refresh_grads()
             self.gen_BA.refresh_grads()
 
+    # ------------------------------------------------------------------------------------------ loss bookkeeping
+    # Every loss term is reduced on the device into a double accumulator (`acc`, one memset per update); ONE kernel then forms
+    # all loss_* scalars and the weighted totals as out = M @ acc (M is built on the host outside any graph capture).
+    GEN_SLOTS = dict(advA1=0, advA2=1, advB=2, adv2a=3, adv2b=4, idtA=17, idtB=18)        # focus tag t: S1, S2, digit, size = 5+4t ..
+    GEN_OUT = ("loss_gen_adv_A", "loss_gen_adv_B", "loss_gen_adv_2", "loss_gen_focus_B_size", "loss_gen_focus_B_digit",
+               "loss_gen_focus_A_size", "loss_gen_focus_A_digit", "loss_gen_focus_A2_size", "loss_gen_focus_A2_digit",
+               "loss_idt_A", "loss_idt_B", "loss_gen_total")
+    DIS_OUT = ("loss_dis_A", "loss_dis_B", "loss_dis_2", "loss_dis_total")
+
+    def _loss_plan(self, kind, hp, shape):
+        """accumulators + combination matrix of one update kind; cached per (kind, weights, input shape)"""
+        key = (kind, tuple(shape), tuple(sorted((k, v) for k, v in hp.items() if isinstance(v, (int, float)))))
+        plan = self._lplans.get(key)
+        if plan is not None:
+            return plan
+        dev = self.eng.device
+        gw, gcw = float(hp["gan_w"]), float(hp["gan_cw"])
+        if kind == "gen":
+            names, K = self.GEN_OUT, 19
+            M = torch.zeros((len(names), K), dtype=torch.float32)
+            row = {n: i for i, n in enumerate(names)}
+            S = self.GEN_SLOTS
+            M[row["loss_gen_adv_A"], S["advA1"]] = M[row["loss_gen_adv_A"], S["advA2"]] = 0.5
+            M[row["loss_gen_adv_B"], S["advB"]] = 1.0
+            M[row["loss_gen_adv_2"], S["adv2a"]] = M[row["loss_gen_adv_2"], S["adv2b"]] = 1.0
+            M[row["loss_idt_A"], S["idtA"]] = M[row["loss_idt_B"], S["idtB"]] = 1.0
+            for t, tag in enumerate(("B", "A", "A2")):
+                M[row["loss_gen_focus_%s_digit" % tag], 5 + 4 * t + 2] = 1.0
+                M[row["loss_gen_focus_%s_size" % tag], 5 + 4 * t + 3] = 1.0
+            tot = M[row["loss_gen_total"]]
+            tot += gw * M[row["loss_gen_adv_A"]] + gw * M[row["loss_gen_adv_B"]] + gcw * M[row["loss_gen_adv_2"]]
+            tot += float(hp["recon_x_w"]) * (M[row["loss_idt_A"]] + M[row["loss_idt_B"]])
+            if hp["focus_loss"] > 0:
+                fscale = float(hp["focus_loss"]) / float(shape[2]) / float(shape[3]) / float(shape[0]) / 3.0      # trainer.py:161
+                for tag in ("B", "A", "A2"):
+                    tot += fscale * (M[row["loss_gen_focus_%s_size" % tag]] + M[row["loss_gen_focus_%s_digit" % tag]])
+        else:
+            names, K = self.DIS_OUT, 8
+            M = torch.zeros((len(names), K), dtype=torch.float32)
+            # slots: dis_A over [x_a, x_A_fake, x_A2_fake] -> 0, 1, 2; dis_B over [x_B_fake, x_b] -> 3, 4; dis_2 pairs -> 5, 6
+            M[0, 0], M[0, 1], M[0, 2] = 1.0, 0.5, 0.5          # (la1 + la2 + 2 la0) / 2: dis_A(x_a) counted twice at 1/2
+            M[1, 3] = M[1, 4] = 1.0
+            M[2, 5] = M[2, 6] = 1.0
+            M[3] = gw * M[0] + gw * M[1] + gcw * M[2]
+        plan = dict(names=names, K=K, M=M.to(dev), acc=torch.zeros(K, dtype=torch.float64, device=dev),
+                    out=torch.zeros(len(names), dtype=torch.float32, device=dev))
+        self._lplans[key] = plan
+        return plan
+
+    def _loss_finish(self, plan):
+        N.check(N.lib().aclgan_loss_combine(plan["acc"].data_ptr(), plan["M"].data_ptr(), plan["out"].data_ptr(),
+                                            len(plan["names"]), plan["K"], E._sp()), "loss_combine")
+        for i, name in enumerate(plan["names"]):
+            if "focus" in name and not self.focus_lam > 0:
+                continue            # the reference only creates the focus loss attributes when the branch is on (trainer.py:146)
+            setattr(self, name, plan["out"][i])
+
     def _gen_fwd_bwd(self, x_a, x_b, hyperparameters, zs):
+        import ctypes as C
         hp = hyperparameters
+        L = N.lib()
+        plan = self._loss_plan("gen", hp, x_a.shape)
+        acc = plan["acc"]
+        E.zero_(acc)
         self.gen_arena.zero_()
         if self.eng.pool is not None:
             self.eng.pool.begin()
         for d in (self.dis_A, self.dis_B, self.dis_2):
             d.train_weights = False                       # their weight grads are discarded (trainer.py:248)
         tape = E.Tape()
-        n = x_a.size(0)
+        n, _, h, w = x_a.shape
         xa, xb = E.ImgT(x_a.detach().float()), E.ImgT(x_b.detach().float())
         focus = hp["focus_loss"] > 0
         r = self._cycle(tape, xa, xb, zs, need_recon=True)
 
         gw, gcw = hp["gan_w"], hp["gan_cw"]
+        S = self.GEN_SLOTS
         self._wait_dis_in_graph()           # the discriminators' weights come from the (possibly still running) dis_update
         cat_a = self._cat(tape, [r["x_A_fake"], r["x_A2_fake"]])
         cat_2a, cat_2b = self._cat(tape, [xa, xa]), self._cat(tape, [r["x_A_fake"], r["x_A2_fake"]])
-        out_a, out_b, out_2 = self._dis_all(tape, [(self.dis_A, cat_a, None), (self.dis_B, r["x_B_fake"], None),
-                                                   (self.dis_2, cat_2a, cat_2b)])
-        la = self._lsgan_multi(out_a, n, [1.0, 1.0], [0.5 * gw, 0.5 * gw])
-        self.loss_gen_adv_A = (la[0] + la[1]) * 0.5
-        self.loss_gen_adv_B = self._lsgan(out_b, 1.0, gw)
-        l2 = self._lsgan_multi(out_2, n, [1.0, 0.0], [gcw, gcw])
-        self.loss_gen_adv_2 = l2[0] + l2[1]
-        total = gw * self.loss_gen_adv_A + gw * self.loss_gen_adv_B + gcw * self.loss_gen_adv_2
+        # LSGAN terms (networks.py:77-106) and d loss / d logits inside the head kernels: calc_gen_loss targets 1; calc_gen_d2_loss
+        # targets (1, 0); loss_gen_adv_A is the 1/2-weighted sum of two calls (trainer.py:136-137)
+        self._dis_all(tape, [
+            (self.dis_A, cat_a, None, dict(acc=acc, targets=[1.0, 1.0], weights=[0.5 * gw, 0.5 * gw], slots=[S["advA1"], S["advA2"]])),
+            (self.dis_B, r["x_B_fake"], None, dict(acc=acc, targets=[1.0], weights=[gw], slots=[S["advB"]])),
+            (self.dis_2, cat_2a, cat_2b, dict(acc=acc, targets=[1.0, 0.0], weights=[gcw, gcw], slots=[S["adv2a"], S["adv2b"]]))])
 
         if focus:
-            # trainer.py:146-161 (sums over the WHOLE batch; normalised by H*W*B*3)
-            delta, up, lo, eps = hp["focus_delta"], hp["focus_upper"], hp["focus_lower"], hp["focus_epsilon"]
-            norm = float(x_a.size(2) * x_a.size(3) * x_a.size(0) * 3)
-            acc = 0
-            for tag, out in (("B", r["o_b"]), ("A", r["o_a"]), ("A2", r["o_a2"])):
-                m = (out.t[:, 3:4] + 1) / 2
-                s1 = torch.relu(torch.sum(m - up))
-                s2 = torch.relu(torch.sum(lo - m))
-                size = s1 ** 2 * delta + s2 ** 2 * delta
-                dev = m - 0.5
-                den = torch.abs(dev) + eps
-                digit = torch.sum(1 / den)
-                setattr(self, "loss_gen_focus_%s_size" % tag, size)
-                setattr(self, "loss_gen_focus_%s_digit" % tag, digit)
-                acc = acc + size + digit
-                dm = (2 * delta) * (s1 - s2) - torch.sign(dev) / (den * den)       # d(size + digit) / dm
-                do = torch.zeros_like(out.t)
-                do[:, 3:4] = dm * (0.5 * hp["focus_loss"] / norm)
-                out.add_grad(do)
-            total = total + hp["focus_loss"] * acc / x_a.size(2) / x_a.size(3) / x_a.size(0) / 3
+            # trainer.py:146-161 (sums over the WHOLE batch; normalised by H*W*B*3): pass 1 reduces sum(m - upper),
+            # sum(lower - m), sum 1/(|m - .5| + eps); pass 2 forms the size loss and writes d(size + digit)/d mask into channel 3
+            gscale = 0.5 * float(hp["focus_loss"]) / float(h * w * n * 3)
+            for t, out in enumerate((r["o_b"], r["o_a"], r["o_a2"])):
+                o4 = out.t
+                a = N.LossReduceArgs()
+                a.mode, a.n, a.ca, a.c, a.h, a.w = N.LOSS_FOCUS, n, 4, 1, h, w
+                a.a, a.acc, a.slot = o4.data_ptr(), acc.data_ptr(), 5 + 4 * t
+                a.upper, a.lower, a.eps = hp["focus_upper"], hp["focus_lower"], hp["focus_epsilon"]
+                N.check(L.aclgan_loss_reduce(C.byref(a), E._sp()), "loss_reduce(focus)")
+                g = N.FocusGradArgs()
+                g.out4, g.dout4 = o4.data_ptr(), out.zero_grad_buffer().data_ptr()
+                g.n, g.h, g.w, g.slot, g.size_slot, g.acc = n, h, w, 5 + 4 * t, 5 + 4 * t + 3, 1
+                g.sums, g.delta, g.eps, g.gscale = acc.data_ptr(), hp["focus_delta"], hp["focus_epsilon"], gscale
+                N.check(L.aclgan_focus_grad(C.byref(g), E._sp()), "focus_grad")
 
-        rec_a, rec_b = self._rgb(tape, r["o_rec_a"]), self._rgb(tape, r["o_rec_b"])
-        da, db = rec_a.t - xa.t, rec_b.t - xb.t
-        self.loss_idt_A = torch.mean(torch.abs(da))
-        self.loss_idt_B = torch.mean(torch.abs(db))
-        rw = hp["recon_x_w"]
-        rec_a.add_grad(torch.sign(da) * (rw / da.numel()))
-        rec_b.add_grad(torch.sign(db) * (rw / db.numel()))
-        self.loss_gen_total = total + rw * self.loss_idt_A + rw * self.loss_idt_B
+        # identity L1 (trainer.py:61-62,162-165) on the first three channels of the reconstructions
+        rw = float(hp["recon_x_w"])
+        for rec, ref, slot in ((r["o_rec_a"], xa, S["idtA"]), (r["o_rec_b"], xb, S["idtB"])):
+            ca = rec.t.shape[1]
+            a = N.LossReduceArgs()
+            a.mode, a.n, a.ca, a.c, a.h, a.w = N.LOSS_L1, n, ca, 3, h, w
+            a.a, a.b, a.acc, a.slot = rec.t.data_ptr(), ref.t.data_ptr(), acc.data_ptr(), slot
+            a.da, a.acc_da, a.gscale = rec.zero_grad_buffer().data_ptr(), 1, rw / float(n * 3 * h * w)
+            N.check(L.aclgan_loss_reduce(C.byref(a), E._sp()), "loss_reduce(l1)")
+        self._loss_finish(plan)
 
         tape.backward(self._side_streams)
         for d in (self.dis_A, self.dis_B, self.dis_2):
@@ -537,20 +574,21 @@ class aclgan_Trainer(nn.Module):
 
     def _dis_fwd_bwd(self, x_a, x_b, hyperparameters, zs):
         hp = hyperparameters
+        plan = self._loss_plan("dis", hp, x_a.shape)
+        acc = plan["acc"]
+        E.zero_(acc)
         self.dis_arena.zero_()
         if self.eng.pool is not None:
             self.eng.pool.begin()
-        n = x_a.size(0)
         xa, xb = E.ImgT(x_a.detach().float()), E.ImgT(x_b.detach().float())
         gw, gcw = hp["gan_w"], hp["gan_cw"]
         early_stream = None
-        losses = {}
 
         def dis_b_pass(fake_b):
+            # calc_dis_loss(fake, real) = LSGAN(fake, 0) + LSGAN(real, 1)  (networks.py:60-75)
             tb = E.Tape()
-            (out_b,) = self._dis_all(tb, [(self.dis_B, self._cat(tb, [fake_b, xb]), None)])
-            lb = self._lsgan_multi(out_b, n, [0.0, 1.0], [gw, gw])
-            losses["B"] = lb[0] + lb[1]
+            self._dis_all(tb, [(self.dis_B, self._cat(tb, [fake_b, xb]), None,
+                                dict(acc=acc, targets=[0.0, 1.0], weights=[gw, gw], slots=[3, 4]))])
             tb.backward(self._side_streams)
 
         def early(x_B_fake):
@@ -578,13 +616,10 @@ class aclgan_Trainer(nn.Module):
         # weight 1/2 in the reference (trainer.py:283-284) == once with weight 1
         cat_a = self._cat(tape, [xa, fake_a, fake_a2])
         cat_2a, cat_2b = self._cat(tape, [xa, xa]), self._cat(tape, [fake_a, fake_a2])
-        out_a, out_2 = self._dis_all(tape, [(self.dis_A, cat_a, None), (self.dis_2, cat_2a, cat_2b)])
-        la = self._lsgan_multi(out_a, n, [1.0, 0.0, 0.0], [gw, 0.5 * gw, 0.5 * gw])
-        losses["A"] = (la[1] + la[2] + 2.0 * la[0]) * 0.5
-        l2 = self._lsgan_multi(out_2, n, [0.0, 1.0], [gcw, gcw])
-        losses["2"] = l2[0] + l2[1]
-        self.loss_dis_A, self.loss_dis_B, self.loss_dis_2 = losses["A"], losses["B"], losses["2"]
-        self.loss_dis_total = gw * losses["A"] + gw * losses["B"] + gcw * losses["2"]
+        self._dis_all(tape, [
+            (self.dis_A, cat_a, None, dict(acc=acc, targets=[1.0, 0.0, 0.0], weights=[gw, 0.5 * gw, 0.5 * gw], slots=[0, 1, 2])),
+            (self.dis_2, cat_2a, cat_2b, dict(acc=acc, targets=[0.0, 1.0], weights=[gcw, gcw], slots=[5, 6]))])
+        self._loss_finish(plan)
         tape.backward(self._side_streams)
 
     @property

@@ -94,7 +94,7 @@ typedef struct aclgan_igemm_plan {
     int32_t seg_dx[16], seg_dy[16]; /* box offset of segment s relative to the tile origin (like tap_dx / tap_dy) */
     int32_t tap_row[ACLGAN_MAX_TAPS]; /* first segment row of tap t */
     aclgan_tmap_spec a_seg[2];        /* [plane] the variant-0 map with a seg_rows-pixel box */
-    /* fold mode (forward of the few-output-channel final conv, EXPERIMENTAL, env ACLGAN_FOLD=1): the k taps of a filter row
+    /* fold mode (forward of the few-output-channel final conv; default, env ACLGAN_FOLD=0 disables): the k taps of a filter row
      * are folded into the N dimension (weight row n = kw*8 + co, one tap per filter ROW), tiles are 128 flattened positions
      * stepping by tile_step = 128 - 8, and the epilogue sums the diagonal out[q][co] = sum_kw P[q + kw][kw*8 + co]. */
     int32_t fold;        /* 0, or the filter width k */
@@ -456,6 +456,10 @@ int aclgan_focus_grad(const aclgan_focus_grad_args* a, void* stream);
 int aclgan_loss_combine(uint64_t acc /* double[K] */, uint64_t M /* fp32 [J][K] */, uint64_t out /* fp32 [J] */, int32_t J,
                         int32_t K, void* stream);
 
+/* dst[ch] += sum_n sums[n][ch][0] for ch < c_valid: conv-bias gradient of a no-norm block from the T1 sums of
+ * aclgan_block_bwd_reduce (planes too small for the fused-bias apply kernel) */
+int aclgan_stats_to_bias(uint64_t sums /* double [n][c][2] */, uint64_t dst /* fp32 [c_valid] */, int32_t n, int32_t c,
+                         int32_t c_valid, void* stream);
 /* dst = alpha * a + beta * b (b may be 0; dst may alias a or b); kind 0 bf16, 1 fp32: gradient accumulation / alpha * z_2 */
 int aclgan_axpby(uint64_t dst, uint64_t a, uint64_t b, float alpha, float beta, int64_t n, int32_t kind, void* stream);
 /* cudaMemsetAsync(0) / device-to-device cudaMemcpyAsync on the caller's stream (memset / memcpy nodes under graph capture) */

@@ -160,17 +160,22 @@ def test_two_iterations_update_parity(golden_dir, case, point):
             nrm = float(d64.norm())
             assert nrm > 0, key
             assert abs(float(dp[key].abs().sum()) / (lr * d64.numel()) - float(d64.abs().sum()) / (lr * d64.numel())) < 5e-2, key
-            e_new = float((dp[key] - d64).norm()) / nrm
-            e_ref = float((dp32[key] - d64).norm()) / nrm
-            sg = float((torch.sign(dp[key]) == torch.sign(d64)).double().mean())
-            sg_ref = float((torch.sign(dp32[key]) == torch.sign(d64)).double().mean())
+            # Adam's first steps move every element by ~lr * sign(g): ONE element whose (gradient + weight decay) sits within
+            # rounding distance of zero flips between any two implementations and alone costs 2 / sqrt(numel) of relative L2
+            # (2.6e-2 on the 6144-element dis_2 first conv).  So: sign agreement >= 99.9 % (or <= 1 element on small
+            # tensors), and <= 1e-2 relative error over the sign-agreeing elements - each with the oracle's own fp32-vs-fp64
+            # disagreement on that tensor as allowance (generators: ReLU-flip noise, tests/test_gpu_step.py docstring).
+            same = torch.sign(dp[key]) == torch.sign(d64)
+            same_ref = torch.sign(dp32[key]) == torch.sign(d64)
+            sg, sg_ref = float(same.double().mean()), float(same_ref.double().mean())
+            e_new = float(((dp[key] - d64) * same).norm()) / nrm
+            e_ref = float(((dp32[key] - d64) * same_ref).norm()) / nrm
             errs.append((e_new, e_ref, key))
             agree.append((sg, sg_ref, key))
-            # update parity: <= 1e-2 rel and >= 99.9 % sign agreement, or within 2x of what the reference's own fp32 run
-            # manages against fp64 on this tensor (ReLU-flip noise, tests/test_gpu_step.py docstring)
-            assert e_new <= max(1e-2, 2 * e_ref) + 1e-12 if kind == "dis" else e_new <= max(3e-2, 3 * e_ref), (
-                "iteration %d %s" % (i // 2 + 1, kind), key, e_new, e_ref)
-            assert sg >= min(0.999, 1 - 2 * (1 - sg_ref)) - (0 if kind == "dis" else 5e-3), (kind, key, sg, sg_ref)
+            n_bad, n_bad_ref = int((~same).sum()), int((~same_ref).sum())
+            assert e_new <= max(1e-2, 2 * e_ref) + 1e-12, ("iteration %d %s" % (i // 2 + 1, kind), key, e_new, e_ref)
+            allow_bad = max(1, int(1e-3 * d64.numel()), 2 * n_bad_ref) if kind == "dis" else max(2, int(5e-3 * d64.numel()), 3 * n_bad_ref)
+            assert n_bad <= allow_bad, ("iteration %d %s" % (i // 2 + 1, kind), key, "sign flips", n_bad, n_bad_ref, d64.numel())
         errs.sort()
         agree.sort()
         print("\n[2-iteration update parity %s, iteration %d %s] %d tensors: dp rel err median %.2e max %.2e (oracle fp32 vs fp64 on "

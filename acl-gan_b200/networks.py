@@ -387,6 +387,7 @@ class AdaINGen(_EngineNet):
                 ds = style.grad.contiguous()
                 style.grad = None
                 g = torch.empty((x.n, x.h, x.w, x.c), dtype=eng.prec.dtype, device=eng.device)
+                a.pooled = pooled.data_ptr()        # (the closure keeps the forward's pooled activations alive)
                 a.dstyle, a.gr, a.g_kind = ds.data_ptr(), g.data_ptr(), eng.prec.kind
                 if tw:
                     a.dweight, a.dbias = self._grad_of(head.weight).data_ptr(), self._grad_of(head.bias).data_ptr()

@@ -145,6 +145,7 @@ def test_two_iterations_update_parity(golden_dir, case, point):
             mine.append((kind, ls, dp))
     skip = _cancelled(tr)
     lr = cfg["lr"]
+    fails = []
     for i, (kind, ls, dp) in enumerate(mine):
         _, ls64, dp64 = runs[torch.float64][i]
         _, ls32, dp32 = runs[torch.float32][i]
@@ -173,15 +174,21 @@ def test_two_iterations_update_parity(golden_dir, case, point):
             errs.append((e_new, e_ref, key))
             agree.append((sg, sg_ref, key))
             n_bad, n_bad_ref = int((~same).sum()), int((~same_ref).sum())
-            assert e_new <= max(1e-2, 2 * e_ref) + 1e-12, ("iteration %d %s" % (i // 2 + 1, kind), key, e_new, e_ref)
-            allow_bad = max(1, int(1e-3 * d64.numel()), 2 * n_bad_ref) if kind == "dis" else max(2, int(5e-3 * d64.numel()), 3 * n_bad_ref)
-            assert n_bad <= allow_bad, ("iteration %d %s" % (i // 2 + 1, kind), key, "sign flips", n_bad, n_bad_ref, d64.numel())
+            # discriminators: 1e-2 / 99.9 %.  Generators: their gradients carry 1e-3 .. 3e-2 of ReLU-flip noise per tensor
+            # (test_gradients_vs_live_oracle), which Adam's sign-like first steps turn into the same fraction of perturbed
+            # update elements: 3e-2 / 99 %
+            tol_e, tol_f = (1e-2, 1e-3) if kind == "dis" else (3e-2, 1e-2)
+            if not e_new <= max(tol_e, 2 * e_ref) + 1e-12:
+                fails.append(("iteration %d %s" % (i // 2 + 1, kind), key, "dp rel err", e_new, e_ref))
+            if not n_bad <= max(2, int(tol_f * d64.numel()), 3 * n_bad_ref):
+                fails.append(("iteration %d %s" % (i // 2 + 1, kind), key, "sign flips", n_bad, n_bad_ref, d64.numel()))
         errs.sort()
         agree.sort()
         print("\n[2-iteration update parity %s, iteration %d %s] %d tensors: dp rel err median %.2e max %.2e (oracle fp32 vs fp64 on "
               "that tensor: %.2e) ; sign agreement min %.5f (oracle fp32: %.5f) ; losses %s" % (
                   case, i // 2 + 1, kind, len(errs), errs[len(errs) // 2][0], errs[-1][0], errs[-1][1], agree[0][0], agree[0][1],
                   " ".join("%s=%.6g" % kv for kv in ls.items() if "total" in kv[0])))
+    assert not fails, fails[:10]
     assert float(tr._adam_gen["hyper"][6]) == 2.0 and float(tr._adam_dis["hyper"][6]) == 2.0
 
 
@@ -215,15 +222,22 @@ def test_step_save_resume_step_same_object(golden_dir, precision, tmp_path):
     iteration(trb, cfg, 2)                         # diverge, then roll back
     assert trb.resume(str(tmp_path), cfg) == 1
     iteration(trb, cfg, 1)
-    worst = 0.0
+    # identical kernels on identical state: only the order of fp32 atomics differs - which can flip a ReLU unit or the sign of a
+    # near-zero gradient element, and Adam turns one such element into a 2 lr difference.  So the comparison is statistical:
+    # a stale step counter (bias correction 0.5 vs 0.75), reset moments or stale packed weights would move EVERY element by
+    # >= 0.3 lr; here almost none may differ
+    tot, big, sabs = 0, 0, 0.0
     for n in ("gen_AB", "gen_BA", "dis_A", "dis_B", "dis_2"):
         for (k, a), (_, b2) in zip(getattr(tra, n).named_parameters(), getattr(trb, n).named_parameters()):
-            worst = max(worst, float((a - b2).abs().max()) / cfg["lr"])
-    # identical kernels on identical state: only the order of fp32 atomics differs (and can flip a ReLU unit)
-    assert worst < 0.5, worst
+            d = ((a - b2).abs() / cfg["lr"]).double()
+            tot += d.numel()
+            big += int((d > 0.1).sum())
+            sabs += float(d.sum())
+    worst = big / tot
+    assert worst < 5e-3 and sabs / tot < 2e-2, (worst, sabs / tot)
     for opt_a, opt_b in ((tra.gen_opt, trb.gen_opt), (tra.dis_opt, trb.dis_opt)):
         for pa, pb in zip(opt_a.param_groups[0]["params"], opt_b.param_groups[0]["params"]):
             ma, mb = opt_a.state[pa]["exp_avg"], opt_b.state[pb]["exp_avg"]
             assert float((ma - mb).norm()) <= 5e-2 * float(ma.norm()) + 1e-12
     assert float(trb._adam_gen["hyper"][6]) == 2.0 and float(trb._adam_dis["hyper"][6]) == 2.0
-    print("\n[step-save-resume-step] max |p_A - p_B| / lr = %.3e" % worst)
+    print("\n[step-save-resume-step] elements with |p_A - p_B| > 0.1 lr: %.2e of %d ; mean |p_A - p_B| / lr = %.2e" % (worst, tot, sabs / tot))

@@ -128,6 +128,42 @@ __global__ void pack_img_kernel(aclgan_pack_img_args a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ generic NCHW <-> plane
+// fp32 NCHW tensor (any channel count) -> reflect-padded NHWC plane(s); stored channels beyond c are zero.
+// One thread per (padded pixel, 8-channel group).  Used by the inference API (AdaINGen.decode takes the content code as an
+// NCHW tensor: reference networks.py:147-152, test.py:96-106).
+__global__ void pack_nchw_kernel(const float* __restrict__ src, int c, int n, int h, int w, aclgan_act dst) {
+    const int p = dst.pad, hp = h + 2 * p, wp = w + 2 * p, cg = dst.c / 8;
+    const int64_t total = (int64_t)n * hp * wp * cg;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int g = (int)(t % cg);
+    const int64_t pix = t / cg;
+    const int X = (int)(pix % wp), Y = (int)((pix / wp) % hp), ni = (int)(pix / ((int64_t)wp * hp));
+    const int y = reflect_idx(Y - p, h), x = reflect_idx(X - p, w);
+    F8 v = f8_zero();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ch = g * 8 + j;
+        if (ch < c) v.v[j] = __ldg(src + (((int64_t)ni * c + ch) * h + y) * w + x);
+    }
+    store8_planes(dst.data, dst.planes, pix * dst.c + g * 8, v);
+}
+
+// plane(s) -> fp32 NCHW [n][c][h][w] (interior, first c channels, hi + lo): thread per (n, c, y, x), x fastest
+__global__ void unpack_plane_kernel(aclgan_act src, int c, float* __restrict__ dst) {
+    const int64_t total = (int64_t)src.n * c * src.h * src.w;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int x = (int)(t % src.w), y = (int)((t / src.w) % src.h);
+    const int ch = (int)((t / ((int64_t)src.w * src.h)) % c), ni = (int)(t / ((int64_t)src.w * src.h * c));
+    const int p = src.pad, wp = src.w + 2 * p, hp = src.h + 2 * p;
+    const int64_t i = (((int64_t)ni * hp + y + p) * wp + x + p) * src.c + ch;
+    float v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src.data[0])[i]);
+    if (src.planes == 2) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src.data[1])[i]);
+    dst[t] = v;
+}
+
 // ------------------------------------------------------------------------------------------ norm_stats
 // CTA = 256 threads = (C/8 channel groups) x (pixel lanes); fp32 partials per thread, CTA reduce, fp64 atomics
 constexpr int kStatThreads = 256;
@@ -939,6 +975,21 @@ extern "C" int aclgan_pack_img(const aclgan_pack_img_args* a, void* stream) {
     if (a->c0 + a->c1 > a->dst.c) return ACLGAN_ERR_SHAPE;
     const int64_t total = (int64_t)a->n * (a->h + 2 * a->dst.pad) * (a->w + 2 * a->dst.pad);
     pack_img_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*a);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int aclgan_pack_nchw(uint64_t src, int32_t c, const aclgan_act* dst, void* stream) {
+    if (dst->c % 8 != 0 || c < 1 || c > dst->c || dst->h <= dst->pad || dst->w <= dst->pad) return ACLGAN_ERR_SHAPE;
+    const int64_t total = (int64_t)dst->n * (dst->h + 2 * dst->pad) * (dst->w + 2 * dst->pad) * (dst->c / 8);
+    pack_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(src), c, dst->n, dst->h,
+                                                                           dst->w, *dst);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int aclgan_unpack_plane(const aclgan_act* src, int32_t c, uint64_t dst, void* stream) {
+    if (c < 1 || c > src->c) return ACLGAN_ERR_SHAPE;
+    const int64_t total = (int64_t)src->n * c * src->h * src->w;
+    unpack_plane_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*src, c, reinterpret_cast<float*>(dst));
     return (int)cudaGetLastError();
 }
 

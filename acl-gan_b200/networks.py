@@ -13,6 +13,7 @@ Two call levels:
     backward pass on an `engine.Tape`.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn.functional as F
@@ -219,7 +220,47 @@ class _EngineNet(nn.Module):
         self._bound = False
         self._own_arena = False
         self.train_weights = True
+        self._igraphs = {}
+        self.infer_graphs = os.environ.get("ACLGAN_INFER_GRAPHS", "1") != "0"
         self.register_load_state_dict_post_hook(lambda module, keys: module.mark_dirty())
+
+    def _repack_dirty(self):
+        for l in self.conv_layers():
+            if l.dirty:
+                l.repack()
+
+    def _graphed(self, key, fn, inputs, owners=None):
+        """forward-only inference as a cached CUDA graph (reference: the eager encode / decode / sample calls of test.py:96-106
+        and trainer.py:179-245, a few hundred launches each at batch 1): static input buffers -> static outputs, cloned for
+        the caller.  Weights are read through the packed buffers the optimizer kernel rewrites in place, so a captured
+        graph stays valid across training steps; masters replaced by load_state_dict are repacked before the replay."""
+        for net in (owners or (self,)):
+            net._ensure_bound()
+            net._repack_dirty()
+        if not self.infer_graphs or not torch.cuda.is_available():
+            return fn(*inputs)
+        ent = self._igraphs.get(key)
+        if ent is None:
+            static_in = [torch.empty_like(t) for t in inputs]
+            for st, t in zip(static_in, inputs):
+                st.copy_(t)
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):           # warm-up off the capture stream (lazy kernel / attribute initialisation)
+                fn(*static_in)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = fn(*static_in)
+            ent = (graph, static_in, outs)
+            self._igraphs[key] = ent
+        graph, static_in, outs = ent
+        for st, t in zip(static_in, inputs):
+            st.copy_(t, non_blocking=True)
+        graph.replay()
+        return tuple(o.clone() for o in outs)
 
     def bind(self, eng, arena=None):
         self._eng = eng
@@ -487,31 +528,40 @@ class AdaINGen(_EngineNet):
 
     # ---- reference-compatible tensor API (forward values only) ---------------------------------------
     def _content_from_tensor(self, content):
+        """NCHW fp32 content code -> reflect-padded plane feeding the decoder's first 3x3 conv (pack kernel)"""
         eng = self._eng
         n, c, h, w = content.shape
         a = E.ActT(eng, n, h, w, c, 1)
-        v = F.pad(content.float(), (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1)
-        full = torch.zeros((n, h + 2, w + 2, a.c), dtype=torch.float32, device=eng.device)
-        full[..., :c] = v
-        hi = full.bfloat16()
-        a.buf[0, :a.numel] = hi.reshape(-1)
-        if a.planes == 2:
-            a.buf[1, :a.numel] = (full - hi.float()).bfloat16().reshape(-1)
+        src = content.detach().float().contiguous()
+        st = a.struct()
+        N.check(N.lib().aclgan_pack_nchw(src.data_ptr(), c, C.byref(st), E._sp()), "pack_nchw")
         return a
 
-    def encode(self, images):
-        self._ensure_bound()
+    def _encode_impl(self, images):
         tape = E.Tape(enabled=False)
-        img = E.ImgT(images.detach().float())
+        img = E.ImgT(images)
         style = self.enc_style_fwd(tape, img)
         content = self.enc_content_fwd(tape, img)
-        return content.value_nchw(), style.t.view(style.t.shape[0], -1, 1, 1)
+        out = torch.empty((content.n, content.c_valid, content.h, content.w), dtype=torch.float32, device=images.device)
+        st = content.struct()
+        N.check(N.lib().aclgan_unpack_plane(C.byref(st), content.c_valid, out.data_ptr(), E._sp()), "unpack_plane")
+        return out, style.t
+
+    def _decode_impl(self, content, style):
+        tape = E.Tape(enabled=False)
+        return (self.dec_fwd(tape, self._content_from_tensor(content), E.ImgT(style)).t,)
+
+    def encode(self, images):
+        """networks.py:141-145 -> (content [N,C,H/4,W/4], style [N,style_dim,1,1])"""
+        x = images.detach().float().contiguous()
+        content, style = self._graphed(("encode", tuple(x.shape)), self._encode_impl, [x])
+        return content, style.view(style.shape[0], -1, 1, 1)
 
     def decode(self, content, style):
-        self._ensure_bound()
-        tape = E.Tape(enabled=False)
-        ap_style = E.ImgT(style.detach().float().reshape(style.shape[0], -1))
-        return self.dec_fwd(tape, self._content_from_tensor(content.detach()), ap_style).t
+        """networks.py:147-152 -> images [N,output_dim,H,W]"""
+        c = content.detach().float().contiguous()
+        st = style.detach().float().reshape(style.shape[0], -1).contiguous()
+        return self._graphed(("decode", tuple(c.shape)), self._decode_impl, [c, st])[0]
 
     def forward(self, images):
         content, style = self.encode(images)

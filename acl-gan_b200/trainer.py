@@ -713,52 +713,52 @@ class aclgan_Trainer(nn.Module):
         raise NotImplementedError("aclgan_Trainer.forward is dead code in the reference (crashes with the shipped "
                                   "4-channel decoder, SURVEY 2.1); use sample() / gen_*.encode / decode")
 
+    def _sample_one(self, a, z1, z2, z3):
+        """the per-image translations of trainer.py:190-226 on the engine (planes stay on the device between encode and decode)"""
+        focus = self.focus_lam > 0
+        tape = E.Tape(enabled=False)
+        AB, BA = self.gen_AB, self.gen_BA
+        xa = E.ImgT(a)
+        c_1, s_1 = BA.enc_content_fwd(tape, xa), BA.enc_style_fwd(tape, xa)
+        o = BA.dec_fwd(tape, c_1, E.ImgT(z1))
+        rec = BA.dec_fwd(tape, c_1, s_1)
+        ob = AB.dec_fwd(tape, AB.enc_content_fwd(tape, xa), E.ImgT(z2))
+        xb_img = self._blend(tape, ob, xa) if focus else ob
+        o2 = BA.dec_fwd(tape, BA.enc_content_fwd(tape, xb_img), E.ImgT(z3))
+        if focus:
+            return (self._blend(tape, o, xa).t, o.t, xb_img.t, ob.t, self._blend(tape, o2, xb_img).t, o2.t, rec.t)
+        return (o.t, xb_img.t, o2.t, rec.t)
+
+    def _recon_b(self, x_b):
+        tape = E.Tape(enabled=False)
+        AB = self.gen_AB
+        xb = E.ImgT(x_b)
+        return (AB.dec_fwd(tape, AB.enc_content_fwd(tape, xb), AB.enc_style_fwd(tape, xb)).t,)
+
     def sample(self, x_a, x_b):
-        """trainer.py:179-245: per-image translations with the fixed display noise"""
+        """trainer.py:179-245: per-image translations with the fixed display noise; every image replays ONE captured CUDA graph
+        of the batch-1 forward passes (5 encodes / decodes + the focus blends)"""
         self._setup()
         self._join_dis()
         self.eval()
         focus = self.focus_lam > 0
-        cols = {k: [] for k in ("x_A", "x_B", "x_A_fake", "x_B_fake", "x_A2_fake", "x_A_recon", "x_B_recon",
-                                "mask_A", "mask_B", "mask_A2", "mask_recon")}
-        with torch.no_grad():
-            for i in range(x_a.size(0)):
-                a, b = x_a[i].unsqueeze(0), x_b[i].unsqueeze(0)
-                cols["x_A"].append(a)
-                cols["x_B"].append(b)
-                c_1, s_1 = self.gen_BA.encode(a)
-                o = self.gen_BA.decode(c_1, self.z_1[i].unsqueeze(0))
-                rec = self.gen_BA.decode(c_1, s_1)
-                c_2, _ = self.gen_AB.encode(a)
-                ob = self.gen_AB.decode(c_2, self.z_2[i].unsqueeze(0))
-                if focus:
-                    cols["x_A_fake"].append(self.focus_translation(o[:, :3], a, o[:, 3:4]))
-                    cols["mask_A"].append(o[:, 3:4])
-                    cols["x_A_recon"].append(rec[:, :3])
-                    cols["mask_recon"].append(rec[:, 3:4])
-                    xb_img = self.focus_translation(ob[:, :3], a, ob[:, 3:4])
-                    cols["mask_B"].append(ob[:, 3:4])
-                else:
-                    cols["x_A_fake"].append(o)
-                    cols["x_A_recon"].append(rec)
-                    xb_img = ob
-                cols["x_B_fake"].append(xb_img)
-                c_3, _ = self.gen_BA.encode(xb_img)
-                o2 = self.gen_BA.decode(c_3, self.z_3[i].unsqueeze(0))
-                if focus:
-                    cols["x_A2_fake"].append(self.focus_translation(o2[:, :3], xb_img, o2[:, 3:4]))
-                    cols["mask_A2"].append(o2[:, 3:4])
-                else:
-                    cols["x_A2_fake"].append(o2)
-                    c_4, s_4 = self.gen_AB.encode(b)
-                    cols["x_B_recon"].append(self.gen_AB.decode(c_4, s_4))
-        cat = {k: torch.cat(v) for k, v in cols.items() if v}
+        nets = (self.gen_AB, self.gen_BA)
+        x_a, x_b = x_a.detach().float().contiguous(), x_b.detach().float().contiguous()
+        sd = self.style_dim
+        rows = []
+        for i in range(x_a.size(0)):
+            ins = [x_a[i:i + 1].contiguous()] + [z[i].reshape(1, sd).float().contiguous() for z in (self.z_1, self.z_2, self.z_3)]
+            rows.append(self.gen_AB._graphed(("sample", tuple(ins[0].shape), focus), self._sample_one, ins, owners=nets))
+        cols = [torch.cat(c) for c in zip(*rows)]
         self.train()
         if focus:
-            return (cat["x_A"], cat["x_A_fake"], cat["mask_A"], cat["x_B_fake"], cat["mask_B"], cat["x_A2_fake"],
-                    cat["mask_A2"], cat["x_A_recon"], cat["mask_recon"])
-        return (cat["x_A"], cat["x_A_fake"], cat["x_B_fake"], cat["x_A2_fake"], cat["x_A_recon"], cat["x_B"],
-                cat["x_B_recon"])
+            fa, oa, fb, ob, fa2, oa2, rec = cols
+            return (x_a, fa, oa[:, 3:4], fb, ob[:, 3:4], fa2, oa2[:, 3:4], rec[:, :3], rec[:, 3:4])
+        fa, fb, fa2, rec = cols
+        # the reference re-encodes the WHOLE x_b batch inside its per-image loop (trainer.py:225-226) and concatenates the
+        # copies: x_B_recon has display_size x batch rows
+        rb = self.gen_AB._graphed(("recon_b", tuple(x_b.shape)), self._recon_b, [x_b], owners=nets)[0]
+        return (x_a, fa, fb, fa2, rec, x_b, rb.repeat(x_a.size(0), 1, 1, 1))
 
     # ------------------------------------------------------------------------------------------ schedule / io
     def update_learning_rate(self):

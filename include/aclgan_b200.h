@@ -207,6 +207,12 @@ typedef struct aclgan_pack_img_args {
 } aclgan_pack_img_args;
 int aclgan_pack_img(const aclgan_pack_img_args* a, void* stream);
 
+/* generic layout conversion at the API boundary of the inference path (AdaINGen.encode returns / decode takes the content
+ * code as an NCHW fp32 tensor: reference networks.py:141-152, test.py:96-106): fp32 NCHW [n][c][h][w] -> reflect-padded NHWC
+ * plane(s) with dst->c >= c stored channels (zero beyond c), and back (interior, first c channels, hi + lo) */
+int aclgan_pack_nchw(uint64_t src, int32_t c, const aclgan_act* dst, void* stream);
+int aclgan_unpack_plane(const aclgan_act* src, int32_t c, uint64_t dst, void* stream);
+
 /* per-(n,c) sum and sum of squares of a raw conv output, accumulated in fp64 (first half of
  * nn.InstanceNorm2d / F.batch_norm / LayerNorm statistics: networks.py:333,499-501,525-529) */
 int aclgan_norm_stats(const aclgan_tensor4* y, uint64_t sums /* double [n][c][2], zeroed by the caller */, void* stream);

@@ -21,7 +21,8 @@ LAUNCHERS = ["aclgan_igemm_launch", "aclgan_wgrad_launch", "aclgan_pack_img", "a
              "aclgan_adam_step", "aclgan_adam_advance", "aclgan_zero", "aclgan_copy", "aclgan_axpby",
              "aclgan_avgpool3x3s2_fwd", "aclgan_avgpool3x3s2_bwd", "aclgan_style_head_fwd", "aclgan_style_head_bwd",
              "aclgan_mlp_fwd", "aclgan_mlp_bwd", "aclgan_dis_head_fwd", "aclgan_dis_head_bwd", "aclgan_focus_blend_fwd",
-             "aclgan_focus_blend_bwd", "aclgan_loss_reduce", "aclgan_focus_grad", "aclgan_loss_combine", "aclgan_stats_to_bias"]
+             "aclgan_focus_blend_bwd", "aclgan_loss_reduce", "aclgan_focus_grad", "aclgan_loss_combine", "aclgan_stats_to_bias", "aclgan_pack_nchw",
+             "aclgan_unpack_plane"]
 
 
 class _Stub:

@@ -121,7 +121,7 @@ class Conv2dBlock(nn.Module):
         self._layer = None
 
     def layer(self, eng, arena, window=N.WINDOW_NONE):
-        if self._layer is None or self._layer.eng is not eng:
+        if self._layer is None or self._layer.eng is not eng or self._layer.arena is not arena:
             self._layer = E.ConvLayer(eng, arena, self.conv.weight, self.conv.bias, self.spec["stride"],
                                       self.spec["pad"], window)
         return self._layer
@@ -263,14 +263,18 @@ class _EngineNet(nn.Module):
         return tuple(o.clone() for o in outs)
 
     def bind(self, eng, arena=None):
+        """(re)binds the network to an engine and a gradient arena: layers, gradient slices and cached inference graphs of a
+        previous binding (e.g. stand-alone encode / decode before the trainer's first update) are dropped"""
         self._eng = eng
         self._own_arena = arena is None
         self._arena = arena if arena is not None else E.GradArena(eng.device)
         self._bound = False
+        self._dense_grads = []
+        self._igraphs = {}
 
     def _ensure_bound(self):
         if self._eng is None:
-            self.bind(get_engine())
+            self.bind(get_engine(getattr(self, "precision_hint", None)))      # (the owning trainer's `precision` setting)
         if not self._bound:
             for p in self.parameters():
                 if p.device.type != "cuda":

@@ -59,6 +59,8 @@ class aclgan_Trainer(nn.Module):
             raise NotImplementedError("vgg_w > 0: the VGG perceptual loss is outside the B200 hot path")
         self.precision = hp.get("precision", os.environ.get("ACLGAN_PRECISION", "bf16"))
         self._hp = hp
+        for net in (self.gen_AB, self.gen_BA, self.dis_A, self.dis_B, self.dis_2):
+            net.precision_hint = self.precision         # stand-alone gen.encode / decode (test.py) run in the trainer's mode
         self.use_graphs = bool(int(hp.get("cuda_graphs", os.environ.get("ACLGAN_CUDA_GRAPHS", "1"))))
         self._graphs = {}
         self._launches = {}

@@ -29,7 +29,9 @@ class OutSpec(C.Structure):
     _fields_ = [("ptr", C.c_uint64 * 2), ("kind", C.c_int32), ("act", C.c_int32), ("slope", C.c_float),
                 ("mirror", C.c_int32), ("off", C.c_int64), ("sn", C.c_int64), ("sy", C.c_int64),
                 ("sx", C.c_int64), ("sc", C.c_int64), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("C", C.c_int32), ("bias", C.c_uint64), ("bias_n", C.c_int32), ("stats", C.c_uint64)]
+                ("C", C.c_int32), ("bias", C.c_uint64), ("bias_n", C.c_int32), ("stats", C.c_uint64),
+                ("d2s_c", C.c_int32), ("ring", C.c_int32), ("d2s_sy", C.c_int64), ("d2s_sx", C.c_int64),
+                ("z_mod", C.c_int32), ("stats_c", C.c_int32), ("z_off", C.c_int64)]
 
 
 class IgemmPlan(C.Structure):
@@ -95,7 +97,8 @@ class NormFinalizeArgs(C.Structure):
     _fields_ = [("mode", C.c_int32), ("n", C.c_int32), ("c", C.c_int32), ("hw", C.c_int32),
                 ("c_valid", C.c_int32), ("eps", C.c_float), ("sums", C.c_uint64), ("w", C.c_uint64),
                 ("b", C.c_uint64), ("scale", C.c_uint64), ("shift", C.c_uint64), ("mean", C.c_uint64),
-                ("inv", C.c_uint64), ("sigma", C.c_uint64), ("wb_stride", C.c_int64)]
+                ("inv", C.c_uint64), ("sigma", C.c_uint64), ("wb_stride", C.c_int64), ("stat_groups", C.c_int32),
+                ("pad_", C.c_int32)]
 
 
 class ApplyArgs(C.Structure):
@@ -117,7 +120,8 @@ class NormBwdFinalizeArgs(C.Structure):
                 ("c_valid", C.c_int32), ("sums", C.c_uint64), ("inv", C.c_uint64), ("sigma", C.c_uint64),
                 ("w", C.c_uint64), ("ca", C.c_uint64), ("cb", C.c_uint64), ("cc", C.c_uint64),
                 ("dw", C.c_uint64), ("db", C.c_uint64), ("wb_stride", C.c_int64),
-                ("fsums", C.c_uint64), ("mean", C.c_uint64), ("dbias", C.c_uint64)]
+                ("fsums", C.c_uint64), ("mean", C.c_uint64), ("dbias", C.c_uint64), ("fstat_groups", C.c_int32),
+                ("pad2_", C.c_int32)]
 
 
 class ImgGradPackArgs(C.Structure):
@@ -190,6 +194,29 @@ class FocusGradArgs(C.Structure):
     _fields_ = [("out4", C.c_uint64), ("dout4", C.c_uint64), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
                 ("slot", C.c_int32), ("size_slot", C.c_int32), ("acc", C.c_int32), ("sums", C.c_uint64),
                 ("delta", C.c_float), ("eps", C.c_float), ("gscale", C.c_float), ("pad_", C.c_int32)]
+
+
+class UpDeriveArgs(C.Structure):
+    _fields_ = [("w5", C.c_uint64), ("bias", C.c_uint64), ("co", C.c_int32), ("ci", C.c_int32), ("planes", C.c_int32),
+                ("pad_", C.c_int32), ("pk", (C.c_uint64 * 2) * 2), ("aff", (C.c_int64 * 5) * 2), ("bias4", C.c_uint64)]
+
+
+class UpStripsArgs(C.Structure):
+    _fields_ = [("src", Act), ("rows", Act), ("cols", Act)]
+
+
+class UpDyPackArgs(C.Structure):
+    _fields_ = [("dy", Act), ("cout", C.c_int32), ("pad_", C.c_int32), ("s2d", Act), ("rows", Act), ("cols", Act)]
+
+
+class UpScatterArgs(C.Structure):
+    _fields_ = [("g", C.c_uint64), ("grows", C.c_uint64), ("gcols", C.c_uint64), ("kind", C.c_int32), ("n", C.c_int32),
+                ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("pad_", C.c_int32)]
+
+
+class UpFoldWgradArgs(C.Structure):
+    _fields_ = [("dwp", C.c_uint64), ("affp", C.c_int64 * 5), ("dw5", C.c_uint64), ("aff5", C.c_int64 * 5),
+                ("co", C.c_int32), ("ci", C.c_int32)]
 
 
 class NativeError(RuntimeError):
@@ -290,6 +317,11 @@ def _declare(L):
     L.aclgan_focus_grad.argtypes = [C.POINTER(FocusGradArgs), C.c_void_p]
     L.aclgan_loss_combine.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]
     L.aclgan_axpby.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_int64, C.c_int32, C.c_void_p]
+    L.aclgan_up_derive_weights.argtypes = [C.POINTER(UpDeriveArgs), C.c_void_p]
+    L.aclgan_up_gather_strips.argtypes = [C.POINTER(UpStripsArgs), C.c_void_p]
+    L.aclgan_up_dy_pack.argtypes = [C.POINTER(UpDyPackArgs), C.c_void_p]
+    L.aclgan_up_scatter_strips.argtypes = [C.POINTER(UpScatterArgs), C.c_void_p]
+    L.aclgan_up_fold_wgrad.argtypes = [C.POINTER(UpFoldWgradArgs), C.c_void_p]
     L.aclgan_pack_nchw.argtypes = [C.c_uint64, C.c_int32, C.POINTER(Act), C.c_void_p]
     L.aclgan_unpack_plane.argtypes = [C.POINTER(Act), C.c_int32, C.c_uint64, C.c_void_p]
     L.aclgan_stats_to_bias.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]

@@ -230,7 +230,13 @@ __global__ void norm_finalize_kernel(aclgan_norm_finalize_args a) {
     float* inv = reinterpret_cast<float*>(a.inv) + (int64_t)n * a.c;
     if (a.mode == ACLGAN_NORM_LN) {
         double s1 = 0.0, s2 = 0.0;
-        for (int c = threadIdx.x; c < c_valid; c += blockDim.x) { s1 += sums[2 * c]; s2 += sums[2 * c + 1]; }
+        if (a.stat_groups > 1) {        // phase groups of the sub-pixel up-convolution: [n][groups * c_valid][2]
+            const int tot = a.stat_groups * c_valid;
+            const double* sg = reinterpret_cast<const double*>(a.sums) + (int64_t)n * tot * 2;
+            for (int c = threadIdx.x; c < tot; c += blockDim.x) { s1 += sg[2 * c]; s2 += sg[2 * c + 1]; }
+        } else {
+            for (int c = threadIdx.x; c < c_valid; c += blockDim.x) { s1 += sums[2 * c]; s2 += sums[2 * c + 1]; }
+        }
         s1 = block_sum(s1, sh);
         s2 = block_sum(s2, sh);
         const double M = (double)c_valid * a.hw;
@@ -847,7 +853,14 @@ __global__ void norm_bwd_finalize_kernel(aclgan_norm_bwd_finalize_args a) {
             if (a.dbias != 0) {
                 // conv bias in front of LayerNorm: db[c] = sum over (n, hw) of dy = ca*T1 + cb*sum_hw(yhat) + cc*HW
                 const double mu = reinterpret_cast<const float*>(a.mean)[(int64_t)n * a.c + c];
-                const double s1f = reinterpret_cast<const double*>(a.fsums)[((int64_t)n * a.c + c) * 2];
+                double s1f;
+                if (a.fstat_groups > 1) {
+                    s1f = 0.0;
+                    for (int gph = 0; gph < a.fstat_groups; ++gph)
+                        s1f += reinterpret_cast<const double*>(a.fsums)[(((int64_t)n * a.fstat_groups + gph) * c_valid + c) * 2];
+                } else {
+                    s1f = reinterpret_cast<const double*>(a.fsums)[((int64_t)n * a.c + c) * 2];
+                }
                 const double syh = (s1f - (double)a.hw * mu) * r;
                 const double dbv = (double)ca[c] * sums[2 * c] + (double)cb[c] * syh + (double)cc[c] * (double)a.hw;
                 atomicAdd(reinterpret_cast<float*>(a.dbias) + c, (float)dbv);

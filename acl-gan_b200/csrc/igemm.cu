@@ -66,7 +66,16 @@ struct EpiArgs {
     int kind, act, mirror, N, C, bias_n, block_n;
     float slope;
     int direct;      // 1: registers -> global without shared-memory staging / shuffles (perf triage, env ACLGAN_EPI_DIRECT)
+    int d2s_c, z_mod, stats_c;      // depth-to-space / strip addressing of the sub-pixel up-convolution (aclgan_out_spec)
+    int64_t d2s_sy, d2s_sx;
 };
+
+// element offset of GEMM column `ch` relative to the pixel: plain channel stride, or depth-to-space (phase -> pixel offset)
+__device__ __forceinline__ int64_t chan_off(const EpiArgs& o, int ch) {
+    if (o.d2s_c == 0) return (int64_t)ch * o.sc;
+    const int ph = ch / o.d2s_c, c = ch - ph * o.d2s_c;
+    return (int64_t)(ph >> 1) * o.d2s_sy + (int64_t)(ph & 1) * o.d2s_sx + c;
+}
 
 __device__ __forceinline__ EpiArgs make_epi_args(const IgemmKParams& P) {
     EpiArgs e;
@@ -75,6 +84,8 @@ __device__ __forceinline__ EpiArgs make_epi_args(const IgemmKParams& P) {
     e.kind = P.out.kind; e.act = P.out.act; e.mirror = P.out.mirror; e.N = P.out.N; e.C = P.out.C;
     e.bias_n = P.out.bias_n; e.block_n = P.block_n; e.slope = P.out.slope;
     e.direct = P.epi_direct;
+    e.d2s_c = P.out.d2s_c; e.z_mod = P.out.z_mod; e.stats_c = P.out.stats_c > 0 ? P.out.stats_c : P.out.C;
+    e.d2s_sy = P.out.d2s_sy; e.d2s_sx = P.out.d2s_sx;
     return e;
 }
 
@@ -101,6 +112,16 @@ __device__ __forceinline__ int mirror_coords(int c, int L, int p, int (&out)[3])
     return n;
 }
 
+// sub-pixel up-convolution helpers (aclgan_out_spec.ring / z_mod): border-ring rows are left to the strip convolutions; a strip
+// launch holds the two sides of the ring as batch indices [0, z_mod) and [z_mod, 2 z_mod) of the same images
+__device__ __forceinline__ bool ring_pixel(const aclgan_out_spec& o, int x, int y) {
+    return o.ring != 0 && (x == 0 || y == 0 || x == o.W - 1 || y == o.H - 1);
+}
+__device__ __forceinline__ int64_t image_off(const aclgan_out_spec& o, int z) {
+    if (o.z_mod <= 0) return (int64_t)z * o.sn;
+    return (int64_t)(z % o.z_mod) * o.sn + (int64_t)(z / o.z_mod) * o.z_off;
+}
+
 // what one epilogue thread knows about its accumulator row (= output pixel)
 struct RowCtx {
     int x, y, z;
@@ -113,20 +134,22 @@ struct RowCtx {
 // ---- generic (cold) path: any output kind / stride / partial channel count; scalar, rolled loops (small code) ----
 __device__ __noinline__ void store_generic(const EpiArgs o, int64_t pix, int ch0, int cnt, const float* v) {
     if (o.kind == ACLGAN_OUT_BF16 || o.kind == ACLGAN_OUT_SPLIT) {
-        __nv_bfloat16* d0 = reinterpret_cast<__nv_bfloat16*>(o.ptr0) + pix + (int64_t)ch0 * o.sc;
-        __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(o.ptr1) + pix + (int64_t)ch0 * o.sc;
+        __nv_bfloat16* d0 = reinterpret_cast<__nv_bfloat16*>(o.ptr0) + pix;
+        __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(o.ptr1) + pix;
 #pragma unroll 1
         for (int i = 0; i < cnt; ++i) {
+            const int64_t co = chan_off(o, ch0 + i);
             const __nv_bfloat16 hi = __float2bfloat16_rn(v[i]);
-            d0[(int64_t)i * o.sc] = hi;
-            if (o.kind == ACLGAN_OUT_SPLIT) d1[(int64_t)i * o.sc] = __float2bfloat16_rn(v[i] - __bfloat162float(hi));
+            d0[co] = hi;
+            if (o.kind == ACLGAN_OUT_SPLIT) d1[co] = __float2bfloat16_rn(v[i] - __bfloat162float(hi));
         }
     } else {
-        float* d = reinterpret_cast<float*>(o.ptr0) + pix + (int64_t)ch0 * o.sc;
+        float* d = reinterpret_cast<float*>(o.ptr0) + pix;
 #pragma unroll 1
         for (int i = 0; i < cnt; ++i) {
-            if (o.kind == ACLGAN_OUT_F32_ATOMIC) atomicAdd(d + (int64_t)i * o.sc, v[i]);
-            else d[(int64_t)i * o.sc] = v[i];
+            const int64_t co = chan_off(o, ch0 + i);
+            if (o.kind == ACLGAN_OUT_F32_ATOMIC) atomicAdd(d + co, v[i]);
+            else d[co] = v[i];
         }
     }
 }
@@ -260,7 +283,7 @@ __device__ __forceinline__ void stats_tile_end(const EpiArgs& o, uint8_t* stage_
                         const float2 v = *reinterpret_cast<const float2*>(stage_out + w * 8192 + 4096 + set * 2048 + ch * 8);
                         s += v.x; qq += v.y;
                     }
-                    double* d = stats + ((int64_t)n * o.C + n0 + ch) * 2;
+                    double* d = stats + ((int64_t)(o.z_mod > 0 ? n % o.z_mod : n) * o.stats_c + n0 + ch) * 2;
                     atomicAdd(d, (double)s);
                     atomicAdd(d + 1, (double)qq);
                 }
@@ -272,7 +295,7 @@ __device__ __forceinline__ void stats_tile_end(const EpiArgs& o, uint8_t* stage_
         if (tile_ok && n_first < o.N) {
             const float* red = reinterpret_cast<const float*>(stage_out + q * 8192 + 4096);
             for (int ch = lane; ch < o.block_n; ch += 32) {
-                double* d = stats + ((int64_t)n_first * o.C + n0 + ch) * 2;
+                double* d = stats + ((int64_t)(o.z_mod > 0 ? n_first % o.z_mod : n_first) * o.stats_c + n0 + ch) * 2;
                 atomicAdd(d, (double)red[ch * 2]);
                 atomicAdd(d + 1, (double)red[ch * 2 + 1]);
             }
@@ -334,7 +357,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& o, int c, const ui
             for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * o.slope;
         }
         if (rc.valid) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(o.ptr0) + rc.pix0 + ch0);
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(o.ptr0) + rc.pix0 + chan_off(o, ch0));
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 uint4 qv;
@@ -406,7 +429,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& o, int c, const ui
     }
     if (f32 || (c & 32)) {      // a full 128-byte row segment is staged: 32 fp32 or 64 bf16 channels
         const int g0 = f32 ? ch0 : ch0 - 32;
-        const int64_t row_off = (rc.pix0 + g0) * esz;
+        const int64_t row_off = (rc.pix0 + chan_off(o, g0)) * esz;      // (fast path: sc == 1; a segment never straddles phases)
         if (st) {
             __syncwarp();
             stage_colsums(stg, reinterpret_cast<float*>(stg + 4096), g0 - n0, f32, lane, stat_rb);
@@ -623,15 +646,15 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                     rc.y = ty * P.box_y + (row / P.box_x) % P.box_y;
                     rc.z = tz * P.box_z + row / (P.box_x * P.box_y);
                 }
-                rc.valid = sub_ok && (rc.x < o.W) && (rc.y < o.H) && (rc.z < o.N) && P.debug != 3;
+                rc.valid = sub_ok && (rc.x < o.W) && (rc.y < o.H) && (rc.z < o.N) && P.debug != 3 && !ring_pixel(o, rc.x, rc.y);
                 if (P.debug == 4) continue;
-                rc.pix0 = o.off + P.group_off[grp] + (int64_t)rc.z * o.sn + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
+                rc.pix0 = o.off + P.group_off[grp] + image_off(o, rc.z) + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
                 rc.ny = mirror_coords(rc.y, o.H, o.mirror, rc.ys);
                 rc.nx = mirror_coords(rc.x, o.W, o.mirror, rc.xs);
                 const uint32_t t_row = tmem_base + acc * set_cols + sub * col_stride + ((uint32_t)(q * 32) << 16);
                 const int n0 = nt * P.block_n;
                 const int group = (o.kind == ACLGAN_OUT_F32) ? 32 : 64;
-                const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) &&
+                const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) && (o.d2s_c % group == 0) &&
                                   (n0 + P.block_n <= o.C) && (o.act != ACLGAN_ACT_TANH) && (P.debug != 5);
                 StatCtx sc;
                 if (o.stats != 0) sc = make_stat_ctx(P, tx, tz, q, lane, rc);
@@ -815,8 +838,8 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
                 rc.y = ty * P.box_y + (row / P.box_x) % P.box_y;
                 rc.z = tz * P.box_z + row / (P.box_x * P.box_y);
             }
-            rc.valid = sub_ok && (rc.x < o.W) && (rc.y < o.H) && (rc.z < o.N) && P.debug != 3;
-            rc.pix0 = o.off + P.group_off[grp] + (int64_t)rc.z * o.sn + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
+            rc.valid = sub_ok && (rc.x < o.W) && (rc.y < o.H) && (rc.z < o.N) && P.debug != 3 && !ring_pixel(o, rc.x, rc.y);
+            rc.pix0 = o.off + P.group_off[grp] + image_off(o, rc.z) + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
             rc.ny = mirror_coords(rc.y, o.H, o.mirror, rc.ys);
             rc.nx = mirror_coords(rc.x, o.W, o.mirror, rc.xs);
             mbar_wait(&tfull_bar[acc], acc_phase);
@@ -825,7 +848,7 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
                 const uint32_t t_row = tmem_base + acc * col_stride + ((uint32_t)(q * 32) << 16);
                 const int n0 = nt * P.block_n;
                 const int group = (o.kind == ACLGAN_OUT_F32) ? 32 : 64;
-                const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) &&
+                const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) && (o.d2s_c % group == 0) &&
                                   (n0 + P.block_n <= o.C);
                 StatCtx sc;
                 if (o.stats != 0) sc = make_stat_ctx(P, tx, tz, q, lane, rc);
@@ -1059,8 +1082,8 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
                 rc.y = ty * P.box_y + (row / P.box_x) % P.box_y;
                 rc.z = tz * P.box_z + row / (P.box_x * P.box_y);
             }
-            rc.valid = sub_ok && (rc.x < o.W) && (rc.y < o.H) && (rc.z < o.N);
-            rc.pix0 = o.off + (int64_t)rc.z * o.sn + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
+            rc.valid = sub_ok && (rc.x < o.W) && (rc.y < o.H) && (rc.z < o.N) && !ring_pixel(o, rc.x, rc.y);
+            rc.pix0 = o.off + image_off(o, rc.z) + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
             rc.ny = mirror_coords(rc.y, o.H, o.mirror, rc.ys);
             rc.nx = mirror_coords(rc.x, o.W, o.mirror, rc.xs);
             const long long tw = prof ? clock64() : 0;
@@ -1070,7 +1093,7 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
             const uint32_t t_row = tmem_base + acc * col_stride + ((uint32_t)(q * 32) << 16);
             const int n0 = nt * P.block_n;
             const int group = (o.kind == ACLGAN_OUT_F32) ? 32 : 64;
-            const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) && (n0 + P.block_n <= o.C) &&
+            const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) && (o.d2s_c % group == 0) && (n0 + P.block_n <= o.C) &&
                               (o.act != ACLGAN_ACT_TANH);
             StatCtx sc;
             if (o.stats != 0) sc = make_stat_ctx(P, tx, tz, q, lane, rc);
@@ -1116,6 +1139,7 @@ static bool stats_supported(const aclgan_igemm_plan* pl) {
     const int group = (o.kind == ACLGAN_OUT_F32) ? 32 : 64;
     if (o.kind != ACLGAN_OUT_BF16 && o.kind != ACLGAN_OUT_F32) return false;
     if (o.sc != 1 || pl->block_n < group || pl->block_n > 256 || o.C % pl->block_n != 0 || o.act == ACLGAN_ACT_TANH) return false;
+    if (o.d2s_c % group != 0) return false;             // depth-to-space phases narrower than a staged row segment: generic path
     if (pl->n_groups > 1) return false;
     if (pl->flat) return pl->flat_img >= 128;           // a 128-row tile then touches at most two images
     if (pl->box_z != 1 && (pl->box_x * pl->box_y) % 32 != 0) return false;

@@ -289,6 +289,7 @@ class ConvLayer:
         self.dw_numel = rows * kt
         self.db_off = arena.reserve(co)
         self.dirty = True
+        self.derived = []           # UpConvLayer views that re-derive their weights whenever the master changes
 
     # -- packed weights -------------------------------------------------------------------------------
     def repack(self):
@@ -305,6 +306,8 @@ class ConvLayer:
             a.planes = self.eng.prec.planes
             N.check(L.aclgan_pack_weight(C.byref(a), _sp()), "pack_weight")
         self.dirty = False
+        for d in self.derived:
+            d.derive()
 
     def wptr(self, tr):
         if self.dirty:
@@ -336,6 +339,84 @@ class ConvLayer:
         else:
             g = torch.as_strided(dw, (co, ci, kh, kw), (s_co, s_ci, s_kh, -s_kw), off + (kw - 1) * s_kw).flip(3)
         return g, self.db()
+
+
+class _LayerView:
+    """what conv_fwd_launch / conv_dgrad / conv_wgrad need from a layer, for derived weight sets"""
+
+    def __init__(self, desc, cin, cout, k, wptr, dw):
+        self.desc, self.cin, self.cout, self.k, self.stride = desc, cin, cout, k, 1
+        self.wptr, self.dw = wptr, dw
+
+
+class UpConvLayer:
+    """Sub-pixel form of an up-block convolution (nearest 2x upsample -> ReflectionPad2d(2) -> Conv2d 5x5, reference
+    networks.py:256-257): derived state around the 5x5 ConvLayer `base` - the phase weights of the 3x3 / 4*Cout main convolution
+    (both packings), the transposed-filter packings for the column strips, the tiled bias and the phase-weight gradient scratch
+    (csrc/upconv.cu; geometry: tools/subpixel_pipeline.py)."""
+
+    def __init__(self, eng, base):
+        assert base.k == 5 and base.stride == 1 and base.pad == 2 and base.cout % 8 == 0
+        self.eng, self.base = eng, base
+        co, ci = base.cout, base.cin
+        L = N.lib()
+        self.desc = N.ConvDesc(ci, 4 * co, 3, 1, 1, N.WINDOW_NONE)
+        self.packed, self.aff = {}, {}
+        for tr in (0, 1):
+            rows, kt = C.c_int64(), C.c_int64()
+            L.aclgan_packed_weight_shape(C.byref(self.desc), tr, C.byref(rows), C.byref(kt))
+            self.packed[tr] = zeros((eng.prec.planes, rows.value * kt.value), torch.bfloat16, eng.device)
+            self.aff[tr] = _affine_index(self.desc, tr, (4 * co, ci, 3, 3))
+            setattr(self, "shape%d" % tr, (rows.value, kt.value))
+        self.layout = L.aclgan_wgrad_layout(C.byref(self.desc))
+        rows, kt = getattr(self, "shape%d" % self.layout)
+        self.dwp = torch.empty(rows * kt, dtype=torch.float32, device=eng.device)
+        self.bias4 = torch.empty(4 * co, dtype=torch.float32, device=eng.device)
+        self.packedT = {tr: torch.zeros_like(base.packed[tr]) for tr in (0, 1)}
+        self.main = _LayerView(self.desc, ci, 4 * co, 3, self.wptr, lambda: self.dwp)
+        self.colview = _LayerView(base.desc, ci, co, 5, self.wptrT, base.dw)
+        base.derived.append(self)
+        if not base.dirty:
+            self.derive()
+
+    @staticmethod
+    def _ptrs(t):
+        return (C.c_uint64 * 2)(t[0].data_ptr(), t[1].data_ptr() if t.shape[0] > 1 else 0)
+
+    def wptr(self, tr):
+        if self.base.dirty:
+            self.base.repack()
+        return self._ptrs(self.packed[tr])
+
+    def wptrT(self, tr):
+        if self.base.dirty:
+            self.base.repack()
+        return self._ptrs(self.packedT[tr])
+
+    def derive(self):
+        """phase weights / tiled bias / transposed-filter packings from the fp32 master (after every optimizer step)"""
+        L = N.lib()
+        base = self.base
+        w = base.weight.detach()
+        planes = self.eng.prec.planes
+        a = N.UpDeriveArgs()
+        a.w5, a.bias, a.co, a.ci, a.planes = w.data_ptr(), base.bias.data_ptr(), base.cout, base.cin, planes
+        for tr in (0, 1):
+            for p in range(planes):
+                a.pk[tr][p] = self.packed[tr][p].data_ptr()
+            for j in range(5):
+                a.aff[tr][j] = self.aff[tr][j]
+        a.bias4 = self.bias4.data_ptr()
+        N.check(L.aclgan_up_derive_weights(C.byref(a), _sp()), "up_derive_weights")
+        co, ci, kh, kw = w.shape
+        for tr in (0, 1):       # W5^T: element (kh, kw) goes where the base packing puts (kw, kh)
+            b = N.PackWeightArgs()
+            b.w, b.co, b.ci, b.kh, b.kw = w.data_ptr(), co, ci, kh, kw
+            b.base, b.s_co, b.s_ci, b.s_kw, b.s_kh = base.aff[tr]
+            for p in range(planes):
+                b.dst[p] = self.packedT[tr][p].data_ptr()
+            b.planes = planes
+            N.check(L.aclgan_pack_weight(C.byref(b), _sp()), "pack_weight(T)")
 
 
 class Engine:
@@ -486,11 +567,18 @@ class Engine:
         N.check(N.lib().aclgan_igemm_launch(C.byref(plan), _sp()), "igemm_launch(dgrad)")
         return g
 
-    def conv_wgrad(self, layer, dy, x):
+    def conv_wgrad(self, layer, dy, x, transpose_taps=False):
         plan = N.WgradPlan()
         dys, xs = dy.struct(), x.struct()
         N.check(N.lib().aclgan_plan_conv_wgrad(C.byref(layer.desc), C.byref(dys), C.byref(xs),
                                                layer.dw().data_ptr(), C.byref(plan)), "plan_conv_wgrad")
+        if transpose_taps:
+            # the operands are TRANSPOSED strips convolved with the transposed filter: tap (kh, kw) of the plan is tap (kw, kh)
+            # of the stored weight gradient (box-per-tap plans only: the segment plans write consecutive tap slots)
+            k = layer.k
+            assert plan.seg_mode == 0 and plan.num_taps == k * k
+            for t in range(k * k):
+                plan.tap_out[t] = (t % k) * k + t // k
         N.check(N.lib().aclgan_wgrad_launch(C.byref(plan), _sp()), "wgrad_launch")
 
     def dy_pad(self, layer):
@@ -615,6 +703,143 @@ class Engine:
                 self.conv_wgrad(layer, dy, x)
             if need_x_grad:
                 x.add_gp(self.conv_dgrad(layer, dy, x))
+
+        tape.push(bwd)
+        return out
+
+    # ------------------------------------------------------------------------------------------ sub-pixel up block
+    def conv_block_up(self, tape, up, x, act=N.ACT_RELU, out_pad=0, ln=None, train_w=True):
+        """nearest 2x upsample -> reflect pad 2 -> conv 5x5 -> LayerNorm -> activation -> reflect pad of the consumer
+        (reference networks.py:256-257 + :520-536) with the up-sampled plane never materialised: `x` is the SOURCE plane
+        (reflect pad 1).  Main 3x3 / 4*Cout convolution + depth-to-space epilogue, exact 5x5 ring strips, LayerNorm
+        statistics fused into the three conv epilogues (csrc/upconv.cu header; tools/subpixel_pipeline.py)."""
+        L = N.lib()
+        base = up.base
+        assert x.pad == 1 and x.h >= 3 and x.w >= 3
+        n, H, W, cout = x.n, x.h, x.w, base.cout
+        cs = round_up(cout, 64)
+        row = 2 * W * cs                                     # elements per output row of y
+        y = self.new_dense(n, 2 * H, 2 * W, cs, zero=(cs != cout))
+        slope = 0.2
+
+        def spec(N_, H_, W_, C_, sy, sx, off=0, bias=None, bias_n=0):
+            o = N.OutSpec()
+            o.ptr[0] = y.data_ptr()
+            o.kind = N.OUT_BF16 if y.dtype == torch.bfloat16 else N.OUT_F32
+            o.act, o.slope, o.mirror, o.off = N.ACT_NONE, 0.2, 0, off
+            o.sn, o.sy, o.sx, o.sc = 2 * H * row, sy, sx, 1
+            o.N, o.H, o.W, o.C = N_, H_, W_, C_
+            o.bias, o.bias_n = (bias.data_ptr() if bias is not None else 0), bias_n
+            return o
+
+        # ---- main: 3x3 conv of the source plane, 4 phases folded into N, depth-to-space store, ring pixels skipped
+        om = spec(n, H, W, 4 * cout, 2 * row, 2 * cs, bias=up.bias4, bias_n=4 * cout)
+        om.d2s_c, om.d2s_sy, om.d2s_sx, om.ring = cout, row, cs, 1
+        plan = N.IgemmPlan()
+        xs = x.struct()
+        N.check(L.aclgan_plan_conv_fwd(C.byref(up.desc), C.byref(xs), up.wptr(0), C.byref(om), C.byref(plan)), "plan_conv_fwd(up)")
+        fused = self.fuse_stats and bool(L.aclgan_igemm_stats_supported(C.byref(plan)))
+        groups = 4 if fused else 1
+        sums = self.sums(n, 4 * cout if fused else cs)
+        if fused:
+            plan.out.stats = sums.data_ptr()
+        N.check(L.aclgan_igemm_launch(C.byref(plan), _sp()), "igemm_launch(up main)")
+        # ---- ring: exact 5x5 on strips of the padded up-sampled plane (columns as transposed strips / transposed filter)
+        xr = ActT(self, 2 * n, 2, 2 * W, x.c_valid, 2, cs=x.c)
+        xc = ActT(self, 2 * n, 2, 2 * H - 4, x.c_valid, 2, cs=x.c)
+        g = N.UpStripsArgs()
+        g.src, g.rows, g.cols = xs, xr.struct(), xc.struct()
+        N.check(L.aclgan_up_gather_strips(C.byref(g), _sp()), "up_gather_strips")
+        orow = spec(2 * n, 2, 2 * W, cs, row, cs, bias=base.bias, bias_n=cout)
+        orow.z_mod, orow.z_off = n, (2 * H - 2) * row
+        ocol = spec(2 * n, 2, 2 * H - 4, cs, cs, row, off=2 * row, bias=base.bias, bias_n=cout)
+        ocol.z_mod, ocol.z_off = n, (2 * W - 2) * cs
+        for lay, xin, o in ((base, xr, orow), (up.colview, xc, ocol)):
+            if fused:
+                o.stats_c = 4 * cout
+            if not self.conv_fwd_launch(lay, xin, o, stats=sums if fused else None) and fused:
+                raise N.NativeError("up-block strip convolution cannot fuse the LayerNorm statistics")
+        y4 = self.t4(y)
+        if not fused:
+            N.check(L.aclgan_norm_stats(C.byref(y4), sums.data_ptr(), _sp()), "norm_stats")
+        # ---- LayerNorm + activation -> the consumer's padded plane
+        coef = torch.empty((4, n, cs), dtype=torch.float32, device=self.device)
+        sigma = torch.empty((n,), dtype=torch.float32, device=self.device)
+        f = N.NormFinalizeArgs()
+        f.mode, f.n, f.c, f.hw, f.c_valid, f.eps = N.NORM_LN, n, cs, 4 * H * W, cout, self.eps
+        f.sums, f.stat_groups = sums.data_ptr(), groups
+        f.w, f.b = ln[0].data_ptr(), ln[1].data_ptr()
+        f.scale, f.shift, f.mean, f.inv = (coef[i].data_ptr() for i in range(4))
+        f.sigma = sigma.data_ptr()
+        N.check(L.aclgan_norm_finalize(C.byref(f), _sp()), "norm_finalize")
+        out = ActT(self, n, 2 * H, 2 * W, cout, out_pad)
+        a = N.ApplyArgs()
+        a.y, a.scale, a.shift, a.act, a.slope = y4, coef[0].data_ptr(), coef[1].data_ptr(), act, slope
+        a.has_res, a.upsample, a.dst = 0, 1, out.struct()
+        N.check(L.aclgan_norm_apply(C.byref(a), _sp()), "norm_apply")
+        need_x_grad = x.requires_grad
+        out.requires_grad = need_x_grad or train_w
+        if not tape.enabled or not out.requires_grad:
+            return out
+
+        def bwd():
+            gp, gr = out.gp, out.gr
+            out.gp = out.gr = None
+            if gp is None and gr is None:
+                return
+            b = N.BlockBwdArgs()
+            b.gp = gp.data_ptr() if gp is not None else 0
+            b.gr = gr.data_ptr() if gr is not None else 0
+            b.g_kind, b.gp_pad, b.upsample = self.prec.kind, out.pad, 1
+            b.n, b.h, b.w, b.c = n, 2 * H, 2 * W, cs
+            b.slope = 0.0 if act == N.ACT_RELU else slope
+            dy = ActT(self, n, 2 * H, 2 * W, cout, 0)
+            b.dy = dy.struct()
+            bs = self.sums(n, cs)
+            b.sums, b.norm = bs.data_ptr(), 1
+            b.mask_mode = N.MASK_NONE if act == N.ACT_NONE else N.MASK_FROM_Z
+            b.y = y4
+            b.scale, b.shift, b.mean, b.inv = (coef[i].data_ptr() for i in range(4))
+            N.check(L.aclgan_block_bwd_reduce(C.byref(b), _sp()), "block_bwd_reduce")
+            cf = torch.empty((3, n, cs), dtype=torch.float32, device=self.device)
+            fb = N.NormBwdFinalizeArgs()
+            fb.mode, fb.n, fb.c, fb.hw, fb.c_valid = N.NORM_LN, n, cs, 4 * H * W, cout
+            fb.sums, fb.inv, fb.sigma = bs.data_ptr(), coef[3].data_ptr(), sigma.data_ptr()
+            fb.w, fb.dw, fb.db = ln[0].data_ptr(), ln[2].data_ptr(), ln[3].data_ptr()
+            fb.ca, fb.cb, fb.cc = (cf[i].data_ptr() for i in range(3))
+            if train_w:         # conv bias in front of the LayerNorm (not cancelled): from the forward statistics
+                fb.fsums, fb.mean, fb.dbias, fb.fstat_groups = sums.data_ptr(), coef[2].data_ptr(), base.db().data_ptr(), groups
+            N.check(L.aclgan_norm_bwd_finalize(C.byref(fb), _sp()), "norm_bwd_finalize")
+            b.ca, b.cb, b.cc = (cf[i].data_ptr() for i in range(3))
+            N.check(L.aclgan_block_bwd_apply(C.byref(b), _sp()), "block_bwd_apply")
+            # dY -> space-to-depth plane (ring zeroed) for the 3x3 main gradients + ring strips for the 5x5 strip gradients
+            ds = ActT(self, n, H, W, 4 * cout, 2)
+            dr = ActT(self, 2 * n, 2, 2 * W, cout, 4)
+            dc = ActT(self, 2 * n, 2, 2 * H - 4, cout, 4)
+            pk = N.UpDyPackArgs()
+            pk.dy, pk.cout, pk.s2d, pk.rows, pk.cols = dy.struct(), cout, ds.struct(), dr.struct(), dc.struct()
+            N.check(L.aclgan_up_dy_pack(C.byref(pk), _sp()), "up_dy_pack")
+            if train_w:
+                zero_(up.dwp)
+                self.conv_wgrad(up.main, ds, x)
+                fw = N.UpFoldWgradArgs()
+                fw.dwp, fw.dw5, fw.co, fw.ci = up.dwp.data_ptr(), base.arena.flat.data_ptr(), cout, base.cin
+                for j in range(5):
+                    fw.affp[j] = up.aff[up.layout][j]
+                    fw.aff5[j] = base.aff[base.layout][j] + (base.dw_off if j == 0 else 0)
+                N.check(L.aclgan_up_fold_wgrad(C.byref(fw), _sp()), "up_fold_wgrad")
+                self.conv_wgrad(base, dr, xr)
+                self.conv_wgrad(up.colview, dc, xc, transpose_taps=True)
+            if need_x_grad:
+                gx = self.conv_dgrad(up.main, ds, x)
+                gxr = self.conv_dgrad(base, dr, xr)
+                gxc = self.conv_dgrad(up.colview, dc, xc)
+                sc = N.UpScatterArgs()
+                sc.g, sc.grows, sc.gcols = gx.data_ptr(), gxr.data_ptr(), gxc.data_ptr()
+                sc.kind, sc.n, sc.h, sc.w, sc.c = self.prec.kind, n, H, W, gx.shape[-1]
+                assert gxr.shape[-1] == gx.shape[-1] and gxc.shape[-1] == gx.shape[-1]
+                N.check(L.aclgan_up_scatter_strips(C.byref(sc), _sp()), "up_scatter_strips")
+                x.add_gp(gx)
 
         tape.push(bwd)
         return out

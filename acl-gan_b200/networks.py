@@ -292,6 +292,13 @@ class _EngineNet(nn.Module):
         for l in self.conv_layers():
             l.dirty = True
 
+    def derive_weights(self):
+        """re-derives every weight set computed FROM a master conv weight (sub-pixel phase weights of the up blocks): called
+        after each optimizer step (the fused Adam kernel rewrites the plain packings itself)"""
+        for l in self.conv_layers():
+            for d in l.derived:
+                d.derive()
+
     def attach_grads(self):
         """points every parameter's .grad at its slice of the arena (conv weights: strided OIHW views)"""
         for blk in self.modules():
@@ -372,9 +379,13 @@ class AdaINGen(_EngineNet):
         for rb in dec[0].model:
             for blk in rb.model:
                 blk.layer(eng, ar)
+        self.subpixel = os.environ.get("ACLGAN_SUBPIXEL", "1") != "0"
         for blk in dec[1:-1]:
             if isinstance(blk, Conv2dBlock):
-                blk.layer(eng, ar)
+                lay = blk.layer(eng, ar)
+                # nearest 2x upsample + 5x5 conv in sub-pixel form (9 instead of 25 taps per output pixel, the up-sampled plane
+                # is never materialised): derived phase weights around the 5x5 layer (engine.UpConvLayer)
+                blk._up = E.UpConvLayer(eng, lay) if (self.subpixel and lay.k == 5 and lay.cout % 8 == 0) else None
                 self._reserve_dense(blk.norm.gamma)
                 self._reserve_dense(blk.norm.beta)
         dec[-1].layer(eng, ar, N.WINDOW_OUT if dec[-1].spec["cout"] <= 8 else N.WINDOW_NONE)
@@ -518,6 +529,8 @@ class AdaINGen(_EngineNet):
                 else:
                     up = 2 if (last_rb and len(m) > 2) else 1
                     nxt = m[2].spec["pad"] if (last_rb and len(m) > 2) else (m[-1].spec["pad"] if last_rb else 1)
+                    if up == 2 and getattr(m[2], "_up", None) is not None:
+                        up, nxt = 1, 1      # sub-pixel up block: it reads the SOURCE plane (reflect pad 1)
                     x = eng.conv_block(tape, blk._layer, h, norm=N.NORM_ADAIN, act=N.ACT_NONE, out_pad=nxt,
                                        upsample=up, res=x, adain=(weight, bias, d_weight, d_bias), train_w=tw)
         ups = [b for b in m[1:-1] if isinstance(b, Conv2dBlock)]
@@ -526,8 +539,14 @@ class AdaINGen(_EngineNet):
             nxt = m[-1].spec["pad"] if last else ups[i + 1].spec["pad"]
             ln = (blk.norm.gamma.detach(), blk.norm.beta.detach(),
                   self._grad_of(blk.norm.gamma), self._grad_of(blk.norm.beta))
-            x = eng.conv_block(tape, blk._layer, x, norm=N.NORM_LN, act=act, out_pad=nxt,
-                               upsample=1 if last else 2, ln=ln, train_w=tw)
+            nxt_up = None if last else getattr(ups[i + 1], "_up", None)
+            if getattr(blk, "_up", None) is not None:
+                x = eng.conv_block_up(tape, blk._up, x, act=act, out_pad=(1 if nxt_up is not None else nxt), ln=ln, train_w=tw)
+                if not last and nxt_up is None:
+                    raise N.NativeError("mixed sub-pixel / materialised up blocks are not supported")
+            else:
+                x = eng.conv_block(tape, blk._layer, x, norm=N.NORM_LN, act=act, out_pad=nxt,
+                                   upsample=1 if last else 2, ln=ln, train_w=tw)
         return eng.conv_to_image(tape, m[-1]._layer, x, act=N.ACT_TANH, train_w=tw)
 
     # ---- reference-compatible tensor API (forward values only) ---------------------------------------

@@ -429,6 +429,8 @@ class aclgan_Trainer(nn.Module):
             self._gen_fwd_bwd(x_a, x_b, hyperparameters, self._draw_noise(x_a.size(0)))
         self._allreduce(self.gen_arena)
         self._adam_step(self._adam_gen)
+        self.gen_AB.derive_weights()
+        self.gen_BA.derive_weights()
         if self.expose_grads:
             self.gen_AB.refresh_grads()
             self.gen_BA.refresh_grads()

@@ -57,6 +57,15 @@ typedef struct aclgan_out_spec {
     int32_t bias_n;         /* channels >= bias_n get no bias (stored padding channels) */
     uint64_t stats;         /* double [N][C][2] (sum, sum of squares of the stored values) accumulated with atomics, or 0:
                                the statistics pass of InstanceNorm / AdaIN / LayerNorm fused into the conv epilogue */
+    /* ---- sub-pixel up-convolution (csrc/upconv.cu): the four output phases of nearest-2x-upsample + 5x5 are folded into N ---- */
+    int32_t d2s_c;          /* 0, or channels per phase: GEMM column ch = phase*d2s_c + c is stored at pixel offset
+                               (phase>>1)*d2s_sy + (phase&1)*d2s_sx, channel c (depth-to-space; sy / sx then step 2 output pixels) */
+    int32_t ring;           /* 1: rows on the 1-pixel border ring of the (H, W) grid are neither stored nor counted in stats
+                               (the ring is recomputed exactly by the strip convolutions) */
+    int64_t d2s_sy, d2s_sx;
+    int32_t z_mod;          /* 0, or images per strip side: batch index z addresses image z % z_mod at offset (z / z_mod) * z_off */
+    int32_t stats_c;        /* 0 (= C), or the channel stride of `stats` when it is shared with a wider launch */
+    int64_t z_off;
 } aclgan_out_spec;
 
 /* ---- implicit GEMM plan:  D[pixel][n] = sum_seg sum_tap sum_chunk A_tap[pixel][64] * B[n][k(tap,chunk) + 64] ---- */
@@ -232,6 +241,9 @@ typedef struct aclgan_norm_finalize_args {
     uint64_t sigma;         /* out fp32 [n] (LN only: the unbiased std) */
     int64_t wb_stride;      /* ADAIN: elements between consecutive samples of w / b (0 = c_valid): the parameters are read
                                in place from the MLP output row (networks.py:154-163 slices, never copied) */
+    int32_t stat_groups;    /* LN after a sub-pixel up-convolution: `sums` holds stat_groups (4) phase groups of c_valid channels
+                               per sample, i.e. [n][stat_groups * c_valid][2]; 0 / 1 = plain [n][c][2] */
+    int32_t pad_;
 } aclgan_norm_finalize_args;
 int aclgan_norm_finalize(const aclgan_norm_finalize_args* a, void* stream);
 
@@ -291,6 +303,8 @@ typedef struct aclgan_norm_bwd_finalize_args {
     uint64_t fsums;         /* double [n][c][2]: the FORWARD statistics (S1 = sum of y) */
     uint64_t mean;          /* fp32 [n][c] forward mean */
     uint64_t dbias;         /* fp32 [c_valid] accumulated with atomics, or 0 */
+    int32_t fstat_groups;   /* fsums is [n][fstat_groups * c_valid][2] (phase groups of the sub-pixel up-convolution); 0 / 1 = [n][c][2] */
+    int32_t pad_;
 } aclgan_norm_bwd_finalize_args;
 int aclgan_norm_bwd_finalize(const aclgan_norm_bwd_finalize_args* a, void* stream);
 
@@ -344,6 +358,58 @@ typedef struct aclgan_adam_tensor {
  * chunks (device, int32[2*n_chunks]): (tensor id, first element / 1024) per CTA. */
 int aclgan_adam_step(uint64_t table, uint64_t chunks, int32_t n_chunks, uint64_t hyper, void* stream);
 int aclgan_adam_advance(uint64_t hyper, void* stream);
+
+/* ================= sub-pixel up-convolution (csrc/upconv.cu) =================
+ * nearest-2x-upsample -> ReflectionPad2d(2) -> Conv2d 5x5 (reference networks.py:256-257) as ONE 3x3 convolution of the
+ * reflect-pad-1 source plane with 4*Cout output channels (the 4 output phases folded into N, depth-to-space epilogue:
+ * aclgan_out_spec.d2s_*, .ring) plus exact 5x5 convolutions on four thin border strips (aclgan_out_spec.z_mod / z_off).
+ * The GEMMs are ordinary plans; these entry points are the layout kernels around them. */
+typedef struct aclgan_up_derive_args {
+    uint64_t w5, bias;        /* fp32 [co][ci][5][5] master weight, fp32 [co] bias */
+    int32_t co, ci, planes, pad_;
+    uint64_t pk[2][2];        /* [forward, transposed packing][plane] bf16 destinations of the phase weights (4co, ci, 3, 3):
+                                 Wp[(py*2+px)*co + o][i][u][v] = sum of W5[o][i][a][b] over the taps a (b) that read source row (column)
+                                 offset u-1 (v-1) in phase py (px): phase 0: {0,1},{2,3},{4}; phase 1: {0},{1,2},{3,4} */
+    int64_t aff[2][5];        /* packed index = base + co'*s0 + ci*s1 + u*s2 + v*s3 (aclgan_packed_weight_index of the 3x3 desc) */
+    uint64_t bias4;           /* out fp32 [4*co]: the bias tiled over the four phases, or 0 */
+} aclgan_up_derive_args;
+int aclgan_up_derive_weights(const aclgan_up_derive_args* a, void* stream);
+
+/* forward: strips of the exactly padded up-sampled plane.  rows: [2n][2][2W] pad 2 = up-sampled rows -2..3 (side 0) and
+ * 2H-4..2H+1 (side 1), columns -2..2W+1; cols: [2n][2][2H-4] pad 2, TRANSPOSED (strip row = up-sampled column -2..3 /
+ * 2W-4..2W+1, strip column = up-sampled row 0..2H-1): both fully written, borders included */
+typedef struct aclgan_up_strips_args {
+    aclgan_act src;           /* source plane [n][H][W][C] (any pad; only the interior is read) */
+    aclgan_act rows, cols;
+} aclgan_up_strips_args;
+int aclgan_up_gather_strips(const aclgan_up_strips_args* a, void* stream);
+
+/* backward: dense dY [n][2H][2W][cs] (pad 0) -> (a) space-to-depth plane [n][H][W][4*cout] pad 2 with the ring source pixels
+ * and the border zero, (b) ring rows [2n][2][2W] pad 4, (c) ring columns [2n][2][2H-4] pad 4 transposed (zero borders) */
+typedef struct aclgan_up_dy_pack_args {
+    aclgan_act dy;
+    int32_t cout, pad_;       /* valid channels per phase (multiple of 8) */
+    aclgan_act s2d, rows, cols;
+} aclgan_up_dy_pack_args;
+int aclgan_up_dy_pack(const aclgan_up_dy_pack_args* a, void* stream);
+
+/* backward: input gradients of the strip convolutions, gathered back onto the source pixels they were copied from and added
+ * to the interior of the padded-source-plane gradient g [n][H+2][W+2][C] */
+typedef struct aclgan_up_scatter_args {
+    uint64_t g, grows, gcols; /* grows [2n][6][2W+4][C], gcols [2n][6][2H][C]; all of `kind` (0 bf16, 1 fp32) */
+    int32_t kind, n, h, w, c, pad_;
+} aclgan_up_scatter_args;
+int aclgan_up_scatter_strips(const aclgan_up_scatter_args* a, void* stream);
+
+/* backward: dW5[o][i][a][b] += sum over the 4 phases of dWp[phase*co + o][i][u(py, a)][v(px, b)] (both in packed layouts) */
+typedef struct aclgan_up_fold_wgrad_args {
+    uint64_t dwp;
+    int64_t affp[5];
+    uint64_t dw5;
+    int64_t aff5[5];
+    int32_t co, ci;
+} aclgan_up_fold_wgrad_args;
+int aclgan_up_fold_wgrad(const aclgan_up_fold_wgrad_args* a, void* stream);
 
 /* ================= small operators: csrc/smallops.cu ================= */
 

@@ -22,7 +22,8 @@ LAUNCHERS = ["aclgan_igemm_launch", "aclgan_wgrad_launch", "aclgan_pack_img", "a
              "aclgan_avgpool3x3s2_fwd", "aclgan_avgpool3x3s2_bwd", "aclgan_style_head_fwd", "aclgan_style_head_bwd",
              "aclgan_mlp_fwd", "aclgan_mlp_bwd", "aclgan_dis_head_fwd", "aclgan_dis_head_bwd", "aclgan_focus_blend_fwd",
              "aclgan_focus_blend_bwd", "aclgan_loss_reduce", "aclgan_focus_grad", "aclgan_loss_combine", "aclgan_stats_to_bias", "aclgan_pack_nchw",
-             "aclgan_unpack_plane"]
+             "aclgan_unpack_plane", "aclgan_up_derive_weights", "aclgan_up_gather_strips", "aclgan_up_dy_pack",
+             "aclgan_up_scatter_strips", "aclgan_up_fold_wgrad"]
 
 
 class _Stub:

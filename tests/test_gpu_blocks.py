@@ -232,3 +232,88 @@ def test_image_io_and_final_conv(precision):
     # the first conv's quantities sit below a LeakyReLU: one flipped unit of this 8x8 plane is ~6e-3 (see test_gpu_step)
     lim = {k: (btol if "final" in k or "window-out" in k else max(btol, 2e-2)) for k in errs}
     assert all(errs[k] < lim[k] for k in errs), errs
+
+
+UP_CASES = [
+    # cin, cout, n, h (source plane h x h -> output 2h x 2h), out_pad
+    (256, 128, 2, 64, 1),        # first up block of the 256x256 decoder (flattened-grid tiles, N = 512 in two tiles)
+    (128, 64, 1, 128, 3),        # second up block: 128-pixel row tiles, N = 256
+    (64, 32, 2, 16, 1),          # narrow ('tiny') networks: phases narrower than a staged row segment -> generic epilogue
+    (32, 16, 2, 32, 3),
+    (64, 64, 1, 8, 2),
+    (128, 64, 2, 5, 1),          # odd, small plane: every source pixel within 2 of the border
+]
+
+
+@pytest.mark.parametrize("precision", ["fp32x3", "bf16"])
+@pytest.mark.parametrize("cin,cout,n,h,out_pad", UP_CASES)
+def test_up_block_subpixel(precision, cin, cout, n, h, out_pad):
+    """nearest 2x upsample -> ReflectionPad2d(2) -> Conv2d 5x5 -> LayerNorm -> ReLU (reference networks.py:256-257,520-536) in
+    sub-pixel form (engine.conv_block_up: 3x3 / 4*Cout main convolution + exact ring strips) vs the plain fp64 composition,
+    forward and every gradient; includes the reflect-in-up-sampled-coordinates border ring."""
+    eng = E.Engine(precision)
+    tol = 2e-4 if precision == "fp32x3" else 4e-2
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = torch.randn(n, cin, h, h, device=dev)
+    w = torch.nn.Parameter(torch.randn(cout, cin, 5, 5, device=dev) / (cin * 25) ** 0.5)
+    b = torch.nn.Parameter(torch.randn(cout, device=dev) * 0.1)
+    gamma, beta = torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev)
+    arena = E.GradArena(eng.device)
+    layer = E.ConvLayer(eng, arena, w, b, 1, 2)
+    ln_off = (arena.reserve(cout), arena.reserve(cout))
+    arena.finalize()
+    up = E.UpConvLayer(eng, layer)
+    xa = plane_from_nchw(eng, x, 1)
+    xa.requires_grad = True
+    ln = (gamma, beta, arena.view(ln_off[0], cout), arena.view(ln_off[1], cout))
+    tape = E.Tape()
+    out = eng.conv_block_up(tape, up, xa, act=N.ACT_RELU, out_pad=out_pad, ln=ln)
+    torch.cuda.synchronize()
+
+    def eff(t, planes):
+        hi = t.detach().float().bfloat16()
+        return (hi.double() + ((t.detach().float() - hi.float()).bfloat16().double() if planes == 2 else 0))
+    P = eng.prec.planes
+    x64 = eff(x, P).requires_grad_(True)
+    w64 = eff(w, P).requires_grad_(True)
+    b64 = b.detach().double().requires_grad_(True)
+    g64, be64 = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    u = F.interpolate(x64, scale_factor=2, mode="nearest")
+    ref = ref_block(u, w64, b64, 1, 2, N.NORM_LN, N.ACT_RELU, None, 1, out_pad, None, (g64, be64))
+    p = out.pad
+    full = out.buf[:, :out.numel].float().sum(0).view(n, out.h + 2 * p, out.w + 2 * p, out.c)
+    got = full[..., :cout].permute(0, 3, 1, 2).double()
+    assert got.shape == ref.shape
+    err = float((got - ref).norm() / ref.norm())
+    ring = torch.ones_like(ref, dtype=torch.bool)
+    ring[:, :, p + 2:ref.shape[2] - p - 2, p + 2:ref.shape[3] - p - 2] = False
+    err_ring = float(((got - ref) * ring).norm() / (ref * ring).norm())
+    assert err < tol and err_ring < tol, ("forward", err, "ring", err_ring)
+    if out.c > cout:
+        assert float(full[..., cout:].abs().max()) == 0.0
+
+    G = torch.randn_like(ref)
+    gp = torch.zeros((n, out.h + 2 * p, out.w + 2 * p, out.c), device=dev, dtype=eng.prec.dtype)
+    gp[..., :cout] = G.permute(0, 2, 3, 1).to(eng.prec.dtype)
+    Geff = gp[..., :cout].double().permute(0, 3, 1, 2)
+    out.gp = gp
+    tape.backward()
+    torch.cuda.synchronize()
+    (ref * Geff).sum().backward()
+
+    def rel(a, bb):
+        return float((a.double() - bb).norm() / (bb.norm() + 1e-30))
+    gx = xa.gp[..., :cin].double().permute(0, 3, 1, 2)
+    probe = torch.zeros_like(x64).requires_grad_(True)
+    (F.pad(probe, (1,) * 4, mode="reflect") * gx).sum().backward()
+    btol = tol * 3
+    if h >= 64 and precision == "fp32x3":
+        btol = 3e-3          # ReLU units within the fp32x3 rounding distance of zero flip against fp64 (test_conv_block)
+    gw, gb = layer.grad_views()
+    errs = {"dgrad": rel(probe.grad, x64.grad), "wgrad": rel(gw, w64.grad), "bgrad": rel(gb, b64.grad),
+            "dgamma": rel(ln[2], g64.grad), "dbeta": rel(ln[3], be64.grad)}
+    print("\n[up block %d->%d %dx%d n=%d %s] forward %.2e (ring %.2e)  %s" % (
+        cin, cout, h, h, n, precision, err, err_ring, "  ".join("%s %.2e" % kv for kv in errs.items())))
+    bad = {k: v for k, v in errs.items() if not v < btol}
+    assert not bad, bad

@@ -798,7 +798,7 @@ class Engine:
             bs = self.sums(n, cs)
             b.sums, b.norm = bs.data_ptr(), 1
             b.mask_mode = N.MASK_NONE if act == N.ACT_NONE else N.MASK_FROM_Z
-            b.y = y4
+            b.y = self.t4(y)            # (referencing `y` here keeps the raw conv output alive until the backward pass)
             b.scale, b.shift, b.mean, b.inv = (coef[i].data_ptr() for i in range(4))
             N.check(L.aclgan_block_bwd_reduce(C.byref(b), _sp()), "block_bwd_reduce")
             cf = torch.empty((3, n, cs), dtype=torch.float32, device=self.device)

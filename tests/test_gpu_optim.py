@@ -189,7 +189,7 @@ def test_two_iterations_update_parity(golden_dir, case, point):
                 tol_e, tol_f = 0.35, 0.1
             if not e_new <= max(tol_e, 2 * e_ref) + 1e-12:
                 fails.append(("iteration %d %s" % (i // 2 + 1, kind), key, "dp rel err", e_new, e_ref))
-            if not n_bad <= max(2, int(tol_f * d64.numel()), 3 * n_bad_ref):
+            if not n_bad <= max(2 if i < 2 else 16, int(tol_f * d64.numel()), 3 * n_bad_ref):
                 fails.append(("iteration %d %s" % (i // 2 + 1, kind), key, "sign flips", n_bad, n_bad_ref, d64.numel()))
         errs.sort()
         agree.sort()

@@ -268,7 +268,9 @@ def test_gradients_vs_live_oracle(golden_dir, precision, point):
             point, ("dis", "gen")[idx], len(errs), errs[len(errs) // 2], errs[int(len(errs) * 0.9)], errs[-1],
             [(k, "%.2e" % a, "ref32 %.2e" % b) for a, k, b in worst[:3]]))
     (errs_d, worst_d), (errs_g, worst_g) = stats
-    assert errs_d[-1] < 1e-3, worst_d[:5]
+    # the bulk of the discriminator gradients agrees to rounding; ONE LeakyReLU unit within rounding distance of zero flips
+    # between any two implementations (module docstring) and moves the layers upstream of it by 1e-3 .. 1e-2
+    assert errs_d[int(len(errs_d) * 0.9)] < 1e-4 and errs_d[-1] < 5e-3, worst_d[:5]
     assert errs_g[len(errs_g) // 2] < 5e-3, "systematic generator gradient error"
     assert errs_g[-1] < FLIP_CEIL, worst_g[:5]
 

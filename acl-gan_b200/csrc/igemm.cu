@@ -173,6 +173,22 @@ __device__ __noinline__ void epilogue_tile_generic(const EpiArgs o, uint32_t t_r
         int cnt = o.C - ch0;
         if (cnt > step) cnt = step;
         if (!rc.valid || cnt <= 0) continue;
+        if (step == 16 && cnt == 16 && o.sc == 1 && o.d2s_c == 0 && o.kind == ACLGAN_OUT_F32 && o.mirror == 0 &&
+            ((rc.pix0 + ch0) & 3) == 0) {
+            // hot small-N case (16-column fp32 tiles: the image gradients of the first-layer data gradients, ~1 M rows of
+            // 64 B per launch): everything in registers, four 16-byte stores per row
+            float w16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float t = __uint_as_float(raw[i]);
+                if (bias != nullptr && ch0 + i < o.bias_n) t += __ldg(bias + ch0 + i);
+                w16[i] = apply_act(t, o.act, o.slope);
+            }
+            float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(o.ptr0) + rc.pix0 + ch0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = make_float4(w16[4 * i], w16[4 * i + 1], w16[4 * i + 2], w16[4 * i + 3]);
+            continue;
+        }
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
@@ -182,12 +198,38 @@ __device__ __noinline__ void epilogue_tile_generic(const EpiArgs o, uint32_t t_r
             if (bias != nullptr && ch0 + i < o.bias_n) t += __ldg(bias + ch0 + i);
             v[i] = apply_act(t, o.act, o.slope);
         }
+        // full, channel-contiguous 16-wide chunks (e.g. the 16-column image-gradient tiles of the first-layer data gradients:
+        // 1 M rows x 64 B) are stored as 16-byte vectors - the scalar loop below made those launches store-bound
+        const bool vec = o.sc == 1 && o.d2s_c == 0 && cnt == 16 && step == 16 && o.kind != ACLGAN_OUT_F32_ATOMIC;
 #pragma unroll 1
         for (int iy = 0; iy < rc.ny; ++iy)
 #pragma unroll 1
-            for (int ix = 0; ix < rc.nx; ++ix)
-                store_generic(o, rc.pix0 + (int64_t)(rc.ys[iy] - rc.y) * o.sy + (int64_t)(rc.xs[ix] - rc.x) * o.sx, ch0,
-                              cnt, v);
+            for (int ix = 0; ix < rc.nx; ++ix) {
+                const int64_t pix = rc.pix0 + (int64_t)(rc.ys[iy] - rc.y) * o.sy + (int64_t)(rc.xs[ix] - rc.x) * o.sx;
+                if (vec && o.kind == ACLGAN_OUT_F32 && ((pix + ch0) & 3) == 0) {
+                    float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(o.ptr0) + pix + ch0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                } else if (vec && o.kind != ACLGAN_OUT_F32 && ((pix + ch0) & 7) == 0) {
+                    uint4* d0 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(o.ptr0) + pix + ch0);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        d0[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                           pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+                    if (o.kind == ACLGAN_OUT_SPLIT) {
+                        uint4* d1 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(o.ptr1) + pix + ch0);
+                        float r[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            d1[i] = make_uint4(pack_bf16x2(r[8 * i], r[8 * i + 1]), pack_bf16x2(r[8 * i + 2], r[8 * i + 3]),
+                                               pack_bf16x2(r[8 * i + 4], r[8 * i + 5]), pack_bf16x2(r[8 * i + 6], r[8 * i + 7]));
+                    }
+                } else {
+                    store_generic(o, pix, ch0, cnt, v);
+                }
+            }
     }
 }
 

@@ -27,6 +27,24 @@ for p in (PKG, os.path.join(ROOT, "oracle")):
 F_ALG_TFLOP_PER_IMG = {4: 2.623, 3: 2.616}      # necessary conv+linear FLOPs per image per step-pair @256^2
 
 
+def executed_tflop_per_image(cfg, size, f_alg, subpixel=True):
+    """conv FLOPs the kernels EXECUTE per image per step-pair: F_alg (SURVEY.md 8d, 25 taps per output pixel in the two
+    up-blocks) minus what the sub-pixel form of nearest-2x-upsample + 5x5 saves (3x3 main convolution with the 4 phases folded
+    into N = 9 taps per output pixel, plus the exact 25-tap ring strips: 2 rows x 2 sides x 2W and 2 columns x 2 sides x (2H-4)
+    outputs per image).  Decodes per step-pair: 8 forward (3 in dis_update, 5 in gen_update) + 5 x (dgrad + wgrad)."""
+    if not subpixel:
+        return f_alg
+    dim, n_down = cfg["gen"]["dim"], cfg["gen"]["n_downsample"]
+    c, h = dim * 2 ** n_down, size // 2 ** n_down
+    saved = 0.0
+    for _ in range(n_down):
+        full = 25.0 * c * (c // 2) * (2 * h) * (2 * h)
+        sub = 9.0 * c * 4 * (c // 2) * h * h + 25.0 * c * (c // 2) * (4 * 2 * h + 4 * (2 * h - 4))
+        saved += full - sub
+        c, h = c // 2, h * 2
+    return f_alg - (8 + 2 * 5) * 2.0 * saved / 1e12
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -375,6 +393,7 @@ def run_b200(args):
     pk = peaks()
     out_dim = cfg["gen"]["output_dim"]
     f_alg = F_ALG_TFLOP_PER_IMG.get(out_dim, 2.623) * (S / 256.0) ** 2
+    f_exec = executed_tflop_per_image(cfg, S, f_alg, os.environ.get("ACLGAN_SUBPIXEL", "1") != "0")
     img_s = B * world / (ms_res * 1e-3)
     img_s_e2e = B * world / (ms_e2e * 1e-3)
     launches = getattr(tr, "launches_per_step_pair", None)
@@ -389,7 +408,12 @@ def run_b200(args):
         clocks=clocks,
         step_tensor_util=dict(f_alg_tflop_per_image=f_alg, achieved_tflops=f_alg * img_s / world,
                               peak=pk["sustained"], frac=f_alg * img_s / world / pk["sustained"],
-                              peak_source=pk["src"] + " bf16_tflops_sustained (kernel inside a long step)"),
+                              executed_tflop_per_image=f_exec, executed_tflops=f_exec * img_s / world,
+                              executed_frac=f_exec * img_s / world / pk["sustained"],
+                              peak_source=pk["src"] + " bf16_tflops_sustained (kernel inside a long step)",
+                              note="frac counts the algorithmic FLOPs of the reference's layer shapes (SURVEY.md 8d F_alg); "
+                                   "executed_* counts what the kernels execute: the sub-pixel up-blocks run 9 instead of 25 taps "
+                                   "per output pixel (+ ring strips)"),
     )
     line["schedule_2to1"] = dict(value=2 * B * world / (ms_2to1 * 1e-3), unit="images/s (iterations x batch; D_update 1, G_update 2 "
                                  "as shipped in the YAML: 2 dis_update + 1 gen_update per 2 iterations)", ms_per_2_iterations=ms_2to1)

@@ -251,8 +251,8 @@ def library_bar(cfg, batch, size, steps=3, warmup=2):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel from the committed ncu --set full capture
-# (profiles/r1_top_kernels_v5.md): 19.2 MB read (input plane 17.8 MB + packed weights 1.2 MB), the 16.8 MB output stays in L2
-ROOFLINE_TRAFFIC_BYTES = 19.2e6
+# (profiles/r2_top_kernels.md): 19.19 MB read (input plane 17.84 MB + packed weights 1.18 MB), the 16.8 MB output stays in L2
+ROOFLINE_TRAFFIC_BYTES = 19.19e6
 
 
 def kernel_roofline(eng_precision, batch, pk):

@@ -6,6 +6,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "elementwise_rows.cuh"
 
 namespace aclgan {
 
@@ -1029,6 +1030,10 @@ extern "C" int aclgan_norm_apply(const aclgan_apply_args* a, void* stream) {
     const int u = a->upsample, p = a->dst.pad;
     const int64_t npix = (int64_t)(a->y.h * u + 2 * p) * (a->y.w * u + 2 * p);
     if (npix >= (1LL << 30)) return ACLGAN_ERR_SHAPE;
+    {
+        const int rc = rows_norm_apply(a, (cudaStream_t)stream);        // row-structured fast path (elementwise_rows.cu)
+        if (rc != -100) return rc;
+    }
     const int lanes = 256 / (a->y.c / 8);
     static int variant = -1;
     if (variant < 0) {
@@ -1070,6 +1075,10 @@ static bool bwd_fast_ok(const aclgan_block_bwd_args* a) {
 
 extern "C" int aclgan_block_bwd_reduce(const aclgan_block_bwd_args* a, void* stream) {
     if (check_cg(a->c)) return ACLGAN_ERR_SHAPE;
+    {
+        const int rc = rows_bwd_reduce(a, (cudaStream_t)stream);
+        if (rc != -100) return rc;
+    }
     const int lanes = kStatThreads / (a->c / 8);
     const int64_t hw = (int64_t)a->h * a->w;
     if (bwd_fast_ok(a)) {
@@ -1102,6 +1111,10 @@ extern "C" int aclgan_block_bwd_reduce(const aclgan_block_bwd_args* a, void* str
 
 extern "C" int aclgan_block_bwd_apply(const aclgan_block_bwd_args* a, void* stream) {
     if (check_cg(a->c) || a->dy.c != a->c) return ACLGAN_ERR_SHAPE;
+    {
+        const int rc = rows_bwd_apply(a, (cudaStream_t)stream);
+        if (rc != -100) return rc;
+    }
     const int64_t npix = (int64_t)(a->h + 2 * a->dy.pad) * (a->w + 2 * a->dy.pad);
     const int lanes = 256 / (a->c / 8);
     if (bwd_fast_ok(a)) {

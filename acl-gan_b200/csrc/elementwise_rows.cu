@@ -1,0 +1,497 @@
+// Row-structured variants of the three plane-sized element-wise passes (norm apply forward, block backward reduce / apply).
+//
+// The round-1 kernels walk a flattened pixel index (one integer division and a reflect computation per pixel), reload their
+// per-channel coefficients from shared memory for every pixel and branch on run-time flags inside the pixel loop:
+// `ncu --set full` shows ~135 thread instructions per 8-channel vector at ~50 % issue-slot utilisation, i.e. they are bound by
+// instruction issue at 0.35-0.55 of the HBM roofline (profiles/r2_elementwise_ncu.md).  Here a CTA owns whole plane ROWS of one
+// image: the row base addresses are computed once per row, a thread keeps ONE 8-channel group for its whole life so the
+// (pre-combined) coefficients live in registers, the pixel loop is unrolled with all loads issued first, and every mode flag
+// is a template parameter.  Same arithmetic as elementwise.cu (which stays as the generic / fallback path: 2x upsample, tanh,
+// degenerate plane sizes).
+//
+// Replaces (reference): InstanceNorm2d networks.py:333, AdaptiveInstanceNorm2d.forward :490-503, LayerNorm.forward :520-536,
+// ReLU / LeakyReLU :345-347, residual add :309, the consumer's ReflectionPad2d :319 - and autograd's backward of them.
+#include "common.cuh"
+#include "elementwise_rows.cuh"
+
+namespace aclgan {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct V8 {
+    float v[8];
+};
+
+__device__ __forceinline__ V8 ldg8(uint64_t base, int kind, int64_t idx) {
+    V8 r;
+    if (kind == 0) {
+        const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r.v[2 * i] = __uint_as_float(w[i] << 16);
+            r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+        }
+    } else {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+        const float4 a = p[0], b = p[1];
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+        r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    }
+    return r;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int PLANES>
+__device__ __forceinline__ void st8_planes(const uint64_t (&pl)[2], int64_t idx, const V8& v) {
+    uint4 q;
+    q.x = pack2(v.v[0], v.v[1]); q.y = pack2(v.v[2], v.v[3]); q.z = pack2(v.v[4], v.v[5]); q.w = pack2(v.v[6], v.v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pl[0]) + idx) = q;
+    if (PLANES == 2) {
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = v.v[i] - __bfloat162float(__float2bfloat16_rn(v.v[i]));
+        q.x = pack2(r[0], r[1]); q.y = pack2(r[2], r[3]); q.z = pack2(r[4], r[5]); q.w = pack2(r[6], r[7]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pl[1]) + idx) = q;
+    }
+}
+
+template <int PLANES>
+__device__ __forceinline__ V8 ld8_planes(const uint64_t (&pl)[2], int64_t idx) {
+    V8 r = ldg8(pl[0], 0, idx);
+    if (PLANES == 2) {
+        const V8 l = ldg8(pl[1], 0, idx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] += l.v[i];
+    }
+    return r;
+}
+
+__device__ __forceinline__ V8 coef8(uint64_t base, int64_t idx) {
+    V8 r;
+    if (base == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
+        return r;
+    }
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+
+__device__ __forceinline__ int reflect1(int i, int L) {
+    if (i < 0) i = -i;
+    if (i >= L) i = 2 * (L - 1) - i;
+    return i;
+}
+
+// mirror image of coordinate c under reflect padding of width p (at most one exists when L > 2p + 1), or -1000
+__device__ __forceinline__ int mirror1(int c, int L, int p) {
+    if (c >= 1 && c <= p) return -c;
+    if (c >= L - 1 - p && c <= L - 2) return 2 * (L - 1) - c;
+    return -1000;
+}
+
+// ------------------------------------------------------------------------------------------ forward apply
+// ACT: 0 none, 1 relu, 2 lrelu
+template <int KIND, int PLANES, int ACT, int RES, int UNR>
+__global__ void __launch_bounds__(kThreads) norm_apply_rows_kernel(aclgan_apply_args a, int rows_per_cta) {
+    const int p = a.dst.pad, h = a.y.h, w = a.y.w, hp = h + 2 * p, wp = w + 2 * p, C = a.y.c;
+    const int cg = C >> 3, lanes = kThreads / cg;
+    const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+    if (lane >= lanes) return;
+    const int n = blockIdx.y;
+    V8 sc, sf;
+    const bool affine = a.scale != 0;
+    if (affine) {
+        sc = coef8(a.scale, (int64_t)n * C + g * 8);
+        sf = coef8(a.shift, (int64_t)n * C + g * 8);
+    }
+    const int rp = a.res.pad, rwp = a.res.w + 2 * rp, rhp = a.res.h + 2 * rp;
+    const float slope = a.slope;
+    const int row_end = min(hp, ((int)blockIdx.x + 1) * rows_per_cta);
+    for (int Y = blockIdx.x * rows_per_cta; Y < row_end; ++Y) {
+        const int y = reflect1(Y - p, h);
+        const int64_t src_row = ((int64_t)n * h + y) * w * C + g * 8;
+        const int64_t res_row = RES ? (((int64_t)n * rhp + y + rp) * rwp + rp) * C + g * 8 : 0;
+        const int64_t dst_row = ((int64_t)n * hp + Y) * wp * C + g * 8;
+        for (int X0 = lane; X0 < wp; X0 += lanes * UNR) {
+            V8 yv[UNR], rv[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int X = min(X0 + u * lanes, wp - 1);           // clamped duplicate: loaded, never stored
+                const int x = reflect1(X - p, w);
+                yv[u] = ldg8(a.y.ptr, KIND, src_row + (int64_t)x * C);
+                if (RES) rv[u] = ld8_planes<PLANES>(a.res.data, res_row + (int64_t)x * C);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int X = X0 + u * lanes;
+                if (X >= wp) break;
+                V8 v = yv[u];
+                if (affine) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v.v[i] = v.v[i] * sc.v[i] + sf.v[i];
+                }
+                if (ACT == 1) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v.v[i] = fmaxf(v.v[i], 0.f);
+                } else if (ACT == 2) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v.v[i] = v.v[i] > 0.f ? v.v[i] : v.v[i] * slope;
+                }
+                if (RES) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v.v[i] += rv[u].v[i];
+                }
+                st8_planes<PLANES>(a.dst.data, dst_row + (int64_t)X * C, v);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward: dz of one pixel
+// MASK: 0 none, 1 from z = y*scale + shift (norm blocks), 2 from the forward output plane (no-norm blocks)
+struct BwdRow {
+    int64_t gp_row, gp_mrow;     // element offsets of gradient-plane row (y + p) and of its mirror row (or -1)
+    int64_t dense_row;           // offset of row y in dense [n][h][w][C] tensors (gr, y)
+    int64_t out_row;             // offset of row (y + po) of the forward output plane, at its column po
+};
+
+template <int KIND>
+__device__ __forceinline__ void add8(V8& acc, uint64_t base, int64_t idx) {
+    const V8 t = ldg8(base, KIND, idx);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] += t.v[i];
+}
+
+// raw loads of pixel x of the current row (no dependent arithmetic): gradient-plane value, dense gradient, y / forward output
+template <int KIND, int MASK, int NORM, int GP, int GR>
+struct PixRaw {
+    V8 g, gr, yv;
+};
+
+template <int KIND, int MASK, int NORM, int GP, int GR>
+__device__ __forceinline__ void pix_raw(const aclgan_block_bwd_args& a, const BwdRow& r, int x, int C, PixRaw<KIND, MASK, NORM, GP, GR>& o) {
+    if (GP) o.g = ldg8(a.gp, KIND, r.gp_row + (int64_t)(x + a.gp_pad) * C);
+    if (GR) o.gr = ldg8(a.gr, KIND, r.dense_row + (int64_t)x * C);
+    if (MASK == 1 || NORM) o.yv = ldg8(a.y.ptr, KIND, r.dense_row + (int64_t)x * C);
+    else if (MASK == 2) o.yv = ldg8(a.out.data[0], 0, r.out_row + (int64_t)x * C);
+}
+
+// dz = (fold of the padded-plane gradient + dense gradient) * act'(z)
+template <int KIND, int MASK, int NORM, int GP, int GR>
+__device__ __forceinline__ V8 pix_dz(const aclgan_block_bwd_args& a, const BwdRow& r, int x, int C, const PixRaw<KIND, MASK, NORM, GP, GR>& in,
+                                     const V8& scale, const V8& shift, float slope) {
+    V8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+    if (GP) {
+        acc = in.g;
+        const int p = a.gp_pad;
+        if (p > 0) {        // reflect images of this pixel in the padded plane (border-adjacent pixels only)
+            const int mx = mirror1(x, a.w, p);
+            if (mx > -1000) add8<KIND>(acc, a.gp, r.gp_row + (int64_t)(mx + p) * C);
+            if (r.gp_mrow >= 0) {
+                add8<KIND>(acc, a.gp, r.gp_mrow + (int64_t)(x + p) * C);
+                if (mx > -1000) add8<KIND>(acc, a.gp, r.gp_mrow + (int64_t)(mx + p) * C);
+            }
+        }
+    }
+    if (GR) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc.v[i] += in.gr.v[i];
+    }
+    if (MASK == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float z = in.yv.v[i] * scale.v[i] + shift.v[i];
+            if (!(z > 0.f)) acc.v[i] *= slope;
+        }
+    } else if (MASK == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (!(in.yv.v[i] > 0.f)) acc.v[i] *= slope;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ BwdRow make_row(const aclgan_block_bwd_args& a, int n, int y, int g) {
+    BwdRow r;
+    const int p = a.gp_pad, C = a.c;
+    const int64_t wpp = a.w + 2 * p, hpp = a.h + 2 * p;
+    r.gp_row = ((int64_t)n * hpp + y + p) * wpp * C + g * 8;
+    const int my = p > 0 ? mirror1(y, a.h, p) : -1000;
+    r.gp_mrow = my > -1000 ? ((int64_t)n * hpp + my + p) * wpp * C + g * 8 : -1;
+    r.dense_row = ((int64_t)n * a.h + y) * a.w * C + g * 8;
+    const int po = a.out.pad;
+    r.out_row = (((int64_t)n * (a.out.h + 2 * po) + y + po) * (a.out.w + 2 * po) + po) * a.out.c + g * 8;
+    return r;
+}
+
+// per-thread channel partials -> CTA -> atomics (fp64 statistics and / or fp32 bias gradient)
+__device__ __forceinline__ void cta_reduce16(float* red, const V8& s, const V8& q, int C, int g, int lane, int lanes, bool active,
+                                             double* stat, float* dbias, int dbias_n) {
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            red[((lane * C) + g * 8 + i) * 2] = s.v[i];
+            red[((lane * C) + g * 8 + i) * 2 + 1] = q.v[i];
+        }
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+        float x = 0.f, y = 0.f;
+        for (int l = 0; l < lanes; ++l) { x += red[(l * C + ch) * 2]; y += red[(l * C + ch) * 2 + 1]; }
+        if (stat != nullptr) {
+            atomicAdd(&stat[ch * 2], (double)x);
+            atomicAdd(&stat[ch * 2 + 1], (double)y);
+        }
+        if (dbias != nullptr && ch < dbias_n) atomicAdd(dbias + ch, x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward reduce
+template <int KIND, int MASK, int GP, int GR, int UNR>
+__global__ void __launch_bounds__(kThreads) bwd_reduce_rows_kernel(aclgan_block_bwd_args a, int rows_per_cta) {
+    extern __shared__ float red[];          // [lanes][C][2]
+    const int C = a.c, cg = C >> 3, lanes = kThreads / cg;
+    const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+    const int n = blockIdx.y;
+    const bool active = lane < lanes;
+    V8 s, q;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.v[i] = q.v[i] = 0.f;
+    if (active) {
+        const int64_t ci = (int64_t)n * C + g * 8;
+        const V8 scale = MASK == 1 ? coef8(a.scale, ci) : V8(), shift = MASK == 1 ? coef8(a.shift, ci) : V8();
+        V8 inv = coef8(a.inv, ci), nmi = coef8(a.mean, ci);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nmi.v[i] = -nmi.v[i] * inv.v[i];          // yhat = y * inv - mean * inv
+        const float slope = a.slope;
+        const int row_end = min(a.h, ((int)blockIdx.x + 1) * rows_per_cta);
+        for (int y = blockIdx.x * rows_per_cta; y < row_end; ++y) {
+            const BwdRow r = make_row(a, n, y, g);
+            for (int x0 = lane; x0 < a.w; x0 += lanes * UNR) {
+                PixRaw<KIND, MASK, 1, GP, GR> in[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) pix_raw<KIND, MASK, 1, GP, GR>(a, r, min(x0 + u * lanes, a.w - 1), C, in[u]);
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int x = x0 + u * lanes;
+                    if (x >= a.w) break;
+                    const V8 dz = pix_dz<KIND, MASK, 1, GP, GR>(a, r, x, C, in[u], scale, shift, slope);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        s.v[i] += dz.v[i];
+                        q.v[i] += dz.v[i] * (in[u].yv.v[i] * inv.v[i] + nmi.v[i]);
+                    }
+                }
+            }
+        }
+    }
+    cta_reduce16(red, s, q, C, g, lane, lanes, active, reinterpret_cast<double*>(a.sums) + (int64_t)n * C * 2, nullptr, 0);
+}
+
+// ------------------------------------------------------------------------------------------ backward apply
+// dy = ca*dz + cb*yhat + cc  (= ca*dz + B*y + Cc with B = cb*inv, Cc = cc - B*mean), written as the zero-bordered plane(s)
+template <int KIND, int PLANES, int MASK, int NORM, int GP, int GR, int DBIAS, int UNR>
+__global__ void __launch_bounds__(kThreads) bwd_apply_rows_kernel(aclgan_block_bwd_args a, int rows_per_cta) {
+    extern __shared__ float red[];
+    const int C = a.c, cg = C >> 3, lanes = kThreads / cg;
+    const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+    const int n = blockIdx.y;
+    const bool active = lane < lanes;
+    const int pz = a.dy.pad, hz = a.h + 2 * pz, wz = a.w + 2 * pz;
+    V8 s, q;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.v[i] = q.v[i] = 0.f;
+    if (active) {
+        const int64_t ci = (int64_t)n * C + g * 8;
+        const V8 scale = MASK == 1 ? coef8(a.scale, ci) : V8(), shift = MASK == 1 ? coef8(a.shift, ci) : V8();
+        V8 ca, cb, cc;
+        if (NORM) {
+            ca = coef8(a.ca, ci);
+            cb = coef8(a.cb, ci);
+            cc = coef8(a.cc, ci);
+            const V8 inv = coef8(a.inv, ci), mean = coef8(a.mean, ci);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                cb.v[i] *= inv.v[i];                    // B
+                cc.v[i] -= cb.v[i] * mean.v[i];         // Cc
+            }
+        }
+        const float slope = a.slope;
+        const int row_end = min(hz, ((int)blockIdx.x + 1) * rows_per_cta);
+        V8 zero;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) zero.v[i] = 0.f;
+        for (int Y = blockIdx.x * rows_per_cta; Y < row_end; ++Y) {
+            const int y = Y - pz;
+            const int64_t dst_row = ((int64_t)n * hz + Y) * wz * C + g * 8;
+            if (y < 0 || y >= a.h) {
+                for (int X = lane; X < wz; X += lanes) st8_planes<PLANES>(a.dy.data, dst_row + (int64_t)X * C, zero);
+                continue;
+            }
+            const BwdRow r = make_row(a, n, y, g);
+            for (int X0 = lane; X0 < wz; X0 += lanes * UNR) {
+                PixRaw<KIND, MASK, NORM, GP, GR> in[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) pix_raw<KIND, MASK, NORM, GP, GR>(a, r, min(max(X0 + u * lanes - pz, 0), a.w - 1), C, in[u]);
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int X = X0 + u * lanes;
+                    if (X >= wz) break;
+                    const int x = X - pz;
+                    if (x < 0 || x >= a.w) {
+                        st8_planes<PLANES>(a.dy.data, dst_row + (int64_t)X * C, zero);
+                        continue;
+                    }
+                    const V8 dz = pix_dz<KIND, MASK, NORM, GP, GR>(a, r, x, C, in[u], scale, shift, slope);
+                    V8 out;
+                    if (NORM) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) out.v[i] = ca.v[i] * dz.v[i] + (cb.v[i] * in[u].yv.v[i] + cc.v[i]);
+                    } else {
+                        out = dz;
+                    }
+                    if (DBIAS) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) s.v[i] += dz.v[i];
+                    }
+                    st8_planes<PLANES>(a.dy.data, dst_row + (int64_t)X * C, out);
+                }
+            }
+        }
+    }
+    if (DBIAS) cta_reduce16(red, s, q, C, g, lane, lanes, active, nullptr, reinterpret_cast<float*>(a.dbias), a.dbias_n);
+}
+
+static int rows_per_cta_for(int rows, int n_images) {
+    // about six CTAs per SM over all images: long enough to amortise the prologue / per-CTA atomics, short enough to balance
+    const int want = (6 * num_sms() + n_images - 1) / n_images;
+    int r = (rows + want - 1) / want;
+    return r < 1 ? 1 : r;
+}
+
+static bool rows_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ACLGAN_ELEMENTWISE_ROWS");
+        v = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
+template <int KIND, int PLANES, int ACT>
+static void launch_apply_res(const aclgan_apply_args* a, dim3 grid, int rpc, cudaStream_t st) {
+    if (a->has_res) norm_apply_rows_kernel<KIND, PLANES, ACT, 1, 4><<<grid, kThreads, 0, st>>>(*a, rpc);
+    else norm_apply_rows_kernel<KIND, PLANES, ACT, 0, 4><<<grid, kThreads, 0, st>>>(*a, rpc);
+}
+template <int KIND, int PLANES>
+static void launch_apply_act(const aclgan_apply_args* a, dim3 grid, int rpc, cudaStream_t st) {
+    if (a->act == ACLGAN_ACT_RELU) launch_apply_res<KIND, PLANES, 1>(a, grid, rpc, st);
+    else if (a->act == ACLGAN_ACT_LRELU) launch_apply_res<KIND, PLANES, 2>(a, grid, rpc, st);
+    else launch_apply_res<KIND, PLANES, 0>(a, grid, rpc, st);
+}
+
+template <int KIND, int MASK>
+static void launch_reduce_g(const aclgan_block_bwd_args* a, dim3 grid, int rpc, size_t smem, cudaStream_t st) {
+    if (a->gp != 0 && a->gr != 0) bwd_reduce_rows_kernel<KIND, MASK, 1, 1, 2><<<grid, kThreads, smem, st>>>(*a, rpc);
+    else if (a->gp != 0) bwd_reduce_rows_kernel<KIND, MASK, 1, 0, 2><<<grid, kThreads, smem, st>>>(*a, rpc);
+    else bwd_reduce_rows_kernel<KIND, MASK, 0, 1, 2><<<grid, kThreads, smem, st>>>(*a, rpc);
+}
+
+template <int KIND, int PLANES, int MASK, int NORM, int GP, int GR>
+static void launch_apply_bwd_db(const aclgan_block_bwd_args* a, dim3 grid, int rpc, size_t smem, cudaStream_t st) {
+    if (a->dbias != 0) bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 1, 2><<<grid, kThreads, smem, st>>>(*a, rpc);
+    else bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 0, 2><<<grid, kThreads, 0, st>>>(*a, rpc);
+}
+template <int KIND, int PLANES, int MASK, int NORM>
+static void launch_apply_bwd_g(const aclgan_block_bwd_args* a, dim3 grid, int rpc, size_t smem, cudaStream_t st) {
+    if (a->gp != 0 && a->gr != 0) launch_apply_bwd_db<KIND, PLANES, MASK, NORM, 1, 1>(a, grid, rpc, smem, st);
+    else if (a->gp != 0) launch_apply_bwd_db<KIND, PLANES, MASK, NORM, 1, 0>(a, grid, rpc, smem, st);
+    else launch_apply_bwd_db<KIND, PLANES, MASK, NORM, 0, 1>(a, grid, rpc, smem, st);
+}
+template <int KIND, int PLANES>
+static void launch_apply_bwd_mode(const aclgan_block_bwd_args* a, dim3 grid, int rpc, size_t smem, cudaStream_t st) {
+    if (a->norm) {
+        if (a->mask_mode == ACLGAN_MASK_FROM_Z) launch_apply_bwd_g<KIND, PLANES, 1, 1>(a, grid, rpc, smem, st);
+        else launch_apply_bwd_g<KIND, PLANES, 0, 1>(a, grid, rpc, smem, st);
+    } else {
+        if (a->mask_mode == ACLGAN_MASK_FROM_OUT) launch_apply_bwd_g<KIND, PLANES, 2, 0>(a, grid, rpc, smem, st);
+        else launch_apply_bwd_g<KIND, PLANES, 0, 0>(a, grid, rpc, smem, st);
+    }
+}
+
+}  // namespace
+
+int rows_norm_apply(const aclgan_apply_args* a, cudaStream_t st) {
+    if (!rows_enabled() || a->upsample != 1 || a->act == ACLGAN_ACT_TANH) return -100;
+    const int C = a->y.c, p = a->dst.pad;
+    if (C % 8 != 0 || C / 8 > kThreads || a->y.h <= p || a->y.w <= p || (a->y.kind != 0 && a->y.kind != 1)) return -100;
+    if (a->dst.planes != 1 && a->dst.planes != 2) return -100;
+    if (a->has_res && a->res.planes != a->dst.planes) return -100;
+    const int hp = a->y.h + 2 * p;
+    const int rpc = rows_per_cta_for(hp, a->y.n);
+    dim3 grid((hp + rpc - 1) / rpc, a->y.n);
+    if (a->y.kind == 0) {
+        if (a->dst.planes == 1) launch_apply_act<0, 1>(a, grid, rpc, st); else launch_apply_act<0, 2>(a, grid, rpc, st);
+    } else {
+        if (a->dst.planes == 1) launch_apply_act<1, 1>(a, grid, rpc, st); else launch_apply_act<1, 2>(a, grid, rpc, st);
+    }
+    return (int)cudaGetLastError();
+}
+
+static bool bwd_rows_ok(const aclgan_block_bwd_args* a) {
+    if (!rows_enabled() || a->upsample != 1) return false;
+    const int C = a->c, p = a->gp_pad;
+    if (C % 8 != 0 || C / 8 > kThreads) return false;
+    if (a->gp == 0 && a->gr == 0) return false;
+    if ((a->mask_mode == ACLGAN_MASK_FROM_Z || a->norm) && a->y.kind != a->g_kind) return false;
+    if (a->gp != 0 && (a->h <= 2 * p + 1 || a->w <= 2 * p + 1)) return false;
+    if (a->mask_mode == ACLGAN_MASK_FROM_Z && !a->norm) return false;
+    if (a->mask_mode == ACLGAN_MASK_FROM_OUT && a->norm) return false;
+    return a->g_kind == 0 || a->g_kind == 1;
+}
+
+int rows_bwd_reduce(const aclgan_block_bwd_args* a, cudaStream_t st) {
+    if (!bwd_rows_ok(a) || !a->norm) return -100;
+    const int C = a->c, lanes = kThreads / (C / 8);
+    const int rpc = rows_per_cta_for(a->h, a->n);
+    dim3 grid((a->h + rpc - 1) / rpc, a->n);
+    const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
+    const bool z = a->mask_mode == ACLGAN_MASK_FROM_Z;
+    if (a->g_kind == 0) {
+        if (z) launch_reduce_g<0, 1>(a, grid, rpc, smem, st); else launch_reduce_g<0, 0>(a, grid, rpc, smem, st);
+    } else {
+        if (z) launch_reduce_g<1, 1>(a, grid, rpc, smem, st); else launch_reduce_g<1, 0>(a, grid, rpc, smem, st);
+    }
+    return (int)cudaGetLastError();
+}
+
+int rows_bwd_apply(const aclgan_block_bwd_args* a, cudaStream_t st) {
+    if (!bwd_rows_ok(a)) return -100;
+    if (a->dy.planes != 1 && a->dy.planes != 2) return -100;
+    const int C = a->c, lanes = kThreads / (C / 8);
+    const int hz = a->h + 2 * a->dy.pad;
+    const int rpc = rows_per_cta_for(hz, a->n);
+    dim3 grid((hz + rpc - 1) / rpc, a->n);
+    const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
+    if (a->g_kind == 0) {
+        if (a->dy.planes == 1) launch_apply_bwd_mode<0, 1>(a, grid, rpc, smem, st); else launch_apply_bwd_mode<0, 2>(a, grid, rpc, smem, st);
+    } else {
+        if (a->dy.planes == 1) launch_apply_bwd_mode<1, 1>(a, grid, rpc, smem, st); else launch_apply_bwd_mode<1, 2>(a, grid, rpc, smem, st);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace aclgan

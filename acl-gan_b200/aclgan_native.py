@@ -324,6 +324,7 @@ def _declare(L):
     L.aclgan_up_fold_wgrad.argtypes = [C.POINTER(UpFoldWgradArgs), C.c_void_p]
     L.aclgan_pack_nchw.argtypes = [C.c_uint64, C.c_int32, C.POINTER(Act), C.c_void_p]
     L.aclgan_unpack_plane.argtypes = [C.POINTER(Act), C.c_int32, C.c_uint64, C.c_void_p]
+    L.aclgan_augment_u8.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.aclgan_stats_to_bias.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.aclgan_zero.argtypes = [C.c_uint64, C.c_int64, C.c_void_p]
     L.aclgan_copy.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p]

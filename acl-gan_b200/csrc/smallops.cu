@@ -424,6 +424,23 @@ __global__ void axpby_kernel<__nv_bfloat16>(__nv_bfloat16* dst, const __nv_bfloa
         dst[i] = __float2bfloat16_rn(alpha * __bfloat162float(a[i]) + (b != nullptr ? beta * __bfloat162float(b[i]) : 0.f));
 }
 
+// ------------------------------------------------------------------------------------------ input pipeline
+// uint8 NHWC batch (decoded / resized / cropped by the loader workers) -> fp32 NCHW in [-1, 1] with per-sample horizontal flip:
+// transforms.RandomHorizontalFlip + ToTensor + Normalize(0.5, 0.5) (reference utils.py:83-100) with the same rounding sequence
+// (u8 -> float, / 255, - 0.5, / 0.5), so the result is bit-identical to the torchvision path
+__global__ void augment_u8_kernel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ flip, float* __restrict__ dst, int n,
+                                  int h, int w) {
+    const int64_t total = (int64_t)n * h * w;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int x = (int)(t % w), y = (int)((t / w) % h), i = (int)(t / ((int64_t)w * h));
+    const int xs = (flip != nullptr && flip[i]) ? w - 1 - x : x;
+    const uint8_t* s = src + (((int64_t)i * h + y) * w + xs) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        dst[(((int64_t)i * 3 + c) * h + y) * w + x] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)s[c], 255.f), 0.5f), 0.5f);
+}
+
 // dst[c] += sum_n sums[n][c][0] (fp64 per-(n, c) sums of the generic backward-reduce kernel -> fp32 conv-bias gradient)
 __global__ void stats_to_bias_kernel(const double* __restrict__ sums, float* __restrict__ dst, int n, int c, int c_valid) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
@@ -599,5 +616,13 @@ extern "C" int aclgan_stats_to_bias(uint64_t sums, uint64_t dst, int32_t n, int3
     if (n < 1 || c_valid < 1 || c_valid > c) return ACLGAN_ERR_SHAPE;
     stats_to_bias_kernel<<<(c_valid + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(sums),
                                                                                 reinterpret_cast<float*>(dst), n, c, c_valid);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int aclgan_augment_u8(uint64_t src, uint64_t flip, uint64_t dst, int32_t n, int32_t h, int32_t w, void* stream) {
+    if (n < 1 || h < 1 || w < 1) return ACLGAN_ERR_SHAPE;
+    const int64_t total = (int64_t)n * h * w;
+    augment_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint8_t*>(src), reinterpret_cast<const uint8_t*>(flip), reinterpret_cast<float*>(dst), n, h, w);
     return (int)cudaGetLastError();
 }

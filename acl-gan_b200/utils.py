@@ -145,38 +145,125 @@ def write_html(filename, iterations, image_save_iterations, image_directory, all
 
 
 # ------------------------------------------------------------------------------------------ data
-def get_data_loader_folder(input_folder, batch_size, train, new_size=None, height=256, width=256, num_workers=4,
-                           crop=True):
-    from torch.utils.data import DataLoader
+# Two pipelines behind the reference's factory signatures (utils.py:43-100):
+#  * host (the reference's): workers decode, Resize, RandomCrop, RandomHorizontalFlip, ToTensor, Normalize -> fp32 NCHW batches;
+#  * device (`gpu_augment`, default whenever CUDA is available): workers only decode / Resize / RandomCrop and hand over uint8
+#    HWC images (4x fewer bytes to collate, pin and copy); `DeviceLoader` copies each pinned batch on a side stream one batch
+#    ahead of the consumer and runs `aclgan_augment_u8` (flip + ToTensor + Normalize + NHWC -> NCHW, bit-identical to the
+#    torchvision ops).  It yields CUDA tensors, so the `.cuda()` of train.py:67 is a no-op.
+def _transform_list(train, new_size, height, width, crop, device_tail):
     from torchvision import transforms
-    from data import ImageFolder
-    tf = [transforms.ToTensor(), transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))]
-    if crop:
-        tf = [transforms.RandomCrop((height, width))] + tf
+    tf = []
     if new_size is not None:
-        tf = [transforms.Resize(new_size)] + tf
-    if train:
-        tf = [transforms.RandomHorizontalFlip()] + tf
-    dataset = ImageFolder(input_folder, transform=transforms.Compose(tf))
-    return DataLoader(dataset=dataset, batch_size=batch_size, shuffle=train, drop_last=True,
-                      num_workers=num_workers, pin_memory=True)
+        tf.append(transforms.Resize(new_size))
+    if crop:
+        tf.append(transforms.RandomCrop((height, width)))
+    if device_tail:
+        tf.append(_ToUint8HWC())
+    else:
+        if train:
+            tf = [transforms.RandomHorizontalFlip()] + tf
+        tf += [transforms.ToTensor(), transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))]
+    return transforms.Compose(tf)
+
+
+class _ToUint8HWC:
+    """PIL image -> uint8 tensor [H, W, 3] (no float conversion on the host)"""
+
+    def __call__(self, img):
+        import numpy as np
+        return torch.from_numpy(np.asarray(img, dtype=np.uint8).copy())
+
+
+class _Reformat(torch.utils.data.Dataset):
+    """the same files as `base` through another transform (the uint8 view the device pipeline's workers read)"""
+
+    def __init__(self, base, transform):
+        import copy
+        self.ds = copy.copy(base)
+        self.ds.transform = transform
+
+    def __getitem__(self, i):
+        return self.ds[i]
+
+    def __len__(self):
+        return len(self.ds)
+
+
+class DeviceLoader:
+    """Iterates a DataLoader of uint8 NHWC batches and yields normalised fp32 NCHW CUDA tensors, one batch ahead: the pinned
+    host batch is copied on a side stream while the previous step computes, then `aclgan_augment_u8` applies the per-sample
+    horizontal flip (drawn from the main-process torch RNG, p = 0.5 as transforms.RandomHorizontalFlip), ToTensor and
+    Normalize.  `.dataset` is the reference-format dataset (train.py:45-48 indexes it for the display images)."""
+
+    def __init__(self, loader, dataset, train, device="cuda"):
+        self.loader, self.dataset, self.train, self.device = loader, dataset, train, torch.device(device)
+        self.batch_size = loader.batch_size
+        self._stream = None
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _stage(self, batch):
+        import ctypes as C
+        import aclgan_native as N
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(self.device)
+        n, h, w, c = batch.shape
+        assert c == 3 and batch.dtype == torch.uint8
+        flip = (torch.rand(n) < 0.5).to(torch.uint8) if self.train else None
+        with torch.cuda.stream(self._stream):
+            src = batch.to(self.device, non_blocking=True)
+            fl = flip.to(self.device, non_blocking=True) if flip is not None else None
+            out = torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device)
+            N.check(N.lib().aclgan_augment_u8(src.data_ptr(), fl.data_ptr() if fl is not None else 0, out.data_ptr(), n, h, w,
+                                              C.c_void_p(self._stream.cuda_stream)), "augment_u8")
+            ev = torch.cuda.Event()
+            ev.record(self._stream)
+        return out, ev, (src, fl)
+
+    def __iter__(self):
+        it = iter(self.loader)
+        nxt = None
+        try:
+            nxt = self._stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            out, ev, keep = nxt
+            try:
+                nxt = self._stage(next(it))
+            except StopIteration:
+                nxt = None
+            torch.cuda.current_stream().wait_event(ev)
+            out.record_stream(torch.cuda.current_stream())
+            yield out
+
+
+def _make_loader(dataset_cls, ds_args, batch_size, train, new_size, height, width, num_workers, crop, gpu_augment):
+    from torch.utils.data import DataLoader
+    ref_ds = dataset_cls(*ds_args, transform=_transform_list(train, new_size, height, width, crop, False))
+    if gpu_augment is None:
+        gpu_augment = torch.cuda.is_available()
+    if not gpu_augment:
+        return DataLoader(dataset=ref_ds, batch_size=batch_size, shuffle=train, drop_last=True, num_workers=num_workers,
+                          pin_memory=True)
+    raw = _Reformat(ref_ds, _transform_list(train, new_size, height, width, crop, True))
+    loader = DataLoader(dataset=raw, batch_size=batch_size, shuffle=train, drop_last=True, num_workers=num_workers,
+                        pin_memory=True, persistent_workers=num_workers > 0, prefetch_factor=4 if num_workers > 0 else None)
+    return DeviceLoader(loader, ref_ds, train)
+
+
+def get_data_loader_folder(input_folder, batch_size, train, new_size=None, height=256, width=256, num_workers=4,
+                           crop=True, gpu_augment=None):
+    from data import ImageFolder
+    return _make_loader(ImageFolder, (input_folder,), batch_size, train, new_size, height, width, num_workers, crop, gpu_augment)
 
 
 def get_data_loader_list(root, file_list, batch_size, train, new_size=None, height=256, width=256, num_workers=4,
-                         crop=True):
-    from torch.utils.data import DataLoader
-    from torchvision import transforms
+                         crop=True, gpu_augment=None):
     from data import ImageFilelist
-    tf = [transforms.ToTensor(), transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))]
-    if crop:
-        tf = [transforms.RandomCrop((height, width))] + tf
-    if new_size is not None:
-        tf = [transforms.Resize(new_size)] + tf
-    if train:
-        tf = [transforms.RandomHorizontalFlip()] + tf
-    dataset = ImageFilelist(root, file_list, transform=transforms.Compose(tf))
-    return DataLoader(dataset=dataset, batch_size=batch_size, shuffle=train, drop_last=True,
-                      num_workers=num_workers, pin_memory=True)
+    return _make_loader(ImageFilelist, (root, file_list), batch_size, train, new_size, height, width, num_workers, crop, gpu_augment)
 
 
 def get_all_data_loaders(conf):
@@ -184,14 +271,16 @@ def get_all_data_loaders(conf):
     size_a = conf.get("new_size", conf.get("new_size_a"))
     size_b = conf.get("new_size", conf.get("new_size_b"))
     h, w = conf["crop_image_height"], conf["crop_image_width"]
+    ga = conf.get("gpu_augment")            # None: device pipeline whenever CUDA is available; 0 / 1 force
+    ga = None if ga is None else bool(ga)
+    # test loaders crop to new_size x new_size (reference utils.py:57-60), train loaders to the configured crop
     if "data_root" in conf:
         root = conf["data_root"]
-        # test loaders crop to new_size x new_size (reference utils.py:57-60), train loaders to the configured crop
         mk = lambda sub, train, size: get_data_loader_folder(os.path.join(root, sub), bs, train, size,
-                                                             h if train else size, w if train else size, nw, True)
+                                                             h if train else size, w if train else size, nw, True, ga)
         return mk("trainA", True, size_a), mk("trainB", True, size_b), mk("testA", False, size_a), mk("testB", False, size_b)
     mk = lambda folder, lst, train, size: get_data_loader_list(conf[folder], conf[lst], bs, train, size,
-                                                               h if train else size, w if train else size, nw, True)
+                                                               h if train else size, w if train else size, nw, True, ga)
     return (mk("data_folder_train_a", "data_list_train_a", True, size_a),
             mk("data_folder_train_b", "data_list_train_b", True, size_b),
             mk("data_folder_test_a", "data_list_test_a", False, size_a),

@@ -528,6 +528,10 @@ int aclgan_focus_grad(const aclgan_focus_grad_args* a, void* stream);
 int aclgan_loss_combine(uint64_t acc /* double[K] */, uint64_t M /* fp32 [J][K] */, uint64_t out /* fp32 [J] */, int32_t J,
                         int32_t K, void* stream);
 
+/* input pipeline (reference utils.py:43-100): uint8 NHWC batch [n][h][w][3] -> fp32 NCHW [n][3][h][w] in [-1, 1] with an
+ * optional per-sample horizontal flip (flip: uint8 [n] or 0) = RandomHorizontalFlip + ToTensor + Normalize(0.5, 0.5), bit-identical
+ * to the torchvision ops (u8 -> float, / 255, - 0.5, / 0.5) */
+int aclgan_augment_u8(uint64_t src, uint64_t flip, uint64_t dst, int32_t n, int32_t h, int32_t w, void* stream);
 /* dst[ch] += sum_n sums[n][ch][0] for ch < c_valid: conv-bias gradient of a no-norm block from the T1 sums of
  * aclgan_block_bwd_reduce (planes too small for the fused-bias apply kernel) */
 int aclgan_stats_to_bias(uint64_t sums /* double [n][c][2] */, uint64_t dst /* fp32 [c_valid] */, int32_t n, int32_t c,

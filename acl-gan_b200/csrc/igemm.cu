@@ -50,6 +50,7 @@ struct alignas(64) IgemmKParams {
     CUtensorMap b_seg[2];                           // rank 3 (k element, weight row, tap): box = 64 x rows x seg_taps
     int seg_rows, num_segs, seg_taps;
     int seg_a_bytes, seg_btile_bytes, seg_stage_bytes, seg_ns;   // shared-memory ring geometry chosen by the host
+    int seg_msub;   // 128-pixel tiles per CTA and work item (1 | 2): with 2 every staged weight tile feeds two accumulators
     int epi_direct;
     long long* prof;                                // perf triage: per-CTA role timers [cta][8] (clock cycles) or null
     int seg_dx[16], seg_dy[16];
@@ -989,13 +990,20 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Work item = m_sub (1 | 2) M tiles per CTA x one N tile.  With m_sub = 2 the weight tiles of a stage (3/4 of the staged
+    // bytes of the 3x3 256->256 layer, whose two-deep ring runs at the ~42 B/clk/SM L2->SM limit) feed two accumulators, and
+    // the 137 tile pairs of a batch-8 res-block conv become 69 items = ONE wave on the 74 clusters instead of 1.85.
+    const int m_sub = P.seg_msub;
+    const int tile_mul = PAIR ? 2 : 1;
     const int m_tiles = P.tiles_x * P.tiles_y * P.tiles_z;
-    const int m_items = PAIR ? (m_tiles + 1) / 2 : m_tiles;
+    const int m_items = (m_tiles + tile_mul * m_sub - 1) / (tile_mul * m_sub);
     const int total_items = m_items * P.n_tiles;
     const int n_workers = PAIR ? gridDim.x / 2 : gridDim.x;
     const int worker = PAIR ? blockIdx.x / 2 : blockIdx.x;
-    const uint32_t stage_tx = (uint32_t)(P.seg_a_bytes + P.seg_taps * P.seg_btile_bytes) * (PAIR ? 2u : 1u);
+    const uint32_t stage_tx = (uint32_t)(m_sub * P.seg_a_bytes + P.seg_taps * P.seg_btile_bytes) * (PAIR ? 2u : 1u);
     const int n_rounds = P.nseg * P.cchunks * P.num_segs;       // stages per work item
+    const int set_cols = m_sub * col_stride;                    // TMEM columns of one accumulator set
+    const int acc_sets = (2 * set_cols <= 512) ? 2 : 1;         // double-buffered across items when they fit
 
     if (warp == 0 && lane == 0) {
         // ---------------- TMA producer ----------------
@@ -1005,11 +1013,14 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
         const long long t_begin = prof ? clock64() : 0;
         for (int item = worker; item < total_items; item += n_workers) {
             const int nt = item % P.n_tiles;
-            int mt = (item / P.n_tiles) * (PAIR ? 2 : 1) + (int)rank;   // past-the-end tile: zero fill, never stored
-            const int x0 = (mt % P.tiles_x) * P.box_x;
-            mt /= P.tiles_x;
-            const int y0 = (mt % P.tiles_y) * P.box_y;
-            const int z0 = (mt / P.tiles_y) * P.box_z;
+            int x0[2], y0[2], z0[2];
+            for (int sub = 0; sub < m_sub; ++sub) {
+                int mt = ((item / P.n_tiles) * m_sub + sub) * tile_mul + (int)rank;   // past-the-end tile: zero fill, never stored
+                x0[sub] = (mt % P.tiles_x) * P.box_x;
+                mt /= P.tiles_x;
+                y0[sub] = (mt % P.tiles_y) * P.box_y;
+                z0[sub] = (mt / P.tiles_y) * P.box_z;
+            }
             const int brow = nt * P.block_n + (int)rank * b_rows;
 #pragma unroll 1
             for (int seg = 0; seg < P.nseg; ++seg) {
@@ -1023,16 +1034,20 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
                         mbar_wait(&empty_bar[st], ph ^ 1);
                         if (prof) t_wait += clock64() - tw;
                         uint8_t* sa = smem + st * P.seg_stage_bytes;
-                        uint8_t* sb = sa + P.seg_a_bytes;
+                        uint8_t* sb = sa + m_sub * P.seg_a_bytes;
                         if (P.debug == 1) {          // MMA without TMA traffic
                             if (!PAIR || leader) mbar_arrive(&full_bar[st]); else mbar_arrive_leader(&full_bar[st]);
                         } else if (PAIR) {
                             if (leader) mbar_arrive_expect_tx(&full_bar[st], stage_tx); else mbar_arrive_leader(&full_bar[st]);
-                            tma_load_4d_pair(sa, am, &full_bar[st], cc * 64, x0 + P.seg_dx[sg], y0 + P.seg_dy[sg], z0);
+                            for (int sub = 0; sub < m_sub; ++sub)
+                                tma_load_4d_pair(sa + sub * P.seg_a_bytes, am, &full_bar[st], cc * 64, x0[sub] + P.seg_dx[sg],
+                                                 y0[sub] + P.seg_dy[sg], z0[sub]);
                             tma_load_3d_pair(sb, bm, &full_bar[st], cc * 64, brow, sg * P.seg_taps);
                         } else {
                             mbar_arrive_expect_tx(&full_bar[st], stage_tx);
-                            tma_load_4d(sa, am, &full_bar[st], cc * 64, x0 + P.seg_dx[sg], y0 + P.seg_dy[sg], z0);
+                            for (int sub = 0; sub < m_sub; ++sub)
+                                tma_load_4d(sa + sub * P.seg_a_bytes, am, &full_bar[st], cc * 64, x0[sub] + P.seg_dx[sg],
+                                            y0[sub] + P.seg_dy[sg], z0[sub]);
                             tma_load_3d(sb, bm, &full_bar[st], cc * 64, brow, sg * P.seg_taps);
                         }
                         if (++st == P.seg_ns) { st = 0; ph ^= 1; }
@@ -1054,13 +1069,13 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
         const int64_t rstep8 = P.seg_taps > 1 ? (int64_t)(P.tap_row[1] - P.tap_row[0]) * 8 : 0;   // rows -> descriptor units
         const uint32_t bt16 = (uint32_t)P.seg_btile_bytes >> 4;
         for (int item = worker; item < total_items; item += n_workers, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
+            const int acc = it % acc_sets;
+            const uint32_t acc_phase = (it / acc_sets) & 1;
             long long tw = prof ? clock64() : 0;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             if (prof) t_wacc += clock64() - tw;
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * col_stride;
+            const uint32_t d_tmem = tmem_base + acc * set_cols;
             uint32_t accum = 0;
 #pragma unroll 1
             for (int r = 0; r < n_rounds; ++r) {
@@ -1070,18 +1085,22 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
                 if (prof) t_wfull += clock64() - tw;
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + st * P.seg_stage_bytes);
-                const uint32_t sb = sa + P.seg_a_bytes;
+                const uint32_t sb = sa + m_sub * P.seg_a_bytes;
                 if (P.debug != 2) {          // (2 = TMA traffic without MMA)
                     // A descriptor of tap j = stage base + (row0 + j * rstep) rows; B descriptor = base + j weight tiles
-                    const uint64_t da0 = make_smem_desc_sw128(sa, 16, 1024) + (uint64_t)(row0 * 8);
                     const uint64_t db0 = make_smem_desc_sw128(sb, 16, 1024);
-                    switch (P.seg_taps) {
-                        case 3: issue_row<3, PAIR>(d_tmem, da0, db0, rstep8, bt16, idesc, accum); break;
-                        case 5: issue_row<5, PAIR>(d_tmem, da0, db0, rstep8, bt16, idesc, accum); break;
-                        case 7: issue_row<7, PAIR>(d_tmem, da0, db0, rstep8, bt16, idesc, accum); break;
-                        default:
 #pragma unroll 1
-                            for (int j = 0; j < P.seg_taps; ++j) issue_row<1, PAIR>(d_tmem, da0 + (int64_t)j * rstep8, db0 + (uint64_t)j * bt16, 0, 0, idesc, accum);
+                    for (int sub = 0; sub < m_sub; ++sub) {
+                        const uint64_t da0 = make_smem_desc_sw128(sa + sub * P.seg_a_bytes, 16, 1024) + (uint64_t)(row0 * 8);
+                        const uint32_t dt = d_tmem + sub * col_stride;
+                        switch (P.seg_taps) {
+                            case 3: issue_row<3, PAIR>(dt, da0, db0, rstep8, bt16, idesc, accum); break;
+                            case 5: issue_row<5, PAIR>(dt, da0, db0, rstep8, bt16, idesc, accum); break;
+                            case 7: issue_row<7, PAIR>(dt, da0, db0, rstep8, bt16, idesc, accum); break;
+                            default:
+#pragma unroll 1
+                                for (int j = 0; j < P.seg_taps; ++j) issue_row<1, PAIR>(dt, da0 + (int64_t)j * rstep8, db0 + (uint64_t)j * bt16, 0, 0, idesc, accum);
+                        }
                     }
                     accum = 1;
                 }
@@ -1103,48 +1122,51 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
         long long t_wt = 0;
         const long long t_begin = prof ? clock64() : 0;
         for (int item = worker; item < total_items; item += n_workers, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
+            const int acc = it % acc_sets;
+            const uint32_t acc_phase = (it / acc_sets) & 1;
             const int nt = item % P.n_tiles;
-            int mt = (item / P.n_tiles) * (PAIR ? 2 : 1) + (int)rank;
-            const bool sub_ok = mt < m_tiles;
-            const int tx = mt % P.tiles_x;
-            mt /= P.tiles_x;
-            const int ty = mt % P.tiles_y;
-            const int tz = mt / P.tiles_y;
-            RowCtx rc;
-            if (P.flat) {
-                const int64_t qq = (int64_t)tx * P.box_x + row;
-                rc.z = (int)(qq / P.flat_img);
-                const int rem = (int)(qq - (int64_t)rc.z * P.flat_img);
-                rc.y = rem / P.flat_w;
-                rc.x = rem - rc.y * P.flat_w;
-            } else {
-                rc.x = tx * P.box_x + row % P.box_x;
-                rc.y = ty * P.box_y + (row / P.box_x) % P.box_y;
-                rc.z = tz * P.box_z + row / (P.box_x * P.box_y);
-            }
-            rc.valid = sub_ok && (rc.x < o.W) && (rc.y < o.H) && (rc.z < o.N) && !ring_pixel(o, rc.x, rc.y);
-            rc.pix0 = o.off + image_off(o, rc.z) + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
-            rc.ny = mirror_coords(rc.y, o.H, o.mirror, rc.ys);
-            rc.nx = mirror_coords(rc.x, o.W, o.mirror, rc.xs);
             const long long tw = prof ? clock64() : 0;
             mbar_wait(&tfull_bar[acc], acc_phase);
             if (prof) t_wt += clock64() - tw;
             tc_fence_after();
-            const uint32_t t_row = tmem_base + acc * col_stride + ((uint32_t)(q * 32) << 16);
-            const int n0 = nt * P.block_n;
-            const int group = (o.kind == ACLGAN_OUT_F32) ? 32 : 64;
-            const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) && (o.d2s_c % group == 0) && (n0 + P.block_n <= o.C) &&
-                              (o.act != ACLGAN_ACT_TANH);
-            StatCtx sc;
-            if (o.stats != 0) sc = make_stat_ctx(P, tx, tz, q, lane, rc);
-            const long long te = prof ? clock64() : 0;
-            if (fast) epilogue_tile_fast(ea, t_row, n0, rc, stage_out + q * 8192, lane, o.stats != 0 ? sc.rb : 32,
-                                         (prof && warp == 4) ? P.prof + blockIdx.x * 16 + 8 : nullptr);
-            else epilogue_tile_generic(ea, t_row, n0, rc);
-            if (o.stats != 0) stats_tile_end(ea, stage_out, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
-            if (prof && warp == 4 && lane == 0) P.prof[blockIdx.x * 16 + 7] += clock64() - te;
+#pragma unroll 1
+            for (int sub = 0; sub < m_sub; ++sub) {
+                int mt = ((item / P.n_tiles) * m_sub + sub) * tile_mul + (int)rank;
+                const bool sub_ok = mt < m_tiles;
+                const int tx = mt % P.tiles_x;
+                mt /= P.tiles_x;
+                const int ty = mt % P.tiles_y;
+                const int tz = mt / P.tiles_y;
+                RowCtx rc;
+                if (P.flat) {
+                    const int64_t qq = (int64_t)tx * P.box_x + row;
+                    rc.z = (int)(qq / P.flat_img);
+                    const int rem = (int)(qq - (int64_t)rc.z * P.flat_img);
+                    rc.y = rem / P.flat_w;
+                    rc.x = rem - rc.y * P.flat_w;
+                } else {
+                    rc.x = tx * P.box_x + row % P.box_x;
+                    rc.y = ty * P.box_y + (row / P.box_x) % P.box_y;
+                    rc.z = tz * P.box_z + row / (P.box_x * P.box_y);
+                }
+                rc.valid = sub_ok && (rc.x < o.W) && (rc.y < o.H) && (rc.z < o.N) && !ring_pixel(o, rc.x, rc.y);
+                rc.pix0 = o.off + image_off(o, rc.z) + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
+                rc.ny = mirror_coords(rc.y, o.H, o.mirror, rc.ys);
+                rc.nx = mirror_coords(rc.x, o.W, o.mirror, rc.xs);
+                const uint32_t t_row = tmem_base + acc * set_cols + sub * col_stride + ((uint32_t)(q * 32) << 16);
+                const int n0 = nt * P.block_n;
+                const int group = (o.kind == ACLGAN_OUT_F32) ? 32 : 64;
+                const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) && (o.d2s_c % group == 0) &&
+                                  (n0 + P.block_n <= o.C) && (o.act != ACLGAN_ACT_TANH);
+                StatCtx sc;
+                if (o.stats != 0) sc = make_stat_ctx(P, tx, tz, q, lane, rc);
+                const long long te = prof ? clock64() : 0;
+                if (fast) epilogue_tile_fast(ea, t_row, n0, rc, stage_out + q * 8192, lane, o.stats != 0 ? sc.rb : 32,
+                                             (prof && warp == 4) ? P.prof + blockIdx.x * 16 + 8 : nullptr);
+                else epilogue_tile_generic(ea, t_row, n0, rc);
+                if (o.stats != 0) stats_tile_end(ea, stage_out, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
+                if (prof && warp == 4 && lane == 0) P.prof[blockIdx.x * 16 + 7] += clock64() - te;
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -1242,6 +1264,7 @@ static int fill_kparams(const aclgan_igemm_plan* pl, IgemmKParams* kp) {
     for (int i = 0; i < 16; ++i) { kp->seg_dx[i] = pl->seg_dx[i]; kp->seg_dy[i] = pl->seg_dy[i]; }
     for (int t = 0; t < ACLGAN_MAX_TAPS; ++t) kp->tap_row[t] = pl->tap_row[t];
     kp->seg_a_bytes = kp->seg_btile_bytes = kp->seg_stage_bytes = kp->seg_ns = 0;
+    kp->seg_msub = 1;
     kp->prof = g_prof;
     {
         const char* ed = getenv("ACLGAN_EPI_DIRECT");
@@ -1299,19 +1322,36 @@ static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repea
     if (plan->planes == 1) { kp.a_seg[1] = kp.a_seg[0]; kp.b_seg[1] = kp.b_seg[0]; }
     kp.seg_a_bytes = plan->seg_rows * 128;
     kp.seg_btile_bytes = b_rows * 128;
-    kp.seg_stage_bytes = kp.seg_a_bytes + plan->seg_taps * kp.seg_btile_bytes;
-    // shared memory requested per CTA: not all of it, so that an element-wise CTA of another chain (<= 24 KB) can be
-    // co-resident on the SM and run under the tensor pipe's shadow (env ACLGAN_SEG_SMEM_KB overrides)
-    static int seg_smem = 0;
-    if (seg_smem == 0) {
-        const char* e = getenv("ACLGAN_SEG_SMEM_KB");
-        seg_smem = (e != nullptr ? atoi(e) : 176) * 1024;
-        if (seg_smem > kSegSmemBytes || seg_smem < 96 * 1024) seg_smem = kSegSmemBytes;
+    // Two M tiles per CTA and work item (m_sub = 2): every staged weight tile feeds two accumulators (half the weight bytes per
+    // FLOP through the ~42 B/clk/SM L2->SM path that bounds the two-deep ring of the N = 256 layers) and the tile count per
+    // wave doubles (batch-8 res-block conv: 137 tile pairs = 69 items = ONE wave on 74 clusters instead of 1.85).  Needs
+    // 2 * block_n <= 512 TMEM columns and the whole shared memory (two stages of 2 A segments + the row's weight tiles), so it is
+    // used for CTA pairs with more than one wave of work; env ACLGAN_SEG_MSUB=1|2 overrides.
+    const int pair_items1 = ((m_tiles + 1) / 2) * plan->n_tiles;
+    int m_sub = (pair && 2 * plan->block_n <= 512 && plan->block_n >= 128 && pair_items1 > num_sms() / 2) ? 2 : 1;
+    {
+        const char* e = getenv("ACLGAN_SEG_MSUB");
+        if (e != nullptr) m_sub = (atoi(e) == 2 && 2 * plan->block_n <= 512) ? 2 : 1;
     }
-    const int budget = seg_smem - 1024 - kStageOutBytes - 512;
-    int ns = budget / kp.seg_stage_bytes;
+    // shared memory requested per CTA: not all of it when it is not needed, so that an element-wise CTA of another chain
+    // (<= 24 KB) can be co-resident on the SM and run under the tensor pipe's shadow (env ACLGAN_SEG_SMEM_KB overrides)
+    static int seg_smem_default = 0;
+    if (seg_smem_default == 0) {
+        const char* e = getenv("ACLGAN_SEG_SMEM_KB");
+        seg_smem_default = (e != nullptr ? atoi(e) : 176) * 1024;
+        if (seg_smem_default > kSegSmemBytes || seg_smem_default < 96 * 1024) seg_smem_default = kSegSmemBytes;
+    }
+    int seg_smem = seg_smem_default, ns = 0;
+    for (;;) {
+        kp.seg_msub = m_sub;
+        kp.seg_stage_bytes = m_sub * kp.seg_a_bytes + plan->seg_taps * kp.seg_btile_bytes;
+        ns = (seg_smem - 1024 - kStageOutBytes - 512) / kp.seg_stage_bytes;
+        if (ns >= 2) break;
+        if (seg_smem < kSegSmemBytes) { seg_smem = kSegSmemBytes; continue; }      // m_sub = 2 stages need the whole budget
+        if (m_sub == 2) { m_sub = 1; seg_smem = seg_smem_default; continue; }
+        return -100;
+    }
     if (ns > kSegMaxStages) ns = kSegMaxStages;
-    if (ns < 2) return -100;
     kp.seg_ns = ns;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1322,12 +1362,12 @@ static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repea
         attr_set = true;
     }
     if (pair) {
-        const int items = ((m_tiles + 1) / 2) * plan->n_tiles;
+        const int items = ((m_tiles + 2 * m_sub - 1) / (2 * m_sub)) * plan->n_tiles;
         int clusters = num_sms() / 2;
         if (items < clusters) clusters = items;
         for (int i = 0; i < repeat; ++i) igemm_seg_pair_kernel<<<2 * clusters, kThreads, seg_smem, stream>>>(kp);
     } else {
-        const int items = m_tiles * plan->n_tiles;
+        const int items = ((m_tiles + m_sub - 1) / m_sub) * plan->n_tiles;
         if (items <= 0) return ACLGAN_OK;
         const int grid = items < num_sms() ? items : num_sms();
         for (int i = 0; i < repeat; ++i) igemm_seg_kernel<<<grid, kThreads, seg_smem, stream>>>(kp);

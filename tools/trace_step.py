@@ -65,3 +65,23 @@ print("   buckets (us): " + "  ".join("[%g,%g)" % (lo, hi) for lo, hi in zip(edg
 print("-- longest launches")
 for s, e, name in sorted(ks, key=lambda t: t[0] - t[1])[:25]:
     print("%9.1f us  %s" % (e - s, name[:100]))
+# concurrency profile: how much of the span runs 0 / 1 / 2 / ... kernels at once, and what runs ALONE (the serial sections)
+evts = sorted([(s, 1, name) for s, e, name in ks] + [(e, -1, name) for s, e, name in ks])
+depth, last_t, hist = 0, evts[0][0], collections.defaultdict(float)
+alone = collections.defaultdict(float)
+active = {}
+for t, d, name in evts:
+    hist[depth] += t - last_t
+    if depth == 1 and active:
+        alone[next(iter(active)).split("(")[0][:48]] += t - last_t
+    last_t = t
+    depth += d
+    if d > 0:
+        active[name] = active.get(name, 0) + 1
+    else:
+        active[name] -= 1
+        if active[name] == 0:
+            del active[name]
+print("-- concurrency (ms of the span with k kernels in flight): " + "  ".join("%d: %.2f" % (k, v / 1e3) for k, v in sorted(hist.items())))
+print("-- kernels that run ALONE (ms): " + "  ".join("%s %.2f" % (k.replace("aclgan::", "").replace("void ", ""), v / 1e3)
+                                                    for k, v in sorted(alone.items(), key=lambda kv: -kv[1])[:12]))

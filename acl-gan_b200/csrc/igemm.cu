@@ -1322,13 +1322,16 @@ static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repea
     if (plan->planes == 1) { kp.a_seg[1] = kp.a_seg[0]; kp.b_seg[1] = kp.b_seg[0]; }
     kp.seg_a_bytes = plan->seg_rows * 128;
     kp.seg_btile_bytes = b_rows * 128;
-    // Two M tiles per CTA and work item (m_sub = 2): every staged weight tile feeds two accumulators (half the weight bytes per
-    // FLOP through the ~42 B/clk/SM L2->SM path that bounds the two-deep ring of the N = 256 layers) and the tile count per
-    // wave doubles (batch-8 res-block conv: 137 tile pairs = 69 items = ONE wave on 74 clusters instead of 1.85).  Needs
-    // 2 * block_n <= 512 TMEM columns and the whole shared memory (two stages of 2 A segments + the row's weight tiles), so it is
-    // used for CTA pairs with more than one wave of work; env ACLGAN_SEG_MSUB=1|2 overrides.
+    // Two M tiles per CTA and work item (m_sub = 2, experimental): every staged weight tile feeds two accumulators (half the
+    // weight bytes per FLOP through the ~42 B/clk/SM L2->SM path) and the tile count per wave doubles (batch-8 res-block conv:
+    // 137 tile pairs = 69 items = ONE wave on 74 clusters instead of 1.85).  Needs 2 * block_n <= 512 TMEM columns and the
+    // whole shared memory (two stages of 2 A segments + the row's weight tiles).
     const int pair_items1 = ((m_tiles + 1) / 2) * plan->n_tiles;
-    int m_sub = (pair && 2 * plan->block_n <= 512 && plan->block_n >= 128 && pair_items1 > num_sms() / 2) ? 2 : 1;
+    // MEASURED (tools/bench_layers.py, batch 8): forward 52.9 -> 66.5 us, dgrad 42.4 -> 45.4 us on the 3x3 256->256 layer: with
+    // N = 256 the two accumulators fill TMEM, the epilogue (as long as the MMAs of a tile) is no longer overlapped, and that
+    // costs more than the halved weight traffic and the single wave save.  Kept behind ACLGAN_SEG_MSUB=2, default 1.
+    int m_sub = 1;
+    (void)pair_items1;
     {
         const char* e = getenv("ACLGAN_SEG_MSUB");
         if (e != nullptr) m_sub = (atoi(e) == 2 && 2 * plan->block_n <= 512) ? 2 : 1;

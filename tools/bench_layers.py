@@ -82,6 +82,20 @@ for name, cin, cout, k, s, pad, window, n, hw in LAYERS:
     xs = x.struct()
     N.check(L.aclgan_plan_conv_fwd(C.byref(layer.desc), C.byref(xs), layer.wptr(0), C.byref(o), C.byref(plan)), "plan")
     t_f = timed(lambda r: N.check(L.aclgan_igemm_launch_repeat(C.byref(plan), r, SP()), "launch"))
+    extra = ""
+    if window != N.WINDOW_OUT and os.environ.get("VARIANTS"):
+        # the forward as the norm blocks run it: dense raw output (+ fused statistics), vs the padded-plane / halo epilogue above
+        yd = eng.new_dense(n, ho, wo, ((cout + 63) // 64) * 64)
+        od = eng._out_dense(yd, b)
+        pd2 = N.IgemmPlan()
+        N.check(L.aclgan_plan_conv_fwd(C.byref(layer.desc), C.byref(xs), layer.wptr(0), C.byref(od), C.byref(pd2)), "plan")
+        t_dense = timed(lambda r: N.check(L.aclgan_igemm_launch_repeat(C.byref(pd2), r, SP()), "launch"))
+        t_stats = float("nan")
+        if L.aclgan_igemm_stats_supported(C.byref(pd2)):
+            sums = torch.zeros((n, od.C, 2), dtype=torch.float64, device="cuda")
+            pd2.out.stats = sums.data_ptr()
+            t_stats = timed(lambda r: N.check(L.aclgan_igemm_launch_repeat(C.byref(pd2), r, SP()), "launch"))
+        extra = " fwd dense %.1f us, dense+stats %.1f us |" % (t_dense, t_stats)
     # data gradient
     dyp = eng.dy_pad(layer)
     dy = E.ActT(eng, n, ho, wo, cout, dyp, cs=8 if window == N.WINDOW_OUT else None, zero=True)
@@ -102,4 +116,4 @@ for name, cin, cout, k, s, pad, window, n, hw in LAYERS:
     N.check(L.aclgan_plan_conv_wgrad(C.byref(layer.desc), C.byref(dys), C.byref(xs), layer.dw().data_ptr(), C.byref(pw)), "plan wgrad")
     t_w = timed(lambda r: N.check(L.aclgan_wgrad_launch_repeat(C.byref(pw), r, SP()), "launch"))
     print("| %s (%d) | %.1f | %.1f | %.0f | %.1f | %.0f | %.1f | %.0f |" % (
-        name, n, flops / 1e9, t_f, flops / t_f / 1e6, t_d, flops / t_d / 1e6, t_w, flops / t_w / 1e6))
+        name, n, flops / 1e9, t_f, flops / t_f / 1e6, t_d, flops / t_d / 1e6, t_w, flops / t_w / 1e6) + extra)

@@ -65,7 +65,7 @@ class WgradPlan(C.Structure):
                 ("dw", C.c_uint64), ("dw_sm", C.c_int64), ("dw_st", C.c_int64), ("M", C.c_int32), ("Nn", C.c_int32),
                 ("seg_mode", C.c_int32), ("seg_rows", C.c_int32), ("seg_taps", C.c_int32), ("seg_on_m", C.c_int32),
                 ("seg_kw0", C.c_int32 * MAX_TAPS), ("seg_cnt", C.c_int32 * MAX_TAPS),
-                ("seg_map", TmapSpec * 2)]
+                ("seg_map", TmapSpec * 2), ("seg_step", C.c_int32), ("pad_", C.c_int32)]
 
 
 class Act(C.Structure):
@@ -302,6 +302,7 @@ def _declare(L):
     L.aclgan_pack_weight.argtypes = [C.POINTER(PackWeightArgs), C.c_void_p]
     L.aclgan_adam_step.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_void_p]
     L.aclgan_adam_advance.argtypes = [C.c_uint64, C.c_void_p]
+    L.aclgan_adam_units.argtypes = [C.POINTER(AdamTensor)]
     L.aclgan_stream_wait_external_event.argtypes = [C.c_void_p, C.c_void_p]
     L.aclgan_avgpool3x3s2_fwd.argtypes = [C.POINTER(AvgPoolArgs), C.c_void_p]
     L.aclgan_avgpool3x3s2_bwd.argtypes = [C.POINTER(AvgPoolArgs), C.c_void_p]

@@ -51,6 +51,8 @@ struct alignas(64) IgemmKParams {
     int seg_rows, num_segs, seg_taps;
     int seg_a_bytes, seg_btile_bytes, seg_stage_bytes, seg_ns;   // shared-memory ring geometry chosen by the host
     int seg_msub;   // 128-pixel tiles per CTA and work item (1 | 2): with 2 every staged weight tile feeds two accumulators
+    int seg_bres;   // 1: weights resident - the seg_taps (x planes) weight tiles are staged ONCE per CTA (one N tile, one chunk,
+                    // one segment per tile: the small-channel window layers), the ring then carries A segments only
     int epi_direct;
     long long* prof;                                // perf triage: per-CTA role timers [cta][8] (clock cycles) or null
     int seg_dx[16], seg_dy[16];
@@ -954,13 +956,16 @@ __device__ __forceinline__ void issue_row(uint32_t d_tmem, uint64_t da0, uint64_
 template <bool PAIR>
 __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* smem_raw) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* stage_out = smem + P.seg_ns * P.seg_stage_bytes;
+    const int bres_bytes = P.seg_bres ? P.planes * P.seg_taps * P.seg_btile_bytes : 0;
+    uint8_t* bres = smem + P.seg_ns * P.seg_stage_bytes;        // resident weight tiles [plane][tap][b_rows][64] (seg_bres)
+    uint8_t* stage_out = bres + bres_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + kStageOutBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = full_bar + kSegMaxStages;
     uint64_t* tfull_bar = empty_bar + kSegMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* bres_bar = tempty_bar + 3;                        // resident weights landed (seg_bres)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -979,6 +984,7 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kSegMaxStages; ++s) { mbar_init(&full_bar[s], PAIR ? 2 : 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], PAIR ? 8 : 4); }
+        mbar_init(bres_bar, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -1000,7 +1006,7 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
     const int total_items = m_items * P.n_tiles;
     const int n_workers = PAIR ? gridDim.x / 2 : gridDim.x;
     const int worker = PAIR ? blockIdx.x / 2 : blockIdx.x;
-    const uint32_t stage_tx = (uint32_t)(m_sub * P.seg_a_bytes + P.seg_taps * P.seg_btile_bytes) * (PAIR ? 2u : 1u);
+    const uint32_t stage_tx = (uint32_t)(m_sub * P.seg_a_bytes + (P.seg_bres ? 0 : P.seg_taps * P.seg_btile_bytes)) * (PAIR ? 2u : 1u);
     const int n_rounds = P.nseg * P.cchunks * P.num_segs;       // stages per work item
     const int set_cols = m_sub * col_stride;                    // TMEM columns of one accumulator set
     const int acc_sets = (2 * set_cols <= 512) ? 2 : 1;         // double-buffered across items when they fit
@@ -1011,6 +1017,11 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
         uint32_t ph = 0;
         long long t_wait = 0;
         const long long t_begin = prof ? clock64() : 0;
+        if (!PAIR && P.seg_bres && worker < total_items) {
+            mbar_arrive_expect_tx(bres_bar, (uint32_t)bres_bytes);
+            for (int p = 0; p < P.planes; ++p)
+                tma_load_3d(bres + p * P.seg_taps * P.seg_btile_bytes, &P.b_seg[p], bres_bar, 0, 0, 0);
+        }
         for (int item = worker; item < total_items; item += n_workers) {
             const int nt = item % P.n_tiles;
             int x0[2], y0[2], z0[2];
@@ -1048,7 +1059,7 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
                             for (int sub = 0; sub < m_sub; ++sub)
                                 tma_load_4d(sa + sub * P.seg_a_bytes, am, &full_bar[st], cc * 64, x0[sub] + P.seg_dx[sg],
                                             y0[sub] + P.seg_dy[sg], z0[sub]);
-                            tma_load_3d(sb, bm, &full_bar[st], cc * 64, brow, sg * P.seg_taps);
+                            if (!P.seg_bres) tma_load_3d(sb, bm, &full_bar[st], cc * 64, brow, sg * P.seg_taps);
                         }
                         if (++st == P.seg_ns) { st = 0; ph ^= 1; }
                     }
@@ -1068,6 +1079,7 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
         const int row0 = P.tap_row[0];
         const int64_t rstep8 = P.seg_taps > 1 ? (int64_t)(P.tap_row[1] - P.tap_row[0]) * 8 : 0;   // rows -> descriptor units
         const uint32_t bt16 = (uint32_t)P.seg_btile_bytes >> 4;
+        if (!PAIR && P.seg_bres && worker < total_items) mbar_wait(bres_bar, 0);
         for (int item = worker; item < total_items; item += n_workers, ++it) {
             const int acc = it % acc_sets;
             const uint32_t acc_phase = (it / acc_sets) & 1;
@@ -1085,7 +1097,9 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
                 if (prof) t_wfull += clock64() - tw;
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + st * P.seg_stage_bytes);
-                const uint32_t sb = sa + m_sub * P.seg_a_bytes;
+                // (resident weights: plane of B follows the hi/lo segment: (a_hi, b_hi), (a_hi, b_lo), (a_lo, b_hi))
+                const uint32_t sb = P.seg_bres ? smem_u32(bres) + (uint32_t)(((r / (P.cchunks * P.num_segs)) == 1 ? 1 : 0) * P.seg_taps * P.seg_btile_bytes)
+                                               : sa + m_sub * P.seg_a_bytes;
                 if (P.debug != 2) {          // (2 = TMA traffic without MMA)
                     // A descriptor of tap j = stage base + (row0 + j * rstep) rows; B descriptor = base + j weight tiles
                     const uint64_t db0 = make_smem_desc_sw128(sb, 16, 1024);
@@ -1265,6 +1279,7 @@ static int fill_kparams(const aclgan_igemm_plan* pl, IgemmKParams* kp) {
     for (int t = 0; t < ACLGAN_MAX_TAPS; ++t) kp->tap_row[t] = pl->tap_row[t];
     kp->seg_a_bytes = kp->seg_btile_bytes = kp->seg_stage_bytes = kp->seg_ns = 0;
     kp->seg_msub = 1;
+    kp->seg_bres = 0;
     kp->prof = g_prof;
     {
         const char* ed = getenv("ACLGAN_EPI_DIRECT");
@@ -1322,6 +1337,13 @@ static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repea
     if (plan->planes == 1) { kp.a_seg[1] = kp.a_seg[0]; kp.b_seg[1] = kp.b_seg[0]; }
     kp.seg_a_bytes = plan->seg_rows * 128;
     kp.seg_btile_bytes = b_rows * 128;
+    // weights resident in shared memory when every tile of the launch uses the same ones (window layers: one N tile, one
+    // 64-wide K chunk per tap, one segment per tile): the per-tile weight re-load was 2/3 of the staged bytes
+    {
+        const char* e = getenv("ACLGAN_SEG_BRES");
+        kp.seg_bres = (!pair && plan->n_tiles == 1 && plan->cchunks == 1 && plan->num_segs == 1 && (e == nullptr || atoi(e) != 0)) ? 1 : 0;
+    }
+    const int bres_bytes = kp.seg_bres ? plan->planes * plan->seg_taps * kp.seg_btile_bytes : 0;
     // Two M tiles per CTA and work item (m_sub = 2, experimental): every staged weight tile feeds two accumulators (half the
     // weight bytes per FLOP through the ~42 B/clk/SM L2->SM path) and the tile count per wave doubles (batch-8 res-block conv:
     // 137 tile pairs = 69 items = ONE wave on 74 clusters instead of 1.85).  Needs 2 * block_n <= 512 TMEM columns and the
@@ -1347,8 +1369,8 @@ static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repea
     int seg_smem = seg_smem_default, ns = 0;
     for (;;) {
         kp.seg_msub = m_sub;
-        kp.seg_stage_bytes = m_sub * kp.seg_a_bytes + plan->seg_taps * kp.seg_btile_bytes;
-        ns = (seg_smem - 1024 - kStageOutBytes - 512) / kp.seg_stage_bytes;
+        kp.seg_stage_bytes = m_sub * kp.seg_a_bytes + (kp.seg_bres ? 0 : plan->seg_taps * kp.seg_btile_bytes);
+        ns = (seg_smem - 1024 - kStageOutBytes - 512 - bres_bytes) / kp.seg_stage_bytes;
         if (ns >= 2) break;
         if (seg_smem < kSegSmemBytes) { seg_smem = kSegSmemBytes; continue; }      // m_sub = 2 stages need the whole budget
         if (m_sub == 2) { m_sub = 1; seg_smem = seg_smem_default; continue; }

@@ -86,6 +86,12 @@ static bool fold_enabled(const aclgan_conv_desc* cd) {
     return (e == nullptr || atoi(e) != 0) && cd->window == ACLGAN_WINDOW_OUT && cd->stride == 1 && cd->k <= 8 && cd->cout <= 8;
 }
 
+// vertical segments of the stride-1 small-channel window layers (ACLGAN_WINDOW_VSEG=0: one 128-pixel box per filter row)
+static bool window_vseg_enabled() {
+    const char* e = getenv("ACLGAN_WINDOW_VSEG");
+    return e == nullptr || atoi(e) != 0;
+}
+
 static bool wgrad_seg_enabled() {
     const char* e = getenv("ACLGAN_WGRAD_SEG");
     return e == nullptr || atoi(e) != 0;
@@ -252,6 +258,23 @@ extern "C" int aclgan_plan_conv_fwd(const aclgan_conv_desc* cd, const aclgan_act
         p->cchunks = 1;
         p->num_taps = k;
         p->n_avariants = (s == 1) ? 1 : 2;
+        // stride 1: VERTICAL segment mode.  Tiles are 16 x 8 output pixels; the k taps (= filter rows) of a tile read the
+        // input rows y .. y + 8 + k - 2, so ONE box of 16 x (8 + k - 1) window rows is staged per tile and tap kh is the
+        // 128-row window starting 16 * kh rows into it (a multiple of the 1 KB swizzle atom) - k times fewer activation bytes
+        // cross L2 -> shared memory than with one 128-pixel box per tap, which is what bounded these layers
+        const bool vseg = (s == 1) && k > 1 && 16 * (8 + k - 1) <= 256 && wo >= 16 && ho >= 8 && window_vseg_enabled();
+        if (vseg) {
+            p->box_x = 16; p->box_y = 8; p->box_z = 1;
+            p->tiles_x = ceil_div(wo, 16); p->tiles_y = ceil_div(ho, 8); p->tiles_z = x->n;
+            p->seg_mode = 1;
+            p->seg_rows = 16 * (8 + k - 1);
+            p->num_segs = 1;
+            p->seg_taps = k;
+            p->seg_dx[0] = 0; p->seg_dy[0] = 0;
+            for (int kh = 0; kh < k; ++kh) p->tap_row[kh] = 16 * kh;
+            for (int pl = 0; pl < x->planes; ++pl)
+                plane_map4(&p->a_seg[pl], x->data[pl], 64, wp, hp, x->n, px, row, img, 16, 8 + k - 1, 1);
+        }
         for (int pl = 0; pl < x->planes; ++pl) {
             if (s == 1) {
                 // window starting at stored pixel x covers pixels x .. x+7 (the caller provides >= 64 elements of
@@ -346,6 +369,30 @@ extern "C" int aclgan_plan_conv_dgrad(const aclgan_conv_desc* cd, const aclgan_a
         for (int kh = 0; kh < k; ++kh) {
             p->tap_dx[kh] = (k - 1 - kh) * wz;       // window pixel j = (k-1-kw) is part of the K chunk
             p->tap_bk[kh] = kh * 64;
+        }
+        if (k > 1 && 16 * (8 + k - 1) <= 256 && wz >= 16 && hz >= 8 && window_vseg_enabled()) {
+            // vertical segment mode (see aclgan_plan_conv_fwd): 16 x 8 tiles of the zero-bordered grid, one staged box of
+            // 16 x (8 + k - 1) window rows per tile; tap kh reads grid rows y + (k - 1 - kh), i.e. starts 16 (k - 1 - kh) rows
+            // into the box (a DEscending arithmetic progression of start rows)
+            const int gw = (out->W > 0 && out->W < wz) ? out->W : wz, gh = (out->H > 0 && out->H < hz) ? out->H : hz;
+            p->flat = 0; p->flat_w = 1; p->flat_img = 1;
+            p->box_x = 16; p->box_y = 8; p->box_z = 1;
+            p->tiles_x = ceil_div(gw, 16); p->tiles_y = ceil_div(gh, 8); p->tiles_z = dy->n;
+            p->seg_mode = 1;
+            p->seg_rows = 16 * (8 + k - 1);
+            p->num_segs = 1;
+            p->seg_taps = k;
+            p->seg_dx[0] = 0; p->seg_dy[0] = 0;
+            for (int kh = 0; kh < k; ++kh) {
+                p->tap_row[kh] = 16 * (k - 1 - kh);
+                p->tap_dx[kh] = 0;
+                p->tap_dy[kh] = k - 1 - kh;
+            }
+            for (int pl = 0; pl < dy->planes; ++pl) {
+                plane_map4(&p->a[pl][0], dy->data[pl], 64, wz, hz, dy->n, 16, (int64_t)wz * 16, (int64_t)hz * wz * 16, 16, 8, 1);
+                plane_map4(&p->a_seg[pl], dy->data[pl], 64, wz, hz, dy->n, 16, (int64_t)wz * 16, (int64_t)hz * wz * 16, 16,
+                           8 + k - 1, 1);
+            }
         }
     }
     p->out = *out;
@@ -543,6 +590,60 @@ extern "C" int aclgan_plan_conv_wgrad(const aclgan_conv_desc* cd, const aclgan_a
                 }
             }
         }
+    }
+    if (cd->window == ACLGAN_WINDOW_IN && s == 1 && k > 1 && k * 64 <= 512 && 16 * (4 + k - 1) <= 256 && wo >= 16 && ho >= 4 &&
+        window_vseg_enabled()) {
+        // vertical segment mode of the stride-1 pixel-window layer: a tap is a filter ROW, so the shifted operand (the window
+        // rows of the conv input) is staged once per 16 x 4 pixel block as 16 x (4 + k - 1) window rows and tap kh starts
+        // 16 * kh rows into it; ONE CTA-tile reduces all k taps (k x 64 accumulator columns)
+        p->seg_mode = 1;
+        p->seg_taps = k;
+        p->seg_step = 16;
+        p->seg_rows = 16 * (4 + k - 1);
+        p->seg_on_m = 0;
+        p->box_x = 16; p->box_y = 4; p->box_z = 1;
+        p->blocks_x = ceil_div(wo, 16); p->blocks_y = ceil_div(ho, 4); p->blocks_z = x->n;
+        p->num_taps = 1;
+        const int64_t px = (int64_t)x->c * 2, row = (int64_t)wp * px, img = (int64_t)hp * row;
+        for (int pl = 0; pl < x->planes; ++pl) {
+            interior_map(&p->mop[pl][0], dy, pl, dy->c, 16, 4, 1);
+            plane_map4(&p->nop[pl][0], x->data[pl], 64, wp, hp, x->n, px, row, img, 16, 4, 1);
+            plane_map4(&p->seg_map[pl], x->data[pl], 64, wp, hp, x->n, px, row, img, 16, 4 + k - 1, 1);
+        }
+        p->n_mvariants = 1; p->n_nvariants = 1;
+        p->m_dx[0] = p->m_dy[0] = p->n_dx[0] = p->n_dy[0] = 0;
+        p->m_var[0] = p->n_var[0] = 0;
+        p->seg_kw0[0] = 0;
+        p->seg_cnt[0] = k;
+        p->tap_out[0] = 0;
+    }
+    if (cd->window == ACLGAN_WINDOW_OUT && s == 1 && k > 1 && k * 64 <= 512 && 16 * (4 + k - 1) <= 256 && wp >= 16 && ho >= 4 &&
+        window_vseg_enabled()) {
+        // the same for the few-output-channel final conv: here the SHIFTED operand is M (the conv input rows y + kh), the
+        // 8-pixel window of the zero-bordered dY is the fixed N operand
+        p->seg_mode = 1;
+        p->seg_taps = k;
+        p->seg_step = 16;
+        p->seg_rows = 16 * (4 + k - 1);
+        p->seg_on_m = 1;
+        p->box_x = 16; p->box_y = 4; p->box_z = 1;
+        p->blocks_x = ceil_div(wp, 16); p->blocks_y = ceil_div(ho, 4); p->blocks_z = x->n;
+        p->num_taps = 1;
+        int nvar = 1;
+        input_maps(p->mop, &nvar, x, 1, 16, 4, 1);
+        const int64_t px = (int64_t)x->c * 2, row = (int64_t)wp * px, img = (int64_t)hp * row;
+        const int hz = ho + 2 * dy->pad, wz = wo + 2 * dy->pad;
+        for (int pl = 0; pl < x->planes; ++pl) {
+            plane_map4(&p->seg_map[pl], x->data[pl], x->c, wp, hp, x->n, px, row, img, 16, 4 + k - 1, 1);
+            plane_map4(&p->nop[pl][0], dy->data[pl], 64, wz, hz, dy->n, 16, (int64_t)wz * 16, (int64_t)hz * wz * 16, 16, 4, 1);
+        }
+        p->n_mvariants = 1; p->n_nvariants = 1;
+        p->m_dx[0] = p->m_dy[0] = p->n_dx[0] = 0;
+        p->n_dy[0] = dy->pad;
+        p->m_var[0] = p->n_var[0] = 0;
+        p->seg_kw0[0] = 0;
+        p->seg_cnt[0] = k;
+        p->tap_out[0] = 0;
     }
     // split-K so that the grid is ONE wave of CTAs (<= number of SMs): a grid of 162 CTAs on 148 SMs would run two
     // waves and take twice as long as 144

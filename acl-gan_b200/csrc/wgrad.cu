@@ -43,6 +43,9 @@ struct alignas(64) WgradKParams {
     CUtensorMap seg_map[2];
     int seg_rows, seg_taps, seg_on_m;
     int seg_m_bytes, seg_n_bytes, seg_stages;    // per-stage operand regions / ring depth chosen by the host
+    int seg_step;      // rows of the staged segment between consecutive taps (1: horizontal segments; box_x: vertical window segments)
+    int seg_merge;     // > 1: that many taps are ONE MMA (N = 64 * taps): their 64-column operand blocks are seg_step rows apart, which
+                       // is the descriptor's leading-dimension offset (N-shifted, one 64-channel chunk, seg_step * 128 B % 1024 == 0)
     int seg_kw0[ACLGAN_MAX_TAPS], seg_cnt[ACLGAN_MAX_TAPS];
 };
 
@@ -292,7 +295,8 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_seg_kernel(const __grid_co
         } else if (warp == 1 && lane == 0) {
             // ---------------- MMA issuer ----------------
             const uint32_t idesc = make_idesc_bf16(128, (uint32_t)ncols, 1, 1);
-            const uint32_t shift_m = P.seg_on_m ? 8u : 0u, shift_n = P.seg_on_m ? 0u : 8u;    // one pixel row = 128 B = 8 units
+            const uint32_t step8 = 8u * (uint32_t)P.seg_step;                                  // one pixel row = 128 B = 8 units
+            const uint32_t shift_m = P.seg_on_m ? step8 : 0u, shift_n = P.seg_on_m ? 0u : step8;
             int stage = 0;
             uint32_t phase = 0;
             for (int k = 0; k < n_iters; ++k) {
@@ -301,13 +305,27 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_seg_kernel(const __grid_co
                 const uint32_t sm = smem_u32(smem + stage * stage_bytes);
                 const uint32_t sn = sm + P.seg_m_bytes;
                 const uint64_t dm0 = make_smem_desc_sw128(sm, m_chunk_bytes, 1024);
-                const uint64_t dn0 = make_smem_desc_sw128(sn, n_chunk_bytes, 1024);
+                if (P.seg_merge > 1) {
+                    // groups of seg_merge taps as one MMA of N = 64 * taps: column block c of the N operand = tap c of the group
+                    const uint64_t dng = make_smem_desc_sw128(sn, P.seg_step * 128, 1024);
 #pragma unroll 1
-                for (int j = 0; j < cnt; ++j) {
-                    const uint64_t dm = dm0 + (uint64_t)((kw0 + j) * shift_m), dn = dn0 + (uint64_t)((kw0 + j) * shift_n);
+                    for (int j0 = 0; j0 < cnt; j0 += P.seg_merge) {
+                        const int g = min(P.seg_merge, cnt - j0);
+                        const uint32_t idg = make_idesc_bf16(128, (uint32_t)(64 * g), 1, 1);
+                        const uint64_t dn = dng + (uint64_t)((kw0 + j0) * shift_n);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)        // 16 pixels (one UMMA K) = 2048 B -> +128 encoded
-                        umma_bf16(tmem_base + j * ncols, dm + 128 * kk, dn + 128 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16(tmem_base + j0 * 64, dm0 + 128 * kk, dn + 128 * kk, idg, (k | kk) != 0 ? 1u : 0u);
+                    }
+                } else {
+                    const uint64_t dn0 = make_smem_desc_sw128(sn, n_chunk_bytes, 1024);
+#pragma unroll 1
+                    for (int j = 0; j < cnt; ++j) {
+                        const uint64_t dm = dm0 + (uint64_t)((kw0 + j) * shift_m), dn = dn0 + (uint64_t)((kw0 + j) * shift_n);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)        // 16 pixels (one UMMA K) = 2048 B -> +128 encoded
+                            umma_bf16(tmem_base + j * ncols, dm + 128 * kk, dn + 128 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(&empty_bar[stage]);
                 if (++stage == P.seg_stages) { stage = 0; phase ^= 1; }
@@ -429,7 +447,8 @@ extern "C" int aclgan_wgrad_launch_repeat(const aclgan_wgrad_plan* pl, int repea
     }
     const int grid = pl->num_taps * pl->m_tiles * pl->n_tiles * pl->ksplit;
     if (pl->seg_mode) {
-        if (pix != 64 || pl->seg_rows % 8 != 0 || pl->seg_rows < 64 + pl->seg_taps - 1 || pl->seg_rows > 256 ||
+        const int step = pl->seg_step > 0 ? pl->seg_step : 1;
+        if (pix != 64 || pl->seg_rows % 8 != 0 || pl->seg_rows < 64 + (pl->seg_taps - 1) * step || pl->seg_rows > 256 ||
             pl->seg_taps * 64 * pl->n_chunks > 512)
             return ACLGAN_ERR_SHAPE;
         for (int p = 0; p < 2; ++p) {
@@ -440,8 +459,14 @@ extern "C" int aclgan_wgrad_launch_repeat(const aclgan_wgrad_plan* pl, int repea
         for (int t = 0; t < ACLGAN_MAX_TAPS; ++t) {
             kp.seg_kw0[t] = pl->seg_kw0[t]; kp.seg_cnt[t] = pl->seg_cnt[t];
             if (t < pl->num_taps && (pl->seg_cnt[t] < 1 || pl->seg_cnt[t] > pl->seg_taps ||
-                                     pl->seg_kw0[t] + pl->seg_cnt[t] + 63 > pl->seg_rows))
+                                     (pl->seg_kw0[t] + pl->seg_cnt[t] - 1) * step + 64 > pl->seg_rows))
                 return ACLGAN_ERR_SHAPE;
+        }
+        kp.seg_step = step;
+        {
+            const char* e = getenv("ACLGAN_WGRAD_MERGE");
+            const bool on = e == nullptr || atoi(e) != 0;
+            kp.seg_merge = (on && !pl->seg_on_m && pl->n_chunks == 1 && (step * 128) % 1024 == 0 && pl->seg_taps > 1) ? 4 : 1;
         }
         kp.seg_m_bytes = pl->m_chunks * (pl->seg_on_m ? pl->seg_rows : 64) * 128;
         kp.seg_n_bytes = pl->n_chunks * (pl->seg_on_m ? 64 : pl->seg_rows) * 128;

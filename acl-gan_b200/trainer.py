@@ -186,7 +186,7 @@ class aclgan_Trainer(nn.Module):
             for j in range(4):
                 t.d[j] = shape[j]
             t.planes = self.eng.prec.planes
-            for c in range((p.numel() + 1023) // 1024):
+            for c in range(N.lib().aclgan_adam_units(C.byref(t))):
                 chunks += [i, c]
         hp = self._hp
         world = 1

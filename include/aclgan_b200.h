@@ -141,6 +141,10 @@ typedef struct aclgan_wgrad_plan {
     int32_t seg_mode, seg_rows, seg_taps, seg_on_m;
     int32_t seg_kw0[ACLGAN_MAX_TAPS], seg_cnt[ACLGAN_MAX_TAPS];
     aclgan_tmap_spec seg_map[2];
+    /* vertical segments (small-channel window layers, where a tap is a filter ROW): the 64-pixel block is box_x x box_y pixels
+     * (16 x 4), the segment box_x x (box_y + k - 1) pixels, and tap kh starts seg_step = box_x rows further into it (0 = 1) */
+    int32_t seg_step;
+    int32_t pad_;
 } aclgan_wgrad_plan;
 
 /* ---- padded NHWC activation handle ---- */
@@ -355,7 +359,10 @@ typedef struct aclgan_adam_tensor {
 } aclgan_adam_tensor;
 
 /* hyper (device, fp32[8]): lr, beta1, beta2, eps, weight_decay, grad_scale, step (advanced on device), unused.
- * chunks (device, int32[2*n_chunks]): (tensor id, first element / 1024) per CTA. */
+ * chunks (device, int32[2*n_chunks]): (tensor id, unit) per CTA, unit = 0 .. aclgan_adam_units(tensor) - 1.  A unit is a
+ * (32 co x 32 ci x all taps) tile of a conv weight - gradient, master / moments and each packed plane are then streamed in their
+ * own fastest order through a shared-memory transpose - or 1024 consecutive elements of a dense tensor. */
+int aclgan_adam_units(const aclgan_adam_tensor* t);   /* host-side: CTAs needed for this table entry */
 int aclgan_adam_step(uint64_t table, uint64_t chunks, int32_t n_chunks, uint64_t hyper, void* stream);
 int aclgan_adam_advance(uint64_t hyper, void* stream);
 

@@ -262,7 +262,8 @@ def run_wgrad(mem, plan):
 def _run_wgrad_seg(mem, plan, dw, dwoff, segs, ncols):
     """segment mode (wgrad_seg_kernel): per filter row one CTA-tile; the shifted operand is staged once per 64-pixel
     block as seg_rows pixels and tap kw uses its rows [kw, kw + 64)"""
-    assert plan.box_x == 64 and plan.box_y == 1 and plan.box_z == 1
+    assert plan.box_x * plan.box_y == 64 and plan.box_z == 1
+    step = plan.seg_step if plan.seg_step > 0 else 1
     for tap in range(plan.num_taps):
         for mt in range(plan.m_tiles):
             for nt in range(plan.n_tiles):
@@ -272,7 +273,7 @@ def _run_wgrad_seg(mem, plan, dw, dwoff, segs, ncols):
                 for bz in range(plan.blocks_z):
                     for by in range(plan.blocks_y):
                         for bx in range(plan.blocks_x):
-                            x0, y0, z0 = bx * 64, by, bz
+                            x0, y0, z0 = bx * plan.box_x, by * plan.box_y, bz
                             for pm, pn in segs:
                                 mm = plan.seg_map[pm] if plan.seg_on_m else plan.mop[pm][0]
                                 nm = plan.nop[pn][0] if plan.seg_on_m else plan.seg_map[pn]
@@ -287,7 +288,7 @@ def _run_wgrad_seg(mem, plan, dw, dwoff, segs, ncols):
                                     Nt[:, c * 64:(c + 1) * 64] = tma_box(
                                         mem, nm, ((nt * plan.n_chunks + c) * 64, x0 + plan.n_dx[tap], y0 + plan.n_dy[tap], z0)).reshape(nr, 64)
                                 for j in range(cnt):
-                                    kw = kw0 + j
+                                    kw = (kw0 + j) * step
                                     Mw = Mt[kw:kw + 64] if plan.seg_on_m else Mt
                                     Nw = Nt if plan.seg_on_m else Nt[kw:kw + 64]
                                     acc[j] += Mw.t() @ Nw

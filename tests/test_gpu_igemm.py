@@ -31,6 +31,9 @@ FWD_CASES = [
     (3, 64, 7, 1, 3, 1, 1, 8, 256, 1),         # first 7x7 3->64: pixel windows at W = 256
     (6, 64, 4, 2, 1, 1, 1, 16, 256, 1),        # discriminator first conv on a 256-wide pair
     (256, 256, 3, 1, 1, 0, 1, 4, 256, 1),
+    # vertical window segments + resident weights: ragged 16 x 8 tile grid over several images, hi / lo planes
+    (3, 64, 7, 1, 3, 1, 3, 20, 40, 1),
+    (3, 64, 7, 1, 3, 1, 2, 16, 32, 2),
 ]
 
 
@@ -215,6 +218,11 @@ WGRAD_CASES = [
     (3, 64, 7, 1, 3, 1, 1, 8, 256, 1),
     (6, 64, 4, 2, 1, 1, 1, 16, 256, 1),
     (64, 128, 4, 2, 1, 0, 1, 16, 256, 1),
+    # vertical window segments (merged taps): ragged 16 x 4 block grid, hi / lo planes, both window sides
+    (3, 64, 7, 1, 3, 1, 3, 10, 40, 1),
+    (3, 64, 7, 1, 3, 1, 2, 16, 32, 2),
+    (64, 4, 7, 1, 3, 2, 3, 10, 40, 1),
+    (64, 3, 7, 1, 3, 2, 2, 16, 32, 2),
 ]
 
 

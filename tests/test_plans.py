@@ -63,6 +63,10 @@ FWD_CASES = [
     (3, 64, 7, 1, 3, 1, 1, 4, 256, 1),
     (64, 4, 7, 1, 3, 0, 1, 4, 256, 1),
     (6, 16, 4, 2, 1, 1, 1, 4, 256, 1),
+    # vertical-segment window plans (16 x 8 pixel tiles): ragged tile grid, several images, hi/lo planes, 256-wide rows
+    (3, 64, 7, 1, 3, 1, 2, 12, 40, 1),
+    (3, 64, 7, 1, 3, 1, 1, 8, 32, 2),
+    (3, 64, 7, 1, 3, 1, 1, 9, 256, 1),
 ]
 
 
@@ -88,7 +92,7 @@ def test_conv_fwd_plan(cin, cout, k, s, pad, window, n, h, w, planes):
     o, obuf = out_spec(mem, n, ho, wo, cout, N.OUT_F32, pad=1, act=N.ACT_LRELU, bias=bias, mirror=1)
     plan = N.IgemmPlan()
     N.check(L.aclgan_plan_conv_fwd(C.byref(desc), C.byref(act), wptr, C.byref(o), C.byref(plan)), "plan fwd")
-    assert bool(plan.seg_mode) == (s == 1 and window != 1 and k > 1)
+    assert bool(plan.seg_mode) == (s == 1 and k > 1 and (window != 1 or (wo >= 16 and ho >= 8)))
     # the box-per-tap description (plain kernels) and, when present, the segment description (igemm_seg_kernel)
     for use_seg in ([False, True] if plan.seg_mode else [False]):
         obuf.zero_()
@@ -115,6 +119,8 @@ DGRAD_CASES = [
     (64, 4, 7, 1, 3, 1, 8, 8, 2),
     (64, 64, 5, 1, 2, 1, 2, 256, 1),          # 256-wide output rows (benchmarked geometry)
     (64, 4, 7, 1, 3, 1, 2, 256, 1),
+    (64, 4, 7, 1, 3, 2, 9, 21, 1),            # vertical window segments: ragged tile grid, two images
+    (64, 3, 7, 1, 3, 1, 10, 18, 2),
 ]
 
 
@@ -143,7 +149,8 @@ def test_conv_dgrad_plan(cin, cout, k, s, pad, n, ho, wo, planes):
     obuf = torch.zeros(n, hp, wp, cin_s, dtype=torch.float32)
     optr = mem.add(obuf)
     merged = (s == 2 and n % 2 == 0)          # even batch sizes exercise the single-launch (4 phases merged) plan
-    seg_pass = (s == 1 and not window)        # stride-1 regular layouts: run the segment description of the plan
+    # stride-1 layouts: run the segment description of the plan too (pixel-window dY: vertical segments of 16 x 8 tiles)
+    seg_pass = (s == 1 and (not window or wo + 2 * (k - 1) >= 16))
     for phase in ([-1] if merged else range(1 if s == 1 else 4)):
         o = N.OutSpec()
         o.ptr[0] = optr
@@ -189,6 +196,12 @@ WGRAD_CASES = [
     (64, 128, 3, 1, 1, 0, 2, 2, 64, 2),
     (64, 64, 5, 1, 2, 0, 1, 3, 256, 1),       # W = 256 (benchmarked geometry)
     (64, 4, 7, 1, 3, 2, 1, 4, 256, 1),
+    # vertical window segments (16 x 4 pixel blocks): ragged block grid / several images, hi / lo planes, 256-wide rows
+    (3, 64, 7, 1, 3, 1, 2, 10, 24, 1),
+    (3, 64, 7, 1, 3, 1, 1, 8, 16, 2),
+    (3, 64, 7, 1, 3, 1, 1, 5, 256, 1),
+    (64, 4, 7, 1, 3, 2, 2, 10, 24, 1),
+    (64, 3, 7, 1, 3, 2, 1, 8, 16, 2),
 ]
 
 
@@ -213,7 +226,9 @@ def test_conv_wgrad_plan(cin, cout, k, s, pad, window, n, h, w, planes):
     dw = torch.zeros(rows.value * kt.value, dtype=torch.float64)
     plan = N.WgradPlan()
     N.check(L.aclgan_plan_conv_wgrad(C.byref(desc), C.byref(yact), C.byref(xact), mem.add(dw), C.byref(plan)), "plan wgrad")
-    assert bool(plan.seg_mode) == (s == 1 and window == 0 and 1 < k <= 7 and wo % 64 == 0)
+    assert bool(plan.seg_mode) == ((s == 1 and window == 0 and 1 < k <= 7 and wo % 64 == 0) or
+                                   (s == 1 and window == 1 and wo >= 16 and ho >= 4) or
+                                   (s == 1 and window == 2 and w + 2 * pad >= 16 and ho >= 4))
     emul.run_wgrad(mem, plan)
     got = emul.unpack_wgrad(desc, dw, (cout, cin, k, k))
     ref = torch.nn.grad.conv2d_weight(xeff, (cout, cin, k, k), yeff, stride=s)

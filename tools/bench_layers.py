@@ -96,6 +96,24 @@ for name, cin, cout, k, s, pad, window, n, hw in LAYERS:
             pd2.out.stats = sums.data_ptr()
             t_stats = timed(lambda r: N.check(L.aclgan_igemm_launch_repeat(C.byref(pd2), r, SP()), "launch"))
         extra = " fwd dense %.1f us, dense+stats %.1f us |" % (t_dense, t_stats)
+        if os.environ.get("PROF"):
+            # device-side role timers of the segment kernel (cycles, mean over CTAs) without / with the fused statistics
+            L.aclgan_igemm_set_prof.argtypes = [C.c_uint64]
+            prof = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
+            for tag, st in (("dense", 0), ("dense+stats", sums.data_ptr() if t_stats == t_stats else 0)):
+                if tag != "dense" and st == 0:
+                    continue
+                pd2.out.stats = st
+                prof.zero_()
+                L.aclgan_igemm_set_prof(prof.data_ptr())
+                N.check(L.aclgan_igemm_launch_repeat(C.byref(pd2), 1, SP()), "launch")
+                torch.cuda.synchronize()
+                L.aclgan_igemm_set_prof(0)
+                pr = prof.view(148, 16).double()
+                pr = pr[pr[:, 5] > 0]
+                m = pr.mean(0)
+                extra += ("\n    [%s] cycles/CTA: producer %.0f (wait %.0f) | mma %.0f (wait operands %.0f, wait acc %.0f) | epilogue %.0f (wait %.0f, tile fn %.0f; "
+                          "fast %.0f: tmem wait %.0f, chunks %.0f) ctas %d" % (tag, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], pr.shape[0]))
     # data gradient
     dyp = eng.dy_pad(layer)
     dy = E.ActT(eng, n, ho, wo, cout, dyp, cs=8 if window == N.WINDOW_OUT else None, zero=True)

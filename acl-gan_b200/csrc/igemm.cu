@@ -51,6 +51,10 @@ struct alignas(64) IgemmKParams {
     int seg_rows, num_segs, seg_taps;
     int seg_a_bytes, seg_btile_bytes, seg_stage_bytes, seg_ns;   // shared-memory ring geometry chosen by the host
     int seg_msub;   // 128-pixel tiles per CTA and work item (1 | 2): with 2 every staged weight tile feeds two accumulators
+    int seg_egroups; // epilogue warp groups (1 | 2): with 2, warps 4-7 drain the first half of a tile's accumulator columns and warps
+                     // 8-11 the second half - the epilogue of a 2-tiles-per-CTA launch is latency-bound and exposed
+    int seg_esplit;  // two groups: 1 = each drains half of the columns of every tile (N >= 128), 0 = the groups alternate tiles (group g
+                     // owns accumulator set g: N < 128, where a tile's epilogue is longer than its few MMAs)
     int seg_bres;   // 1: weights resident - the seg_taps (x planes) weight tiles are staged ONCE per CTA (one N tile, one chunk,
                     // one segment per tile: the small-channel window layers), the ring then carries A segments only
     int epi_direct;
@@ -304,19 +308,23 @@ __device__ __forceinline__ void stage_colsums(const uint8_t* stg, float* red, in
     }
 }
 
+// named barrier of one 128-thread epilogue group (immediate ids, so that ptxas reserves 3 barriers, not all 16)
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+    (void)threads;
+    if (id == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
 }
 
 // end of a tile with statistics: the four epilogue warps' slots -> fp64 atomics into stats[n][C][2].
 // combine != 0: the tile's rows belong to image n_first (set 0) and, when `straddle`, n_first + 1 (set 1); the four warps
 // are summed first (4x fewer atomics).  combine == 0 (tiny planes, several images per tile): every warp's 32 rows
 // belong to the single image n_first (the host guarantees box_x * box_y % 32 == 0) and the warp adds its own slots.
-__device__ __forceinline__ void stats_tile_end(const EpiArgs& o, uint8_t* stage_out, int q, int lane, int n0, bool combine,
+// red0: reduction slots of the group's warp 0 (warp w: red0 + w * 8192); bar_id: named barrier of the (128-thread) group
+__device__ __forceinline__ void stats_tile_end(const EpiArgs& o, const uint8_t* red0, int bar_id, int q, int lane, int n0, bool combine,
                                                int n_first, bool straddle, bool tile_ok) {
     double* stats = reinterpret_cast<double*>(o.stats);
     if (combine) {
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_id, 128);
         if (tile_ok) {
             for (int set = 0; set < (straddle ? 2 : 1); ++set) {
                 const int n = n_first + set;
@@ -325,7 +333,7 @@ __device__ __forceinline__ void stats_tile_end(const EpiArgs& o, uint8_t* stage_
                     float s = 0.f, qq = 0.f;
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
-                        const float2 v = *reinterpret_cast<const float2*>(stage_out + w * 8192 + 4096 + set * 2048 + ch * 8);
+                        const float2 v = *reinterpret_cast<const float2*>(red0 + w * 8192 + set * 2048 + ch * 8);
                         s += v.x; qq += v.y;
                     }
                     double* d = stats + ((int64_t)(o.z_mod > 0 ? n % o.z_mod : n) * o.stats_c + n0 + ch) * 2;
@@ -334,11 +342,11 @@ __device__ __forceinline__ void stats_tile_end(const EpiArgs& o, uint8_t* stage_
                 }
             }
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_id, 128);
     } else {
         __syncwarp();
         if (tile_ok && n_first < o.N) {
-            const float* red = reinterpret_cast<const float*>(stage_out + q * 8192 + 4096);
+            const float* red = reinterpret_cast<const float*>(red0 + q * 8192);
             for (int ch = lane; ch < o.block_n; ch += 32) {
                 double* d = stats + ((int64_t)(o.z_mod > 0 ? n_first % o.z_mod : n_first) * o.stats_c + n0 + ch) * 2;
                 atomicAdd(d, (double)red[ch * 2]);
@@ -375,6 +383,47 @@ __device__ __forceinline__ StatCtx make_stat_ctx(const IgemmKParams& P, int tx, 
     return sc;
 }
 
+// Column sums over the warp's 32 rows of a 32-column register chunk, without shared memory: transpose-reduce butterfly.  In
+// step k a lane keeps the half of its remaining columns that its lane bit selects and receives the partner's partial sums of
+// that half (16 + 8 + 4 + 2 + 1 = 31 shuffles); lane l ends with the sum of column l.
+__device__ __forceinline__ float warp_colsum32(float (&a)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? a[i] : a[i + off];
+            const float keep = up ? a[i + off] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return a[0];
+}
+
+// statistics of one register chunk (bf16 output, values exactly as stored): per-column sum / sum of squares over the rows of
+// image set 0 (lanes < rb) and set 1 (lanes >= rb) -> the warp's reduction slots red[set][column][2]
+__device__ __forceinline__ void chunk_stats_regs(const float (&v)[32], bool row_ok, int lane, int rb, float* red, int col0) {
+    float xr[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) xr[i] = row_ok ? __bfloat162float(__float2bfloat16_rn(v[i])) : 0.f;
+#pragma unroll 1
+    for (int set = 0; set < 2; ++set) {
+        const bool any = set == 0 ? rb > 0 : rb < 32;            // warp-uniform
+        float s = 0.f, q = 0.f;
+        if (any) {
+            const bool mine = (rb == 32 || rb == 0) ? true : (set == 0 ? lane < rb : lane >= rb);
+            float a[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = mine ? xr[i] : 0.f;
+            s = warp_colsum32(a, lane);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = mine ? xr[i] * xr[i] : 0.f;
+            q = warp_colsum32(a, lane);
+        }
+        *reinterpret_cast<float2*>(red + set * 512 + (col0 + lane) * 2) = make_float2(s, q);
+    }
+}
+
 // one 32-column chunk of the accumulator row: bias, activation, conversion, staging, and - once a full 128-byte row
 // segment is staged - statistics and the global stores
 __device__ __forceinline__ void epilogue_chunk(const EpiArgs& o, int c, const uint32_t (&raw)[32], float bl, int n0,
@@ -384,8 +433,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& o, int c, const ui
     const int esz = f32 ? 4 : 2;
     const int ch0 = n0 + c;
     float v[32];
-    if (o.direct && o.kind == ACLGAN_OUT_BF16 && !st && o.mirror == 0) {
-        // no shared memory at all: broadcast bias loads, each lane stores its own row's 64 bytes
+    if (o.direct && o.kind == ACLGAN_OUT_BF16) {
+        // no shared-memory staging: broadcast bias loads, each lane stores its own row's 64 bytes; the fused statistics are
+        // reduced across the warp's rows with a shuffle butterfly straight from the registers
         const float4* bp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(o.bias) + ch0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -402,15 +452,29 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& o, int c, const ui
             for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * o.slope;
         }
         if (rc.valid) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(o.ptr0) + rc.pix0 + chan_off(o, ch0));
+            uint4 qv[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                uint4 qv;
-                qv.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); qv.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                qv.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); qv.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                dst[i] = qv;
+                qv[i].x = pack_bf16x2(v[8 * i], v[8 * i + 1]); qv[i].y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+                qv[i].z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); qv[i].w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            }
+            __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(o.ptr0) + rc.pix0 + chan_off(o, ch0);
+            uint4* dst = reinterpret_cast<uint4*>(base);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = qv[i];
+            if (rc.ny * rc.nx > 1) {
+                // reflect-halo replicas of border pixels (few lanes): the same 64 bytes again at the mirrored coordinates
+#pragma unroll 1
+                for (int iy = 0; iy < rc.ny; ++iy)
+#pragma unroll 1
+                    for (int ix = (iy == 0 ? 1 : 0); ix < rc.nx; ++ix) {
+                        uint4* d2 = reinterpret_cast<uint4*>(base + (int64_t)(rc.ys[iy] - rc.y) * o.sy + (int64_t)(rc.xs[ix] - rc.x) * o.sx);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) d2[i] = qv[i];
+                    }
             }
         }
+        if (st) chunk_stats_regs(v, rc.valid, lane, stat_rb, reinterpret_cast<float*>(stg + 4096), c);
         return;
     }
     // bias: every lane needs the same 32 values -> broadcast loads (one L1 transaction each; shuffles would go through the
@@ -705,7 +769,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 if (o.stats != 0) sc = make_stat_ctx(P, tx, tz, q, lane, rc);
                 if (fast) epilogue_tile_fast(ea, t_row, n0, rc, stage_out + q * 8192, lane, o.stats != 0 ? sc.rb : 32);
                 else epilogue_tile_generic(ea, t_row, n0, rc);
-                if (o.stats != 0) stats_tile_end(ea, stage_out, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
+                if (o.stats != 0) stats_tile_end(ea, stage_out + 4096, 1, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
             }
             tc_fence_before();
             __syncwarp();
@@ -899,7 +963,7 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
                 if (o.stats != 0) sc = make_stat_ctx(P, tx, tz, q, lane, rc);
                 if (fast) epilogue_tile_fast(ea, t_row, n0, rc, stage_out + q * 8192, lane, o.stats != 0 ? sc.rb : 32);
                 else epilogue_tile_generic(ea, t_row, n0, rc);
-                if (o.stats != 0) stats_tile_end(ea, stage_out, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
+                if (o.stats != 0) stats_tile_end(ea, stage_out + 4096, 1, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
             }
             tc_fence_before();
             __syncwarp();
@@ -930,6 +994,7 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
 #define ACLGAN_SEG_MAXREG 168     // leaves registers for a co-resident element-wise CTA of another chain (see seg_smem_bytes)
 #endif
 constexpr int kSegMaxStages = 6;
+constexpr int kSegThreads = 384;       // warps 0-3: TMA / MMA / TMEM roles, 4-7 and 8-11: two epilogue groups
 constexpr int kSegSmemBytes = 232448;   // the whole opt-in budget; the ring is sized from it by the host
 
 // One pipeline stage = one filter row of one 64-channel chunk: the A segment (seg_rows pixels) and the weight tiles of
@@ -983,7 +1048,7 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kSegMaxStages; ++s) { mbar_init(&full_bar[s], PAIR ? 2 : 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], PAIR ? 8 : 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], (PAIR ? 8 : 4) * (P.seg_esplit ? P.seg_egroups : 1)); }
         mbar_init(bres_bar, 1);
         fence_barrier_init();
     }
@@ -1126,16 +1191,26 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
         if (prof) {
             P.prof[blockIdx.x * 16 + 2] = clock64() - t_begin; P.prof[blockIdx.x * 16 + 3] = t_wfull; P.prof[blockIdx.x * 16 + 4] = t_wacc;
         }
-    } else if (warp >= 4) {
-        // ---------------- epilogue (own 128 rows) ----------------
+    } else if (warp >= 4 && ((warp - 4) >> 2) < P.seg_egroups) {
+        // ---------------- epilogue (own 128 rows; with two groups: own half of the accumulator columns) ----------------
         const int q = warp & 3;
+        const int eg = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         const aclgan_out_spec& o = P.out;
-        const EpiArgs ea = make_epi_args(P);
+        EpiArgs ea = make_epi_args(P);
+        const bool alternate = P.seg_egroups > 1 && !P.seg_esplit;      // group g drains the items with it % 2 == g (accumulator set g)
+        const int ecols = P.seg_esplit ? P.block_n / P.seg_egroups : P.block_n;      // columns drained by this group
+        const int ecol0 = P.seg_esplit ? eg * ecols : 0;
+        ea.block_n = ecols;
+        // reduction slots: group 0 uses the second half of each warp's 8 KB staging area, group 1 (direct epilogue only: the
+        // staging half is unused) the first half; epilogue_chunk finds them at stg + 4096
+        uint8_t* const stg = stage_out + q * 8192 - (eg != 0 ? 4096 : 0);
+        const uint8_t* const red0 = stage_out + (eg != 0 ? 0 : 4096);
         int it = 0;
         long long t_wt = 0;
         const long long t_begin = prof ? clock64() : 0;
         for (int item = worker; item < total_items; item += n_workers, ++it) {
+            if (alternate && (it & 1) != eg) continue;
             const int acc = it % acc_sets;
             const uint32_t acc_phase = (it / acc_sets) & 1;
             const int nt = item % P.n_tiles;
@@ -1167,18 +1242,18 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
                 rc.pix0 = o.off + image_off(o, rc.z) + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
                 rc.ny = mirror_coords(rc.y, o.H, o.mirror, rc.ys);
                 rc.nx = mirror_coords(rc.x, o.W, o.mirror, rc.xs);
-                const uint32_t t_row = tmem_base + acc * set_cols + sub * col_stride + ((uint32_t)(q * 32) << 16);
-                const int n0 = nt * P.block_n;
+                const uint32_t t_row = tmem_base + acc * set_cols + sub * col_stride + ecol0 + ((uint32_t)(q * 32) << 16);
+                const int n0 = nt * P.block_n + ecol0;
                 const int group = (o.kind == ACLGAN_OUT_F32) ? 32 : 64;
-                const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) && (o.d2s_c % group == 0) &&
-                                  (n0 + P.block_n <= o.C) && (o.act != ACLGAN_ACT_TANH);
+                const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (ecols >= group) && (o.d2s_c % group == 0) &&
+                                  (n0 + ecols <= o.C) && (o.act != ACLGAN_ACT_TANH);
                 StatCtx sc;
                 if (o.stats != 0) sc = make_stat_ctx(P, tx, tz, q, lane, rc);
                 const long long te = prof ? clock64() : 0;
-                if (fast) epilogue_tile_fast(ea, t_row, n0, rc, stage_out + q * 8192, lane, o.stats != 0 ? sc.rb : 32,
+                if (fast) epilogue_tile_fast(ea, t_row, n0, rc, stg, lane, o.stats != 0 ? sc.rb : 32,
                                              (prof && warp == 4) ? P.prof + blockIdx.x * 16 + 8 : nullptr);
                 else epilogue_tile_generic(ea, t_row, n0, rc);
-                if (o.stats != 0) stats_tile_end(ea, stage_out, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
+                if (o.stats != 0) stats_tile_end(ea, red0, 1 + eg, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
                 if (prof && warp == 4 && lane == 0) P.prof[blockIdx.x * 16 + 7] += clock64() - te;
             }
             tc_fence_before();
@@ -1280,6 +1355,8 @@ static int fill_kparams(const aclgan_igemm_plan* pl, IgemmKParams* kp) {
     kp->seg_a_bytes = kp->seg_btile_bytes = kp->seg_stage_bytes = kp->seg_ns = 0;
     kp->seg_msub = 1;
     kp->seg_bres = 0;
+    kp->seg_egroups = 1;
+    kp->seg_esplit = 0;
     kp->prof = g_prof;
     {
         const char* ed = getenv("ACLGAN_EPI_DIRECT");
@@ -1358,6 +1435,17 @@ static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repea
         const char* e = getenv("ACLGAN_SEG_MSUB");
         if (e != nullptr) m_sub = (atoi(e) == 2 && 2 * plan->block_n <= 512) ? 2 : 1;
     }
+    // two epilogue warp groups (N >= 128: columns split in halves; else alternating tiles) whenever every tile takes the direct
+    // bf16 epilogue
+    {
+        const char* e = getenv("ACLGAN_EPI_GROUPS");
+        const aclgan_out_spec& o = plan->out;
+        const bool ok = plan->block_n >= 64 && o.kind == ACLGAN_OUT_BF16 && kp.epi_direct && o.sc == 1 && o.C % plan->block_n == 0 &&
+                        o.act != ACLGAN_ACT_TANH && o.d2s_c % 64 == 0 && m_sub == 1;
+        kp.seg_egroups = (ok && (e == nullptr || atoi(e) != 1)) ? 2 : 1;
+        kp.seg_esplit = plan->block_n >= 128 ? 1 : 0;
+        if (kp.seg_egroups == 2 && !kp.seg_esplit && 2 * (plan->block_n < 32 ? 32 : plan->block_n) > 512) kp.seg_egroups = 1;
+    }
     // shared memory requested per CTA: not all of it when it is not needed, so that an element-wise CTA of another chain
     // (<= 24 KB) can be co-resident on the SM and run under the tensor pipe's shadow (env ACLGAN_SEG_SMEM_KB overrides)
     static int seg_smem_default = 0;
@@ -1390,12 +1478,12 @@ static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repea
         const int items = ((m_tiles + 2 * m_sub - 1) / (2 * m_sub)) * plan->n_tiles;
         int clusters = num_sms() / 2;
         if (items < clusters) clusters = items;
-        for (int i = 0; i < repeat; ++i) igemm_seg_pair_kernel<<<2 * clusters, kThreads, seg_smem, stream>>>(kp);
+        for (int i = 0; i < repeat; ++i) igemm_seg_pair_kernel<<<2 * clusters, kSegThreads, seg_smem, stream>>>(kp);
     } else {
         const int items = ((m_tiles + m_sub - 1) / m_sub) * plan->n_tiles;
         if (items <= 0) return ACLGAN_OK;
         const int grid = items < num_sms() ? items : num_sms();
-        for (int i = 0; i < repeat; ++i) igemm_seg_kernel<<<grid, kThreads, seg_smem, stream>>>(kp);
+        for (int i = 0; i < repeat; ++i) igemm_seg_kernel<<<grid, kSegThreads, seg_smem, stream>>>(kp);
     }
     return (int)cudaGetLastError();
 }

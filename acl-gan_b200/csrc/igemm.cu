@@ -29,6 +29,7 @@ constexpr int kPipeBytes = kMaxStages * (kABytes + kBBytesMax);   // 192 KB ring
 constexpr int kStageOutBytes = 4 * 2 * 4096;    // epilogue staging: 4 warps x 2 planes x (32 rows x 128 B)
 constexpr int kSmemBytes = kPipeBytes + kStageOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kThreads = 256;
+constexpr int kEpiThreads = 384;       // warps 0-3: TMA / MMA / TMEM roles, 4-7 and 8-11: two epilogue warp groups
 
 struct alignas(64) IgemmKParams {
     CUtensorMap a[2][ACLGAN_MAX_AVARIANTS];
@@ -580,7 +581,7 @@ __device__ __noinline__ void epilogue_tile_fast(const EpiArgs o, uint32_t t_row,
     if (pt && lane == 0) { pt[0] += clock64() - pt0; pt[1] += pt_ld; pt[2] += pt_chunk; }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmKParams P) {
+__global__ void __launch_bounds__(kEpiThreads, 1) igemm_kernel(const __grid_constant__ IgemmKParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_out = smem + kPipeBytes;
@@ -614,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 4);
+            mbar_init(&tempty_bar[s], 4 * (P.seg_esplit ? P.seg_egroups : 1));
         }
         fence_barrier_init();
     }
@@ -719,14 +720,22 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             if (P.debug == 2) mbar_arrive(&tfull_bar[acc]);
             else umma_commit(&tfull_bar[acc]);
         }
-    } else if (warp >= 4) {
-        // ---------------- epilogue ----------------
+    } else if (warp >= 4 && ((warp - 4) >> 2) < P.seg_egroups) {
+        // ---------------- epilogue (one or two warp groups, see IgemmKParams::seg_egroups) ----------------
         const int q = warp & 3;              // TMEM lane quarter this warp may read
+        const int eg = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         const aclgan_out_spec& o = P.out;
-        const EpiArgs ea = make_epi_args(P);
+        EpiArgs ea = make_epi_args(P);
+        const bool alternate = P.seg_egroups > 1 && !P.seg_esplit;
+        const int ecols = P.seg_esplit ? P.block_n / P.seg_egroups : P.block_n;
+        const int ecol0 = P.seg_esplit ? eg * ecols : 0;
+        ea.block_n = ecols;
+        uint8_t* const stg = stage_out + q * 8192 - (eg != 0 ? 4096 : 0);
+        const uint8_t* const red0 = stage_out + (eg != 0 ? 0 : 4096);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            if (alternate && (it & 1) != eg) continue;
             const int acc = it % acc_sets;
             const uint32_t acc_phase = (it / acc_sets) & 1;
             const int grp = tile / group_items;
@@ -760,16 +769,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                 rc.pix0 = o.off + P.group_off[grp] + image_off(o, rc.z) + (int64_t)rc.y * o.sy + (int64_t)rc.x * o.sx;
                 rc.ny = mirror_coords(rc.y, o.H, o.mirror, rc.ys);
                 rc.nx = mirror_coords(rc.x, o.W, o.mirror, rc.xs);
-                const uint32_t t_row = tmem_base + acc * set_cols + sub * col_stride + ((uint32_t)(q * 32) << 16);
-                const int n0 = nt * P.block_n;
+                const uint32_t t_row = tmem_base + acc * set_cols + sub * col_stride + ecol0 + ((uint32_t)(q * 32) << 16);
+                const int n0 = nt * P.block_n + ecol0;
                 const int group = (o.kind == ACLGAN_OUT_F32) ? 32 : 64;
-                const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) && (o.d2s_c % group == 0) &&
-                                  (n0 + P.block_n <= o.C) && (o.act != ACLGAN_ACT_TANH) && (P.debug != 5);
+                const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (ecols >= group) && (o.d2s_c % group == 0) &&
+                                  (n0 + ecols <= o.C) && (o.act != ACLGAN_ACT_TANH) && (P.debug != 5);
                 StatCtx sc;
                 if (o.stats != 0) sc = make_stat_ctx(P, tx, tz, q, lane, rc);
-                if (fast) epilogue_tile_fast(ea, t_row, n0, rc, stage_out + q * 8192, lane, o.stats != 0 ? sc.rb : 32);
+                if (fast) epilogue_tile_fast(ea, t_row, n0, rc, stg, lane, o.stats != 0 ? sc.rb : 32);
                 else epilogue_tile_generic(ea, t_row, n0, rc);
-                if (o.stats != 0) stats_tile_end(ea, stage_out + 4096, 1, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
+                if (o.stats != 0) stats_tile_end(ea, red0, 1 + eg, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
             }
             tc_fence_before();
             __syncwarp();
@@ -798,7 +807,7 @@ constexpr int kPairStages = 6;
 constexpr int kPairStageBytes = kABytes + kBBytesMax / 2;                  // 16 KB A + up to 16 KB B half
 constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kStageOutBytes + 1024 + 256;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kEpiThreads, 1)
 igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -830,7 +839,7 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 8);     // 4 epilogue warps of each CTA
+            mbar_init(&tempty_bar[s], 8 * (P.seg_esplit ? P.seg_egroups : 1));     // 4 epilogue warps per group of each CTA
         }
         fence_barrier_init();
     }
@@ -916,14 +925,22 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
             }
             umma_commit_pair(&tfull_bar[acc], 3);
         }
-    } else if (warp >= 4) {
-        // ---------------- epilogue (both CTAs, own 128 rows) ----------------
+    } else if (warp >= 4 && ((warp - 4) >> 2) < P.seg_egroups) {
+        // ---------------- epilogue (both CTAs, own 128 rows; one or two warp groups, see IgemmKParams::seg_egroups) ----------------
         const int q = warp & 3;
+        const int eg = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         const aclgan_out_spec& o = P.out;
-        const EpiArgs ea = make_epi_args(P);
+        EpiArgs ea = make_epi_args(P);
+        const bool alternate = P.seg_egroups > 1 && !P.seg_esplit;
+        const int ecols = P.seg_esplit ? P.block_n / P.seg_egroups : P.block_n;
+        const int ecol0 = P.seg_esplit ? eg * ecols : 0;
+        ea.block_n = ecols;
+        uint8_t* const stg = stage_out + q * 8192 - (eg != 0 ? 4096 : 0);
+        const uint8_t* const red0 = stage_out + (eg != 0 ? 0 : 4096);
         int it = 0;
         for (int item = cluster_id; item < total_items; item += n_clusters, ++it) {
+            if (alternate && (it & 1) != eg) continue;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int grp = item / group_items;
@@ -954,16 +971,16 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             if (P.debug != 4) {
-                const uint32_t t_row = tmem_base + acc * col_stride + ((uint32_t)(q * 32) << 16);
-                const int n0 = nt * P.block_n;
+                const uint32_t t_row = tmem_base + acc * col_stride + ecol0 + ((uint32_t)(q * 32) << 16);
+                const int n0 = nt * P.block_n + ecol0;
                 const int group = (o.kind == ACLGAN_OUT_F32) ? 32 : 64;
-                const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (P.block_n >= group) && (o.d2s_c % group == 0) &&
-                                  (n0 + P.block_n <= o.C);
+                const bool fast = (o.sc == 1) && (o.kind != ACLGAN_OUT_F32_ATOMIC) && (ecols >= group) && (o.d2s_c % group == 0) &&
+                                  (n0 + ecols <= o.C);
                 StatCtx sc;
                 if (o.stats != 0) sc = make_stat_ctx(P, tx, tz, q, lane, rc);
-                if (fast) epilogue_tile_fast(ea, t_row, n0, rc, stage_out + q * 8192, lane, o.stats != 0 ? sc.rb : 32);
+                if (fast) epilogue_tile_fast(ea, t_row, n0, rc, stg, lane, o.stats != 0 ? sc.rb : 32);
                 else epilogue_tile_generic(ea, t_row, n0, rc);
-                if (o.stats != 0) stats_tile_end(ea, stage_out + 4096, 1, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
+                if (o.stats != 0) stats_tile_end(ea, red0, 1 + eg, q, lane, n0, sc.combine, sc.n_first, sc.straddle, sub_ok);
             }
             tc_fence_before();
             __syncwarp();
@@ -1373,6 +1390,19 @@ static int fill_kparams(const aclgan_igemm_plan* pl, IgemmKParams* kp) {
     return ACLGAN_OK;
 }
 
+// Two epilogue warp groups whenever every tile of the launch takes the direct bf16 epilogue (no shared-memory staging: group 1
+// has none): N >= 128: the groups split the accumulator columns in halves; N = 64: they alternate tiles (needs two accumulator
+// sets).  acc_cols = TMEM columns of one accumulator set.  env ACLGAN_EPI_GROUPS=1 switches back to one group.
+static void decide_egroups(const aclgan_igemm_plan* plan, IgemmKParams& kp, int acc_cols) {
+    const char* e = getenv("ACLGAN_EPI_GROUPS");
+    const aclgan_out_spec& o = plan->out;
+    const bool ok = plan->block_n >= 64 && o.kind == ACLGAN_OUT_BF16 && kp.epi_direct && o.sc == 1 && o.C % plan->block_n == 0 &&
+                    o.act != ACLGAN_ACT_TANH && o.d2s_c % 64 == 0 && kp.debug == 0;
+    kp.seg_egroups = (ok && (e == nullptr || atoi(e) != 1)) ? 2 : 1;
+    kp.seg_esplit = plan->block_n >= 128 ? 1 : 0;
+    if (kp.seg_egroups == 2 && !kp.seg_esplit && 2 * acc_cols > 512) kp.seg_egroups = 1;
+}
+
 // segment-mode launch (returns -100 when the plan is not eligible and the plain kernels must run it)
 static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repeat, cudaStream_t stream) {
     const char* env = getenv("ACLGAN_SEGK");
@@ -1435,17 +1465,8 @@ static int launch_seg(const aclgan_igemm_plan* plan, IgemmKParams& kp, int repea
         const char* e = getenv("ACLGAN_SEG_MSUB");
         if (e != nullptr) m_sub = (atoi(e) == 2 && 2 * plan->block_n <= 512) ? 2 : 1;
     }
-    // two epilogue warp groups (N >= 128: columns split in halves; else alternating tiles) whenever every tile takes the direct
-    // bf16 epilogue
-    {
-        const char* e = getenv("ACLGAN_EPI_GROUPS");
-        const aclgan_out_spec& o = plan->out;
-        const bool ok = plan->block_n >= 64 && o.kind == ACLGAN_OUT_BF16 && kp.epi_direct && o.sc == 1 && o.C % plan->block_n == 0 &&
-                        o.act != ACLGAN_ACT_TANH && o.d2s_c % 64 == 0 && m_sub == 1;
-        kp.seg_egroups = (ok && (e == nullptr || atoi(e) != 1)) ? 2 : 1;
-        kp.seg_esplit = plan->block_n >= 128 ? 1 : 0;
-        if (kp.seg_egroups == 2 && !kp.seg_esplit && 2 * (plan->block_n < 32 ? 32 : plan->block_n) > 512) kp.seg_egroups = 1;
-    }
+    decide_egroups(plan, kp, m_sub * (plan->block_n < 32 ? 32 : plan->block_n));
+    if (m_sub != 1) kp.seg_egroups = 1;
     // shared memory requested per CTA: not all of it when it is not needed, so that an element-wise CTA of another chain
     // (<= 24 KB) can be co-resident on the SM and run under the tensor pipe's shadow (env ACLGAN_SEG_SMEM_KB overrides)
     static int seg_smem_default = 0;
@@ -1544,17 +1565,19 @@ extern "C" int aclgan_igemm_launch_repeat(const aclgan_igemm_plan* plan, int rep
                 if (e != cudaSuccess) return (int)e;
                 pair_attr = true;
             }
+            decide_egroups(plan, kp, plan->block_n < 32 ? 32 : plan->block_n);
             const int items = ((m_tiles_all + 1) / 2) * plan->n_tiles * n_groups;
             int clusters = num_sms() / 2;
             if (items < clusters) clusters = items;
             for (int i = 0; i < repeat; ++i)
-                igemm_pair_kernel<<<2 * clusters, kThreads, kPairSmemBytes, (cudaStream_t)stream>>>(kp);
+                igemm_pair_kernel<<<2 * clusters, kEpiThreads, kPairSmemBytes, (cudaStream_t)stream>>>(kp);
             return (int)cudaGetLastError();
         }
     }
+    decide_egroups(plan, kp, kp.m_sub * (plan->block_n < 32 ? 32 : plan->block_n));
     const int total = ((m_tiles_all + kp.m_sub - 1) / kp.m_sub) * plan->n_tiles * kp.n_groups;
     if (total <= 0) return ACLGAN_OK;
     const int grid = total < num_sms() ? total : num_sms();
-    for (int i = 0; i < repeat; ++i) igemm_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(kp);
+    for (int i = 0; i < repeat; ++i) igemm_kernel<<<grid, kEpiThreads, kSmemBytes, (cudaStream_t)stream>>>(kp);
     return (int)cudaGetLastError();
 }

@@ -11,7 +11,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libaclgan_b200.so")
+LIB_PATH = os.environ.get("ACLGAN_LIB") or os.path.join(HERE, "libaclgan_b200.so")      # (ACLGAN_LIB: perf triage with a variant build)
 
 MAX_TAPS = 64
 MAX_AVARIANTS = 4

@@ -41,7 +41,7 @@ __host__ __device__ inline AdamTile adam_tile(const aclgan_adam_tensor& T) {
     t.tci = T.d[1] < 32 ? T.d[1] : 32;
     t.tco = T.d[0] < 32 ? T.d[0] : 32;
     while (t.tco > 8 && t.tco * (t.tci * t.tp + 1) > kAdamTileFloats) t.tco /= 2;
-    if (t.tco * (t.tci * t.tp + 1) > kAdamTileFloats) t.flat = 2;      // (no shipped layer: > 100 taps) scalar fallback
+    if (t.tco * (t.tci * t.tp + 1) > kAdamTileFloats || t.taps > 64) t.flat = 2;      // (no shipped layer: > 64 taps) scalar fallback
     t.co_stride = t.tci * t.tp + 1;
     t.n_ct = (T.d[1] + t.tci - 1) / t.tci;
     if (t.flat) t.units = (int)((numel + kAdamFlat - 1) / kAdamFlat);
@@ -132,69 +132,85 @@ __global__ void __launch_bounds__(kAdamThreads, 4) adam_kernel(const aclgan_adam
 
     const int co0 = (unit / G.n_ct) * G.tco, ci0 = (unit % G.n_ct) * G.tci;
     const int nco = min(G.tco, T.d[0] - co0), nci = min(G.tci, T.d[1] - ci0);      // valid extent of this tile
-    const int KW = T.d[3];
+    const int taps = G.taps;
 
-    // Index arithmetic without divisions: a warp walks (slow index, tap) rows, its lanes are the fast index; the loops are
-    // unrolled with all loads of a batch issued before the first use (the kernel is latency-bound otherwise: one 4-byte load
-    // in flight per thread is ~1 TB/s on the whole chip).
+    // The kernel is bound by instruction issue unless the per-element index arithmetic is kept to a handful of 32-bit
+    // operations (the first tiled version spent 360 thread instructions per parameter, ncu: issue slots 73 % busy at 2.3 TB/s):
+    //  * per-tap offsets (kh * s_kh + kw * s_kw) of the gradient and of both packings come from small shared-memory tables;
+    //  * a warp walks (slow index, tap) rows with incremental (no division) updates, its lanes are the fast index;
+    //  * all offsets are 32-bit (every buffer of a parameter group is far below 2^31 elements);
+    //  * loops are unrolled with the loads of a batch issued before the first use (memory-level parallelism).
+    __shared__ int tab[3][64];
+    if (threadIdx.x < taps) {
+        const int kh = threadIdx.x / T.d[3], kw = threadIdx.x - kh * T.d[3];
+        tab[0][threadIdx.x] = (int)(kh * T.gs[2] + kw * T.gs[3]);
+        tab[1][threadIdx.x] = (int)(kh * T.aff[0][3] + kw * T.aff[0][4]);
+        tab[2][threadIdx.x] = (int)(kh * T.aff[1][3] + kw * T.aff[1][4]);
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kWarps = kAdamThreads / 32;
     constexpr int U = 8;
+    const int q16 = kWarps / taps, r16 = kWarps % taps;       // advancing a (slow, tap) row index by kWarps
 
     // phase 1: gradient tile -> shared memory, read in the gradient layout's fastest order
     {
         const bool co_fast = (T.gs[0] == 1 || T.gs[0] == -1);
         const int nf = co_fast ? nco : nci, ns = co_fast ? nci : nco;            // fast / slow extents
-        const int64_t gf = co_fast ? T.gs[0] : T.gs[1], gsl = co_fast ? T.gs[1] : T.gs[0];
+        const int gf = (int)(co_fast ? T.gs[0] : T.gs[1]), gsl = (int)(co_fast ? T.gs[1] : T.gs[0]);
         const int sf = co_fast ? G.co_stride : G.tp, ss = co_fast ? G.tp : G.co_stride;
-        const int64_t g0 = (int64_t)co0 * T.gs[0] + (int64_t)ci0 * T.gs[1];
-        const int rows = ns * G.taps;
-        const int q16 = kWarps / G.taps, r16 = kWarps % G.taps;
-        int sl = warp / G.taps, tap = warp % G.taps;                               // row r = sl * taps + tap
+        const float* __restrict__ gl = g + ((int64_t)co0 * T.gs[0] + (int64_t)ci0 * T.gs[1]) + lane * gf;
+        float* tl = tile + lane * sf;
+        const int rows = ns * taps;
+        const bool lane_ok = lane < nf;
+        int sl = warp / taps, tap = warp - (warp / taps) * taps;                   // row r = sl * taps + tap
         for (int r0 = warp; r0 < rows; r0 += U * kWarps) {
             float val[U];
             int so[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const bool ok = (r0 + u * kWarps < rows) && lane < nf;
-                const int kh = tap / KW, kw = tap - kh * KW;
-                so[u] = ok ? sl * ss + lane * sf + tap : -1;
-                if (ok) val[u] = g[g0 + (int64_t)sl * gsl + (int64_t)lane * gf + kh * T.gs[2] + kw * T.gs[3]];
+                const bool ok = (r0 + u * kWarps < rows) && lane_ok;
+                so[u] = ok ? sl * ss + tap : -1;
+                if (ok) val[u] = gl[sl * gsl + tab[0][tap]];
                 sl += q16; tap += r16;
-                if (tap >= G.taps) { tap -= G.taps; ++sl; }
+                if (tap >= taps) { tap -= taps; ++sl; }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (so[u] >= 0) tile[so[u]] = val[u];
+                if (so[u] >= 0) tl[so[u]] = val[u];
         }
     }
     __syncthreads();
     // phase 2: the update in OIHW order: one warp per output channel, lanes along the contiguous (ci, tap) run of p / m / v
     {
-        const int run = nci * G.taps;
-        const int q32 = 32 / G.taps, r32 = 32 % G.taps;
+        const int run = nci * taps;
+        const int q32 = 32 / taps, r32 = 32 % taps;
         constexpr int V = 4;
         for (int co_l = warp; co_l < nco; co_l += kWarps) {
-            const int64_t e0 = ((int64_t)(co0 + co_l) * T.d[1] + ci0) * G.taps;
-            int ci_l = lane / G.taps, tap = lane % G.taps;
+            const int64_t e0 = ((int64_t)(co0 + co_l) * T.d[1] + ci0) * taps;
+            float* __restrict__ pp = p + e0;
+            float* __restrict__ mm = m + e0;
+            float* __restrict__ vp = v + e0;
+            float* trow = tile + co_l * G.co_stride;
+            int ci_l = lane / taps, tap = lane - (lane / taps) * taps;
             for (int i0 = lane; i0 < run; i0 += V * 32) {
                 float pv[V], mv[V], vv[V];
                 int so[V];
 #pragma unroll
                 for (int u = 0; u < V; ++u) {
                     const int i = i0 + u * 32;
-                    so[u] = i < run ? co_l * G.co_stride + ci_l * G.tp + tap : -1;
-                    if (i < run) { pv[u] = p[e0 + i]; mv[u] = m[e0 + i]; vv[u] = v[e0 + i]; }
+                    so[u] = i < run ? ci_l * G.tp + tap : -1;
+                    if (i < run) { pv[u] = pp[i]; mv[u] = mm[i]; vv[u] = vp[i]; }
                     ci_l += q32; tap += r32;
-                    if (tap >= G.taps) { tap -= G.taps; ++ci_l; }
+                    if (tap >= taps) { tap -= taps; ++ci_l; }
                 }
 #pragma unroll
                 for (int u = 0; u < V; ++u) {
                     const int i = i0 + u * 32;
                     if (so[u] >= 0) {
-                        const float np = adam_update(c, pv[u], tile[so[u]], mv[u], vv[u]);
-                        m[e0 + i] = mv[u]; v[e0 + i] = vv[u]; p[e0 + i] = np;
-                        tile[so[u]] = np;
+                        const float np = adam_update(c, pv[u], trow[so[u]], mv[u], vv[u]);
+                        mm[i] = mv[u]; vp[i] = vv[u]; pp[i] = np;
+                        trow[so[u]] = np;
                     }
                 }
             }
@@ -207,25 +223,27 @@ __global__ void __launch_bounds__(kAdamThreads, 4) adam_kernel(const aclgan_adam
         if (T.pk[k][0] == 0) continue;
         const bool co_fast = (T.aff[k][1] == 1 || T.aff[k][1] == -1);
         const int nf = co_fast ? nco : nci, ns = co_fast ? nci : nco;
-        const int64_t af = co_fast ? T.aff[k][1] : T.aff[k][2], asl = co_fast ? T.aff[k][2] : T.aff[k][1];
+        const int af = (int)(co_fast ? T.aff[k][1] : T.aff[k][2]), asl = (int)(co_fast ? T.aff[k][2] : T.aff[k][1]);
         const int sf = co_fast ? G.co_stride : G.tp, ss = co_fast ? G.tp : G.co_stride;
-        const int64_t o0 = T.aff[k][0] + (int64_t)co0 * T.aff[k][1] + (int64_t)ci0 * T.aff[k][2];
-        __nv_bfloat16* hi_p = reinterpret_cast<__nv_bfloat16*>(T.pk[k][0]);
-        __nv_bfloat16* lo_p = reinterpret_cast<__nv_bfloat16*>(T.pk[k][1]);
-        const int rows = ns * G.taps;
-        const int q16 = kWarps / G.taps, r16 = kWarps % G.taps;
-        int sl = warp / G.taps, tap = warp % G.taps;
-        for (int r = warp; r < rows; r += kWarps) {
-            if (lane < nf) {
-                const int kh = tap / KW, kw = tap - kh * KW;
-                const float np = tile[sl * ss + lane * sf + tap];
-                const int64_t o = o0 + (int64_t)sl * asl + (int64_t)lane * af + kh * T.aff[k][3] + kw * T.aff[k][4];
+        const int64_t o0 = T.aff[k][0] + (int64_t)co0 * T.aff[k][1] + (int64_t)ci0 * T.aff[k][2] + (int64_t)lane * af;
+        __nv_bfloat16* __restrict__ hi_p = reinterpret_cast<__nv_bfloat16*>(T.pk[k][0]) + o0;
+        __nv_bfloat16* __restrict__ lo_p = reinterpret_cast<__nv_bfloat16*>(T.pk[k][1]) + o0;
+        const float* tl = tile + lane * sf;
+        const int* tb = tab[1 + k];
+        const int rows = ns * taps;
+        const bool two = T.planes == 2;
+        int sl = warp / taps, tap = warp - (warp / taps) * taps;
+        if (lane < nf) {
+#pragma unroll 4
+            for (int r = warp; r < rows; r += kWarps) {
+                const float np = tl[sl * ss + tap];
+                const int o = sl * asl + tb[tap];
                 const __nv_bfloat16 hi = __float2bfloat16_rn(np);
                 hi_p[o] = hi;
-                if (T.planes == 2) lo_p[o] = __float2bfloat16_rn(np - __bfloat162float(hi));
+                if (two) lo_p[o] = __float2bfloat16_rn(np - __bfloat162float(hi));
+                sl += q16; tap += r16;
+                if (tap >= taps) { tap -= taps; ++sl; }
             }
-            sl += q16; tap += r16;
-            if (tap >= G.taps) { tap -= G.taps; ++sl; }
         }
     }
 }

@@ -1398,8 +1398,11 @@ static void decide_egroups(const aclgan_igemm_plan* plan, IgemmKParams& kp, int 
     const aclgan_out_spec& o = plan->out;
     const bool ok = plan->block_n >= 64 && o.kind == ACLGAN_OUT_BF16 && kp.epi_direct && o.sc == 1 && o.C % plan->block_n == 0 &&
                     o.act != ACLGAN_ACT_TANH && o.d2s_c % 64 == 0 && kp.debug == 0;
-    kp.seg_egroups = (ok && (e == nullptr || atoi(e) != 1)) ? 2 : 1;
-    kp.seg_esplit = plan->block_n >= 128 ? 1 : 0;
+    // narrow tiles (N = 16 | 32: image-gradient planes of the first layers) take the generic epilogue for every tile, which uses
+    // no staging either: alternating groups there too
+    const bool generic_all = plan->block_n < (o.kind == ACLGAN_OUT_F32 ? 32 : 64) && o.stats == 0 && kp.debug == 0;
+    kp.seg_egroups = ((ok || generic_all) && (e == nullptr || atoi(e) != 1)) ? 2 : 1;
+    kp.seg_esplit = (ok && plan->block_n >= 128) ? 1 : 0;
     if (kp.seg_egroups == 2 && !kp.seg_esplit && 2 * acc_cols > 512) kp.seg_egroups = 1;
 }
 

@@ -92,6 +92,14 @@ static bool window_vseg_enabled() {
     return e == nullptr || atoi(e) != 0;
 }
 
+// fold mode of the first (few-INPUT-channel) conv's data gradient: the same trick on the transposed problem (ACLGAN_FOLD_DGRAD=0:
+// one 16-column MMA group per tap)
+static bool fold_dgrad_enabled(const aclgan_conv_desc* cd) {
+    const char* e = getenv("ACLGAN_FOLD_DGRAD");
+    return (e == nullptr || atoi(e) != 0) && cd->window == ACLGAN_WINDOW_IN && cd->stride == 1 && cd->k <= 8 && cd->k > 1 &&
+           cd->cin <= 8;
+}
+
 static bool wgrad_seg_enabled() {
     const char* e = getenv("ACLGAN_WGRAD_SEG");
     return e == nullptr || atoi(e) != 0;
@@ -120,6 +128,11 @@ extern "C" int aclgan_packed_weight_shape(const aclgan_conv_desc* cd, int transp
         *k_total = (int64_t)cd->k * k_channels(cd, 0);
         return ACLGAN_OK;
     }
+    if (transposed && fold_dgrad_enabled(cd)) {     // rows n = (k-1-kw) * 8 + ci, k = (k-1-kh) * Cs + co: the flipped filter, columns folded into N
+        *rows = 64;
+        *k_total = (int64_t)cd->k * k_channels(cd, 1);
+        return ACLGAN_OK;
+    }
     if (uses_window(cd, transposed)) *k_total = (int64_t)cd->k * 64;
     else *k_total = (int64_t)cd->k * cd->k * k_channels(cd, transposed);
     return ACLGAN_OK;
@@ -130,6 +143,8 @@ extern "C" int64_t aclgan_packed_weight_index(const aclgan_conv_desc* cd, int tr
     int64_t rows, kt;
     aclgan_packed_weight_shape(cd, transposed, &rows, &kt);
     if (!transposed && fold_enabled(cd)) return (int64_t)(kw * 8 + co) * kt + (int64_t)kh * k_channels(cd, 0) + ci;
+    if (transposed && fold_dgrad_enabled(cd))
+        return (int64_t)((cd->k - 1 - kw) * 8 + ci) * kt + (int64_t)(cd->k - 1 - kh) * k_channels(cd, 1) + co;
     if (!uses_window(cd, transposed)) {
         if (!transposed) return (int64_t)co * kt + (int64_t)(kh * cd->k + kw) * k_channels(cd, 0) + ci;
         return (int64_t)ci * kt + (int64_t)(kh * cd->k + kw) * k_channels(cd, 1) + co;
@@ -323,6 +338,32 @@ extern "C" int aclgan_plan_conv_dgrad(const aclgan_conv_desc* cd, const aclgan_a
     aclgan_packed_weight_shape(cd, 1, &rows, &kt);
     for (int pl = 0; pl < dy->planes; ++pl) weight_map2(&p->b[pl], wt[pl], kt, rows, p->block_n);
 
+    if (fold_dgrad_enabled(cd)) {
+        // few input channels (first conv): dX_pad[q][ci] = sum_{kh', kw'} dYz[q + kh' Wz + kw'][co] * W[co][ci][k-1-kh'][k-1-kw'] is the
+        // FORWARD fold problem (see aclgan_plan_conv_fwd) on the zero-bordered dY plane with the flipped filter: the k filter
+        // columns are folded into N (weight row n = kw' * 8 + ci), one tap per filter row, diagonal sum in the epilogue -
+        // k times fewer MMAs than one 16-column MMA group per tap (309 -> ~90 us on the 256 x 256 batch-8 plane)
+        if (cs % 64 != 0 || cs != k_channels(cd, 1)) return ACLGAN_ERR_SHAPE;
+        p->block_n = 64; p->n_tiles = 1;
+        p->fold = k;
+        p->tile_step = 120;
+        p->tiles_x = (int)((total + p->tile_step - 1) / p->tile_step);
+        p->cchunks = cs / 64;
+        p->num_taps = k;
+        for (int pl = 0; pl < dy->planes; ++pl) {
+            plane_map4(&p->a[pl][0], dy->data[pl], cs, total, 1, 1, (int64_t)cs * 2, total * cs * 2, total * cs * 2, 128, 1, 1);
+            weight_map2(&p->b[pl], wt[pl], kt, rows, 64);
+        }
+        for (int t = 0; t < k; ++t) {
+            p->tap_dx[t] = t * wz;
+            p->tap_bk[t] = t * cs;
+        }
+        p->out = *out;
+        if (p->out.C > 8) p->out.C = 8;        // (the folded weight rows hold 8 channel slots per filter column)
+        p->n_groups = 1;
+        p->group_taps = p->num_taps;
+        return ACLGAN_OK;
+    }
     if (cd->window != ACLGAN_WINDOW_OUT) {
         if (cs % 64 != 0 || cs != k_channels(cd, 1)) return ACLGAN_ERR_SHAPE;
         p->cchunks = cs / 64;

@@ -122,10 +122,10 @@ def test_conv_dgrad(monkeypatch, msub, cin, cout, k, s, pad, n, ho, wo, planes):
     torch.manual_seed(1)
     dy = torch.randn(n, cout, ho, wo, device="cuda")
     wt = torch.randn(cout, cin, k, k) * 0.05
-    window = 2 if cout <= 8 else 0          # tiny cout: dY stored with 8 channels, pixel-window dgrad (final conv)
+    window = 2 if cout <= 8 else (1 if cin <= 8 else 0)   # tiny cout: pixel-window dY (final conv); tiny cin: first conv (fold-mode dgrad)
     desc = N.ConvDesc(cin, cout, k, s, pad, window)
     pz = k - 1 if s == 1 else k // 2 - 1
-    cs = 8 if window else ((cout + 63) // 64) * 64
+    cs = 8 if window == 2 else ((cout + 63) // 64) * 64
     act, abuf, dyeff = G.make_act(dy, pz, cs, planes, mode="constant")
     if pz > 0:
         dyeff = dyeff[:, :, pz:pz + ho, pz:pz + wo]

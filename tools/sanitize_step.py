@@ -13,8 +13,9 @@ import trainer as T  # noqa: E402
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 cfg = yaml.safe_load(open(os.path.join(ROOT, "acl-gan_b200", "configs", "male2female.yaml")))
-cfg["gen"].update(dim=16, mlp_dim=32, n_res=2)
-cfg["dis"].update(dim=16)
+DIM = int(os.environ.get("SAN_DIM", "16"))      # 32: res blocks of 128 channels (column-split epilogue groups, CTA pairs)
+cfg["gen"].update(dim=DIM, mlp_dim=32, n_res=2)
+cfg["dis"].update(dim=DIM)
 cfg["display_size"] = 2
 cfg["precision"] = prec
 cfg["cuda_graphs"] = int(os.environ.get("SAN_GRAPHS", "0"))

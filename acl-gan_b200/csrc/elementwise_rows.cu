@@ -173,29 +173,65 @@ __device__ __forceinline__ void add8(V8& acc, uint64_t base, int64_t idx) {
     for (int i = 0; i < 8; ++i) acc.v[i] += t.v[i];
 }
 
+// 8 channels exactly as loaded (16 B of bf16 or 32 B of fp32): the loads of a whole batch of pixels stay in flight in this form
+// (4 registers per bf16 vector) and are unpacked at the point of use
+template <int KIND>
+struct Raw8 {
+    uint4 q[KIND == 0 ? 1 : 2];
+};
+template <int KIND>
+__device__ __forceinline__ Raw8<KIND> ldg_raw(uint64_t base, int64_t idx) {
+    Raw8<KIND> r;
+    if (KIND == 0) {
+        r.q[0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+    } else {
+        const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(base) + idx);
+        r.q[0] = p[0]; r.q[KIND == 0 ? 0 : 1] = p[1];
+    }
+    return r;
+}
+template <int KIND>
+__device__ __forceinline__ V8 unpack8(const Raw8<KIND>& q) {
+    V8 r;
+    if (KIND == 0) {
+        const uint32_t w[4] = {q.q[0].x, q.q[0].y, q.q[0].z, q.q[0].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r.v[2 * i] = __uint_as_float(w[i] << 16);
+            r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+        }
+    } else {
+        const uint4 a = q.q[0], b = q.q[KIND == 0 ? 0 : 1];
+        r.v[0] = __uint_as_float(a.x); r.v[1] = __uint_as_float(a.y); r.v[2] = __uint_as_float(a.z); r.v[3] = __uint_as_float(a.w);
+        r.v[4] = __uint_as_float(b.x); r.v[5] = __uint_as_float(b.y); r.v[6] = __uint_as_float(b.z); r.v[7] = __uint_as_float(b.w);
+    }
+    return r;
+}
+
 // raw loads of pixel x of the current row (no dependent arithmetic): gradient-plane value, dense gradient, y / forward output
 template <int KIND, int MASK, int NORM, int GP, int GR>
 struct PixRaw {
-    V8 g, gr, yv;
+    Raw8<KIND> g, gr;
+    Raw8<(MASK == 2 && !NORM) ? 0 : KIND> yv;      // (MASK 2 reads the bf16 forward output plane)
 };
 
 template <int KIND, int MASK, int NORM, int GP, int GR>
 __device__ __forceinline__ void pix_raw(const aclgan_block_bwd_args& a, const BwdRow& r, int x, int C, PixRaw<KIND, MASK, NORM, GP, GR>& o) {
-    if (GP) o.g = ldg8(a.gp, KIND, r.gp_row + (int64_t)(x + a.gp_pad) * C);
-    if (GR) o.gr = ldg8(a.gr, KIND, r.dense_row + (int64_t)x * C);
-    if (MASK == 1 || NORM) o.yv = ldg8(a.y.ptr, KIND, r.dense_row + (int64_t)x * C);
-    else if (MASK == 2) o.yv = ldg8(a.out.data[0], 0, r.out_row + (int64_t)x * C);
+    if (GP) o.g = ldg_raw<KIND>(a.gp, r.gp_row + (int64_t)(x + a.gp_pad) * C);
+    if (GR) o.gr = ldg_raw<KIND>(a.gr, r.dense_row + (int64_t)x * C);
+    if constexpr (MASK == 1 || NORM) o.yv = ldg_raw<KIND>(a.y.ptr, r.dense_row + (int64_t)x * C);
+    else if constexpr (MASK == 2) o.yv = ldg_raw<0>(a.out.data[0], r.out_row + (int64_t)x * C);
 }
 
 // dz = (fold of the padded-plane gradient + dense gradient) * act'(z)
 template <int KIND, int MASK, int NORM, int GP, int GR>
 __device__ __forceinline__ V8 pix_dz(const aclgan_block_bwd_args& a, const BwdRow& r, int x, int C, const PixRaw<KIND, MASK, NORM, GP, GR>& in,
-                                     const V8& scale, const V8& shift, float slope) {
+                                     const V8& yv, const V8& scale, const V8& shift, float slope) {
     V8 acc;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
     if (GP) {
-        acc = in.g;
+        acc = unpack8<KIND>(in.g);
         const int p = a.gp_pad;
         if (p > 0) {        // reflect images of this pixel in the padded plane (border-adjacent pixels only)
             const int mx = mirror1(x, a.w, p);
@@ -207,19 +243,20 @@ __device__ __forceinline__ V8 pix_dz(const aclgan_block_bwd_args& a, const BwdRo
         }
     }
     if (GR) {
+        const V8 gr = unpack8<KIND>(in.gr);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc.v[i] += in.gr.v[i];
+        for (int i = 0; i < 8; ++i) acc.v[i] += gr.v[i];
     }
     if (MASK == 1) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float z = in.yv.v[i] * scale.v[i] + shift.v[i];
+            const float z = yv.v[i] * scale.v[i] + shift.v[i];
             if (!(z > 0.f)) acc.v[i] *= slope;
         }
     } else if (MASK == 2) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            if (!(in.yv.v[i] > 0.f)) acc.v[i] *= slope;
+            if (!(yv.v[i] > 0.f)) acc.v[i] *= slope;
     }
     return acc;
 }
@@ -288,11 +325,12 @@ __global__ void __launch_bounds__(kThreads) bwd_reduce_rows_kernel(aclgan_block_
                 for (int u = 0; u < UNR; ++u) {
                     const int x = x0 + u * lanes;
                     if (x >= a.w) break;
-                    const V8 dz = pix_dz<KIND, MASK, 1, GP, GR>(a, r, x, C, in[u], scale, shift, slope);
+                    const V8 yv = unpack8<KIND>(in[u].yv);
+                    const V8 dz = pix_dz<KIND, MASK, 1, GP, GR>(a, r, x, C, in[u], yv, scale, shift, slope);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         s.v[i] += dz.v[i];
-                        q.v[i] += dz.v[i] * (in[u].yv.v[i] * inv.v[i] + nmi.v[i]);
+                        q.v[i] += dz.v[i] * (yv.v[i] * inv.v[i] + nmi.v[i]);
                     }
                 }
             }
@@ -355,11 +393,13 @@ __global__ void __launch_bounds__(kThreads) bwd_apply_rows_kernel(aclgan_block_b
                         st8_planes<PLANES>(a.dy.data, dst_row + (int64_t)X * C, zero);
                         continue;
                     }
-                    const V8 dz = pix_dz<KIND, MASK, NORM, GP, GR>(a, r, x, C, in[u], scale, shift, slope);
+                    V8 yv;
+                    if (MASK != 0 || NORM) yv = unpack8<(MASK == 2 && !NORM) ? 0 : KIND>(in[u].yv);
+                    const V8 dz = pix_dz<KIND, MASK, NORM, GP, GR>(a, r, x, C, in[u], yv, scale, shift, slope);
                     V8 out;
                     if (NORM) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) out.v[i] = ca.v[i] * dz.v[i] + (cb.v[i] * in[u].yv.v[i] + cc.v[i]);
+                        for (int i = 0; i < 8; ++i) out.v[i] = ca.v[i] * dz.v[i] + (cb.v[i] * yv.v[i] + cc.v[i]);
                     } else {
                         out = dz;
                     }
@@ -376,8 +416,15 @@ __global__ void __launch_bounds__(kThreads) bwd_apply_rows_kernel(aclgan_block_b
 }
 
 static int rows_per_cta_for(int rows, int n_images) {
-    // about six CTAs per SM over all images: long enough to amortise the prologue / per-CTA atomics, short enough to balance
-    const int want = (6 * num_sms() + n_images - 1) / n_images;
+    // about two CTAs per SM over all images = ONE wave at the occupancy of the backward kernels (4 pixels per thread in flight,
+    // ~120 registers): measured on the 256 x 256 batch-8 step-pair, env ACLGAN_ROWS_PER_SM = 12 / 6 / 3 / 2: 31.40 / 31.28 / 31.12 /
+    // 30.99 ms - a second, partially filled wave of one-row CTAs costs more than the longer per-CTA row loop
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        const char* e = getenv("ACLGAN_ROWS_PER_SM");
+        per_sm = e != nullptr && atoi(e) > 0 ? atoi(e) : 2;
+    }
+    const int want = (per_sm * num_sms() + n_images - 1) / n_images;
     int r = (rows + want - 1) / want;
     return r < 1 ? 1 : r;
 }
@@ -403,8 +450,25 @@ static void launch_apply_act(const aclgan_apply_args* a, dim3 grid, int rpc, cud
     else launch_apply_res<KIND, PLANES, 0>(a, grid, rpc, st);
 }
 
+// pixels per thread and loop iteration of the backward kernels (env ACLGAN_BWD_UNR = 2 | 4): a CTA owns one or two plane rows, so
+// the kernels are bound by the latency of their few dependent load -> compute -> store rounds, not by bandwidth
+static int bwd_unr() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("ACLGAN_BWD_UNR");
+        v = (e != nullptr && atoi(e) == 2) ? 2 : 4;
+    }
+    return v;
+}
+
 template <int KIND, int MASK>
 static void launch_reduce_g(const aclgan_block_bwd_args* a, dim3 grid, int rpc, size_t smem, cudaStream_t st) {
+    if constexpr (KIND == 0) if (bwd_unr() == 4) {
+        if (a->gp != 0 && a->gr != 0) bwd_reduce_rows_kernel<KIND, MASK, 1, 1, 4><<<grid, kThreads, smem, st>>>(*a, rpc);
+        else if (a->gp != 0) bwd_reduce_rows_kernel<KIND, MASK, 1, 0, 4><<<grid, kThreads, smem, st>>>(*a, rpc);
+        else bwd_reduce_rows_kernel<KIND, MASK, 0, 1, 4><<<grid, kThreads, smem, st>>>(*a, rpc);
+        return;
+    }
     if (a->gp != 0 && a->gr != 0) bwd_reduce_rows_kernel<KIND, MASK, 1, 1, 2><<<grid, kThreads, smem, st>>>(*a, rpc);
     else if (a->gp != 0) bwd_reduce_rows_kernel<KIND, MASK, 1, 0, 2><<<grid, kThreads, smem, st>>>(*a, rpc);
     else bwd_reduce_rows_kernel<KIND, MASK, 0, 1, 2><<<grid, kThreads, smem, st>>>(*a, rpc);
@@ -412,6 +476,11 @@ static void launch_reduce_g(const aclgan_block_bwd_args* a, dim3 grid, int rpc, 
 
 template <int KIND, int PLANES, int MASK, int NORM, int GP, int GR>
 static void launch_apply_bwd_db(const aclgan_block_bwd_args* a, dim3 grid, int rpc, size_t smem, cudaStream_t st) {
+    if constexpr (KIND == 0 && PLANES == 1) if (bwd_unr() == 4) {
+        if (a->dbias != 0) bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 1, 4><<<grid, kThreads, smem, st>>>(*a, rpc);
+        else bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 0, 4><<<grid, kThreads, 0, st>>>(*a, rpc);
+        return;
+    }
     if (a->dbias != 0) bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 1, 2><<<grid, kThreads, smem, st>>>(*a, rpc);
     else bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 0, 2><<<grid, kThreads, 0, st>>>(*a, rpc);
 }

@@ -294,9 +294,11 @@ def _declare(L):
     L.aclgan_norm_stats.argtypes = [C.POINTER(Tensor4), C.c_uint64, C.c_void_p]
     L.aclgan_norm_finalize.argtypes = [C.POINTER(NormFinalizeArgs), C.c_void_p]
     L.aclgan_norm_apply.argtypes = [C.POINTER(ApplyArgs), C.c_void_p]
+    L.aclgan_norm_finalize_apply.argtypes = [C.POINTER(NormFinalizeArgs), C.POINTER(ApplyArgs), C.c_void_p]
     L.aclgan_block_bwd_reduce.argtypes = [C.POINTER(BlockBwdArgs), C.c_void_p]
     L.aclgan_block_bwd_apply.argtypes = [C.POINTER(BlockBwdArgs), C.c_void_p]
     L.aclgan_norm_bwd_finalize.argtypes = [C.POINTER(NormBwdFinalizeArgs), C.c_void_p]
+    L.aclgan_norm_bwd_finalize_apply.argtypes = [C.POINTER(NormBwdFinalizeArgs), C.POINTER(BlockBwdArgs), C.c_void_p]
     L.aclgan_img_grad_pack.argtypes = [C.POINTER(ImgGradPackArgs), C.c_void_p]
     L.aclgan_img_grad_unpack.argtypes = [C.POINTER(ImgGradUnpackArgs), C.c_void_p]
     L.aclgan_pack_weight.argtypes = [C.POINTER(PackWeightArgs), C.c_void_p]

@@ -1048,6 +1048,20 @@ extern "C" int aclgan_norm_apply(const aclgan_apply_args* a, void* stream) {
     return (int)cudaGetLastError();
 }
 
+extern "C" int aclgan_norm_finalize_apply(const aclgan_norm_finalize_args* f, const aclgan_apply_args* a, void* stream) {
+    if (f->c_valid < 1 || f->c_valid > f->c) return ACLGAN_ERR_SHAPE;
+    if (a->y.c % 8 || a->dst.c != a->y.c || (a->upsample != 1 && a->upsample != 2)) return ACLGAN_ERR_SHAPE;
+    if (a->has_res && (a->res.c != a->y.c || a->res.h != a->y.h || a->res.w != a->y.w)) return ACLGAN_ERR_SHAPE;
+    if (a->scale != f->scale || a->shift != f->shift) return ACLGAN_ERR_SHAPE;      // the apply pass uses exactly the finalized coefficients
+    if (check_cg(a->y.c) == 0) {
+        const int rc = rows_norm_finalize_apply(f, a, (cudaStream_t)stream);       // ONE launch (elementwise_rows.cu)
+        if (rc != -100) return rc;
+    }
+    const int rc = aclgan_norm_finalize(f, stream);
+    if (rc) return rc;
+    return aclgan_norm_apply(a, stream);
+}
+
 // variant 0: 4 pixels / thread, 2 CTAs / SM (128 registers); 1: 2 pixels, 3 CTAs (85); 2: 2 pixels, 4 CTAs (64)
 static int bwd_variant() {
     static int v = -1;
@@ -1149,6 +1163,19 @@ extern "C" int aclgan_norm_bwd_finalize(const aclgan_norm_bwd_finalize_args* a, 
     if (a->c_valid < 1 || a->c_valid > a->c) return ACLGAN_ERR_SHAPE;
     norm_bwd_finalize_kernel<<<a->n, 256, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
+}
+
+extern "C" int aclgan_norm_bwd_finalize_apply(const aclgan_norm_bwd_finalize_args* f, const aclgan_block_bwd_args* a, void* stream) {
+    if (f->c_valid < 1 || f->c_valid > f->c) return ACLGAN_ERR_SHAPE;
+    if (check_cg(a->c) || a->dy.c != a->c) return ACLGAN_ERR_SHAPE;
+    if (a->ca != f->ca || a->cb != f->cb || a->cc != f->cc || a->sums != f->sums) return ACLGAN_ERR_SHAPE;
+    {
+        const int rc = rows_bwd_finalize_apply(f, a, (cudaStream_t)stream);        // ONE launch (elementwise_rows.cu)
+        if (rc != -100) return rc;
+    }
+    const int rc = aclgan_norm_bwd_finalize(f, stream);
+    if (rc) return rc;
+    return aclgan_block_bwd_apply(a, stream);
 }
 
 extern "C" int aclgan_img_grad_pack(const aclgan_img_grad_pack_args* a, void* stream) {

@@ -101,17 +101,112 @@ __device__ __forceinline__ int mirror1(int c, int L, int p) {
 }
 
 // ------------------------------------------------------------------------------------------ forward apply
-// ACT: 0 none, 1 relu, 2 lrelu
-template <int KIND, int PLANES, int ACT, int RES, int UNR>
-__global__ void __launch_bounds__(kThreads) norm_apply_rows_kernel(aclgan_apply_args a, int rows_per_cta) {
+// statistics -> scale / shift of this thread's 8 channels of image n: the arithmetic of norm_finalize_kernel (elementwise.cu),
+// done by every CTA for itself so that no separate launch sits between the convolution and this pass; CTA 0 of the image also
+// stores the coefficients the backward pass reads (scale, shift, mean, inv, sigma)
+constexpr int kFinMaxC = 512;       // channels per plane the fused finalize steps share through shared memory
+
+__device__ __forceinline__ void finalize8(const aclgan_norm_finalize_args& f, int n, int g, bool store, V8& sc, V8& sf) {
+    __shared__ double sh[kThreads / 32];
+    __shared__ float sh_sc[kFinMaxC], sh_sf[kFinMaxC];
+    // only the first C / 8 threads (one per channel group) do the fp64 arithmetic - 256 threads x 8 channels x (2 divisions + 1
+    // square root) in fp64 cost every CTA ~2.5 us - and hand the coefficients to the CTA's other pixel lanes through shared memory
+    const bool compute = threadIdx.x < (f.c >> 3);
+    const int C = f.c, c_valid = f.c_valid;
+    double mu_ln = 0.0, r_ln = 0.0;
+    if (f.mode == ACLGAN_NORM_LN) {
+        const int tot = f.stat_groups > 1 ? f.stat_groups * c_valid : c_valid;
+        const double* sg = reinterpret_cast<const double*>(f.sums) + (int64_t)n * (f.stat_groups > 1 ? tot : C) * 2;
+        double s1 = 0.0, s2 = 0.0;
+        for (int c = threadIdx.x; c < tot; c += kThreads) { s1 += sg[2 * c]; s2 += sg[2 * c + 1]; }
+        const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            double v = pass == 0 ? s1 : s2;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            __syncthreads();
+            if (lane == 0) sh[wp] = v;
+            __syncthreads();
+            double t = 0.0;
+            for (int i = 0; i < kThreads / 32; ++i) t += sh[i];
+            if (pass == 0) s1 = t; else s2 = t;
+        }
+        const double M = (double)c_valid * f.hw;
+        mu_ln = s1 / M;
+        double var = (s2 - M * mu_ln * mu_ln) / (M - 1.0);
+        if (var < 0.0) var = 0.0;
+        const double sd = sqrt(var);
+        r_ln = 1.0 / (sd + (double)f.eps);
+        if (store && threadIdx.x == 0) reinterpret_cast<float*>(f.sigma)[n] = (float)sd;
+    }
+    const double* sums = reinterpret_cast<const double*>(f.sums) + (int64_t)n * C * 2;
+    V8 mean, inv;
+    if (compute) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = g * 8 + i;
+        float scv = 0.f, sfv = 0.f, mv = 0.f, iv = 0.f;
+        if (c < c_valid) {
+            if (f.mode == ACLGAN_NORM_LN) {
+                const double s = (double)reinterpret_cast<const float*>(f.w)[c] * r_ln;
+                scv = (float)s;
+                sfv = (float)((double)reinterpret_cast<const float*>(f.b)[c] - mu_ln * s);
+                mv = (float)mu_ln; iv = (float)r_ln;
+            } else {
+                const double mu = sums[2 * c] / f.hw;
+                double var = sums[2 * c + 1] / f.hw - mu * mu;
+                if (var < 0.0) var = 0.0;
+                const double r = 1.0 / sqrt(var + (double)f.eps);
+                double s = r, t = -mu * r;
+                if (f.mode == ACLGAN_NORM_ADAIN) {
+                    const int64_t ld = f.wb_stride > 0 ? f.wb_stride : c_valid;
+                    const double w = reinterpret_cast<const float*>(f.w)[(int64_t)n * ld + c];
+                    const double b = reinterpret_cast<const float*>(f.b)[(int64_t)n * ld + c];
+                    s = r * w;
+                    t = b - mu * s;
+                }
+                scv = (float)s; sfv = (float)t; mv = (float)mu; iv = (float)r;
+            }
+        }
+        sc.v[i] = scv; sf.v[i] = sfv; mean.v[i] = mv; inv.v[i] = iv;
+        sh_sc[c] = scv; sh_sf[c] = sfv;
+    }
+    }
+    __syncthreads();
+    if (!compute) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sc.v[i] = sh_sc[g * 8 + i]; sf.v[i] = sh_sf[g * 8 + i]; }
+    }
+    if (store && compute) {
+        const int64_t o = (int64_t)n * C + g * 8;
+        float4* d;
+        d = reinterpret_cast<float4*>(reinterpret_cast<float*>(f.scale) + o);
+        d[0] = make_float4(sc.v[0], sc.v[1], sc.v[2], sc.v[3]); d[1] = make_float4(sc.v[4], sc.v[5], sc.v[6], sc.v[7]);
+        d = reinterpret_cast<float4*>(reinterpret_cast<float*>(f.shift) + o);
+        d[0] = make_float4(sf.v[0], sf.v[1], sf.v[2], sf.v[3]); d[1] = make_float4(sf.v[4], sf.v[5], sf.v[6], sf.v[7]);
+        d = reinterpret_cast<float4*>(reinterpret_cast<float*>(f.mean) + o);
+        d[0] = make_float4(mean.v[0], mean.v[1], mean.v[2], mean.v[3]); d[1] = make_float4(mean.v[4], mean.v[5], mean.v[6], mean.v[7]);
+        d = reinterpret_cast<float4*>(reinterpret_cast<float*>(f.inv) + o);
+        d[0] = make_float4(inv.v[0], inv.v[1], inv.v[2], inv.v[3]); d[1] = make_float4(inv.v[4], inv.v[5], inv.v[6], inv.v[7]);
+    }
+}
+
+// ACT: 0 none, 1 relu, 2 lrelu; FIN: the statistics -> scale / shift step fused (finalize8)
+template <int KIND, int PLANES, int ACT, int RES, int UNR, int FIN>
+__global__ void __launch_bounds__(kThreads) norm_apply_rows_kernel(aclgan_apply_args a, int rows_per_cta, aclgan_norm_finalize_args f) {
     const int p = a.dst.pad, h = a.y.h, w = a.y.w, hp = h + 2 * p, wp = w + 2 * p, C = a.y.c;
     const int cg = C >> 3, lanes = kThreads / cg;
     const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
-    if (lane >= lanes) return;
     const int n = blockIdx.y;
     V8 sc, sf;
-    const bool affine = a.scale != 0;
-    if (affine) {
+    bool affine = a.scale != 0;
+    if (FIN) {
+        // (before the early exit below: the LayerNorm totals are a block-wide reduction)
+        finalize8(f, n, g < cg ? g : 0, blockIdx.x == 0 && lane == 0, sc, sf);
+        affine = true;
+    }
+    if (lane >= lanes) return;
+    if (!FIN && affine) {
         sc = coef8(a.scale, (int64_t)n * C + g * 8);
         sf = coef8(a.shift, (int64_t)n * C + g * 8);
     }
@@ -339,10 +434,100 @@ __global__ void __launch_bounds__(kThreads) bwd_reduce_rows_kernel(aclgan_block_
     cta_reduce16(red, s, q, C, g, lane, lanes, active, reinterpret_cast<double*>(a.sums) + (int64_t)n * C * 2, nullptr, 0);
 }
 
+// T1 / T2 -> (ca, cb, cc) of this thread's 8 channels of image n: the arithmetic of norm_bwd_finalize_kernel (elementwise.cu),
+// done by every CTA for itself (no separate launch between the reduce and the apply pass); `store` (CTA 0 of the image, one
+// thread per channel group) also performs the kernel's side effects: the norm layer's parameter gradients and, for
+// LayerNorm, the gradient of the conv bias in front of it
+__device__ __forceinline__ void bwd_finalize8(const aclgan_norm_bwd_finalize_args& f, int n, int g, bool store, V8& ca, V8& cb, V8& cc) {
+    __shared__ double sh[kThreads / 32];
+    __shared__ float sh_a[kFinMaxC], sh_b[kFinMaxC], sh_c[kFinMaxC];
+    const bool compute = threadIdx.x < (f.c >> 3);            // (see finalize8)
+    const int C = f.c, c_valid = f.c_valid;
+    const double* sums = reinterpret_cast<const double*>(f.sums) + (int64_t)n * C * 2;
+    const float* inv = reinterpret_cast<const float*>(f.inv) + (int64_t)n * C;
+    double s1 = 0.0, s2 = 0.0, sd = 0.0;
+    if (f.mode == ACLGAN_NORM_LN) {
+        const float* gam = reinterpret_cast<const float*>(f.w);
+        for (int c = threadIdx.x; c < c_valid; c += kThreads) {
+            s1 += (double)gam[c] * sums[2 * c];
+            s2 += (double)gam[c] * sums[2 * c + 1];
+        }
+        const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            double v = pass == 0 ? s1 : s2;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            __syncthreads();
+            if (lane == 0) sh[wp] = v;
+            __syncthreads();
+            double t = 0.0;
+            for (int i = 0; i < kThreads / 32; ++i) t += sh[i];
+            if (pass == 0) s1 = t; else s2 = t;
+        }
+        sd = reinterpret_cast<const float*>(f.sigma)[n];
+    }
+    const double M = (double)c_valid * f.hw;
+    if (compute) {
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        const int c = g * 8 + i;
+        float av = 0.f, bv = 0.f, cv = 0.f;
+        if (c < c_valid) {
+            const double r = inv[c];
+            if (f.mode == ACLGAN_NORM_LN) {
+                const float* gam = reinterpret_cast<const float*>(f.w);
+                av = (float)(r * gam[c]);
+                bv = (float)(sd > 0.0 ? -s2 / ((M - 1.0) * sd) : 0.0);
+                cv = (float)(-r * s1 / M);
+                if (store) {
+                    atomicAdd(reinterpret_cast<float*>(f.dw) + c, (float)sums[2 * c + 1]);
+                    atomicAdd(reinterpret_cast<float*>(f.db) + c, (float)sums[2 * c]);
+                    if (f.dbias != 0) {
+                        const double mu = reinterpret_cast<const float*>(f.mean)[(int64_t)n * C + c];
+                        double s1f;
+                        if (f.fstat_groups > 1) {
+                            s1f = 0.0;
+                            for (int gph = 0; gph < f.fstat_groups; ++gph)
+                                s1f += reinterpret_cast<const double*>(f.fsums)[(((int64_t)n * f.fstat_groups + gph) * c_valid + c) * 2];
+                        } else {
+                            s1f = reinterpret_cast<const double*>(f.fsums)[((int64_t)n * C + c) * 2];
+                        }
+                        const double syh = (s1f - (double)f.hw * mu) * r;
+                        const double dbv = (double)av * sums[2 * c] + (double)bv * syh + (double)cv * (double)f.hw;
+                        atomicAdd(reinterpret_cast<float*>(f.dbias) + c, (float)dbv);
+                    }
+                }
+            } else {
+                double gg = 1.0;
+                if (f.mode == ACLGAN_NORM_ADAIN) {
+                    const int64_t ld = f.wb_stride > 0 ? f.wb_stride : c_valid;
+                    gg = reinterpret_cast<const float*>(f.w)[(int64_t)n * ld + c];
+                    if (store) {
+                        reinterpret_cast<float*>(f.dw)[(int64_t)n * ld + c] = (float)sums[2 * c + 1];
+                        reinterpret_cast<float*>(f.db)[(int64_t)n * ld + c] = (float)sums[2 * c];
+                    }
+                }
+                av = (float)(r * gg);
+                bv = (float)(-r * gg * sums[2 * c + 1] / f.hw);
+                cv = (float)(-r * gg * sums[2 * c] / f.hw);
+            }
+        }
+        ca.v[i] = av; cb.v[i] = bv; cc.v[i] = cv;
+        sh_a[c] = av; sh_b[c] = bv; sh_c[c] = cv;
+    }
+    }
+    __syncthreads();
+    if (!compute) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ca.v[i] = sh_a[g * 8 + i]; cb.v[i] = sh_b[g * 8 + i]; cc.v[i] = sh_c[g * 8 + i]; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ backward apply
 // dy = ca*dz + cb*yhat + cc  (= ca*dz + B*y + Cc with B = cb*inv, Cc = cc - B*mean), written as the zero-bordered plane(s)
 template <int KIND, int PLANES, int MASK, int NORM, int GP, int GR, int DBIAS, int UNR>
-__global__ void __launch_bounds__(kThreads) bwd_apply_rows_kernel(aclgan_block_bwd_args a, int rows_per_cta) {
+__global__ void __launch_bounds__(kThreads) bwd_apply_rows_kernel(aclgan_block_bwd_args a, int rows_per_cta, int fin,
+                                                                  aclgan_norm_bwd_finalize_args f) {
     extern __shared__ float red[];
     const int C = a.c, cg = C >> 3, lanes = kThreads / cg;
     const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
@@ -352,14 +537,17 @@ __global__ void __launch_bounds__(kThreads) bwd_apply_rows_kernel(aclgan_block_b
     V8 s, q;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s.v[i] = q.v[i] = 0.f;
+    V8 ca, cb, cc;
+    if (NORM && fin) bwd_finalize8(f, n, g, blockIdx.x == 0 && lane == 0, ca, cb, cc);      // (block-wide for LayerNorm: all threads)
     if (active) {
         const int64_t ci = (int64_t)n * C + g * 8;
         const V8 scale = MASK == 1 ? coef8(a.scale, ci) : V8(), shift = MASK == 1 ? coef8(a.shift, ci) : V8();
-        V8 ca, cb, cc;
         if (NORM) {
-            ca = coef8(a.ca, ci);
-            cb = coef8(a.cb, ci);
-            cc = coef8(a.cc, ci);
+            if (!fin) {
+                ca = coef8(a.ca, ci);
+                cb = coef8(a.cb, ci);
+                cc = coef8(a.cc, ci);
+            }
             const V8 inv = coef8(a.inv, ci), mean = coef8(a.mean, ci);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -439,15 +627,22 @@ static bool rows_enabled() {
 }
 
 template <int KIND, int PLANES, int ACT>
-static void launch_apply_res(const aclgan_apply_args* a, dim3 grid, int rpc, cudaStream_t st) {
-    if (a->has_res) norm_apply_rows_kernel<KIND, PLANES, ACT, 1, 4><<<grid, kThreads, 0, st>>>(*a, rpc);
-    else norm_apply_rows_kernel<KIND, PLANES, ACT, 0, 4><<<grid, kThreads, 0, st>>>(*a, rpc);
+static void launch_apply_res(const aclgan_apply_args* a, const aclgan_norm_finalize_args* f, dim3 grid, int rpc, cudaStream_t st) {
+    if (f != nullptr) {
+        if (a->has_res) norm_apply_rows_kernel<KIND, PLANES, ACT, 1, 4, 1><<<grid, kThreads, 0, st>>>(*a, rpc, *f);
+        else norm_apply_rows_kernel<KIND, PLANES, ACT, 0, 4, 1><<<grid, kThreads, 0, st>>>(*a, rpc, *f);
+        return;
+    }
+    aclgan_norm_finalize_args none;
+    memset(&none, 0, sizeof(none));
+    if (a->has_res) norm_apply_rows_kernel<KIND, PLANES, ACT, 1, 4, 0><<<grid, kThreads, 0, st>>>(*a, rpc, none);
+    else norm_apply_rows_kernel<KIND, PLANES, ACT, 0, 4, 0><<<grid, kThreads, 0, st>>>(*a, rpc, none);
 }
 template <int KIND, int PLANES>
-static void launch_apply_act(const aclgan_apply_args* a, dim3 grid, int rpc, cudaStream_t st) {
-    if (a->act == ACLGAN_ACT_RELU) launch_apply_res<KIND, PLANES, 1>(a, grid, rpc, st);
-    else if (a->act == ACLGAN_ACT_LRELU) launch_apply_res<KIND, PLANES, 2>(a, grid, rpc, st);
-    else launch_apply_res<KIND, PLANES, 0>(a, grid, rpc, st);
+static void launch_apply_act(const aclgan_apply_args* a, const aclgan_norm_finalize_args* f, dim3 grid, int rpc, cudaStream_t st) {
+    if (a->act == ACLGAN_ACT_RELU) launch_apply_res<KIND, PLANES, 1>(a, f, grid, rpc, st);
+    else if (a->act == ACLGAN_ACT_LRELU) launch_apply_res<KIND, PLANES, 2>(a, f, grid, rpc, st);
+    else launch_apply_res<KIND, PLANES, 0>(a, f, grid, rpc, st);
 }
 
 // pixels per thread and loop iteration of the backward kernels (env ACLGAN_BWD_UNR = 2 | 4): a CTA owns one or two plane rows, so
@@ -475,35 +670,48 @@ static void launch_reduce_g(const aclgan_block_bwd_args* a, dim3 grid, int rpc, 
 }
 
 template <int KIND, int PLANES, int MASK, int NORM, int GP, int GR>
-static void launch_apply_bwd_db(const aclgan_block_bwd_args* a, dim3 grid, int rpc, size_t smem, cudaStream_t st) {
+static void launch_apply_bwd_db(const aclgan_block_bwd_args* a, const aclgan_norm_bwd_finalize_args* fp, dim3 grid, int rpc, size_t smem,
+                                cudaStream_t st) {
+    aclgan_norm_bwd_finalize_args f;
+    if (fp != nullptr) f = *fp; else memset(&f, 0, sizeof(f));
+    const int fin = fp != nullptr ? 1 : 0;
     if constexpr (KIND == 0 && PLANES == 1) if (bwd_unr() == 4) {
-        if (a->dbias != 0) bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 1, 4><<<grid, kThreads, smem, st>>>(*a, rpc);
-        else bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 0, 4><<<grid, kThreads, 0, st>>>(*a, rpc);
+        if (a->dbias != 0) bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 1, 4><<<grid, kThreads, smem, st>>>(*a, rpc, fin, f);
+        else bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 0, 4><<<grid, kThreads, 0, st>>>(*a, rpc, fin, f);
         return;
     }
-    if (a->dbias != 0) bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 1, 2><<<grid, kThreads, smem, st>>>(*a, rpc);
-    else bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 0, 2><<<grid, kThreads, 0, st>>>(*a, rpc);
+    if (a->dbias != 0) bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 1, 2><<<grid, kThreads, smem, st>>>(*a, rpc, fin, f);
+    else bwd_apply_rows_kernel<KIND, PLANES, MASK, NORM, GP, GR, 0, 2><<<grid, kThreads, 0, st>>>(*a, rpc, fin, f);
 }
 template <int KIND, int PLANES, int MASK, int NORM>
-static void launch_apply_bwd_g(const aclgan_block_bwd_args* a, dim3 grid, int rpc, size_t smem, cudaStream_t st) {
-    if (a->gp != 0 && a->gr != 0) launch_apply_bwd_db<KIND, PLANES, MASK, NORM, 1, 1>(a, grid, rpc, smem, st);
-    else if (a->gp != 0) launch_apply_bwd_db<KIND, PLANES, MASK, NORM, 1, 0>(a, grid, rpc, smem, st);
-    else launch_apply_bwd_db<KIND, PLANES, MASK, NORM, 0, 1>(a, grid, rpc, smem, st);
+static void launch_apply_bwd_g(const aclgan_block_bwd_args* a, const aclgan_norm_bwd_finalize_args* f, dim3 grid, int rpc, size_t smem,
+                               cudaStream_t st) {
+    if (a->gp != 0 && a->gr != 0) launch_apply_bwd_db<KIND, PLANES, MASK, NORM, 1, 1>(a, f, grid, rpc, smem, st);
+    else if (a->gp != 0) launch_apply_bwd_db<KIND, PLANES, MASK, NORM, 1, 0>(a, f, grid, rpc, smem, st);
+    else launch_apply_bwd_db<KIND, PLANES, MASK, NORM, 0, 1>(a, f, grid, rpc, smem, st);
 }
 template <int KIND, int PLANES>
-static void launch_apply_bwd_mode(const aclgan_block_bwd_args* a, dim3 grid, int rpc, size_t smem, cudaStream_t st) {
+static void launch_apply_bwd_mode(const aclgan_block_bwd_args* a, const aclgan_norm_bwd_finalize_args* f, dim3 grid, int rpc, size_t smem,
+                                  cudaStream_t st) {
     if (a->norm) {
-        if (a->mask_mode == ACLGAN_MASK_FROM_Z) launch_apply_bwd_g<KIND, PLANES, 1, 1>(a, grid, rpc, smem, st);
-        else launch_apply_bwd_g<KIND, PLANES, 0, 1>(a, grid, rpc, smem, st);
+        if (a->mask_mode == ACLGAN_MASK_FROM_Z) launch_apply_bwd_g<KIND, PLANES, 1, 1>(a, f, grid, rpc, smem, st);
+        else launch_apply_bwd_g<KIND, PLANES, 0, 1>(a, f, grid, rpc, smem, st);
     } else {
-        if (a->mask_mode == ACLGAN_MASK_FROM_OUT) launch_apply_bwd_g<KIND, PLANES, 2, 0>(a, grid, rpc, smem, st);
-        else launch_apply_bwd_g<KIND, PLANES, 0, 0>(a, grid, rpc, smem, st);
+        if (a->mask_mode == ACLGAN_MASK_FROM_OUT) launch_apply_bwd_g<KIND, PLANES, 2, 0>(a, nullptr, grid, rpc, smem, st);
+        else launch_apply_bwd_g<KIND, PLANES, 0, 0>(a, nullptr, grid, rpc, smem, st);
     }
 }
 
 }  // namespace
 
-int rows_norm_apply(const aclgan_apply_args* a, cudaStream_t st) {
+int rows_norm_apply(const aclgan_apply_args* a, cudaStream_t st) { return rows_norm_finalize_apply(nullptr, a, st); }
+
+// f != nullptr: the statistics -> coefficient step of aclgan_norm_finalize fused into the apply launch
+int rows_norm_finalize_apply(const aclgan_norm_finalize_args* f, const aclgan_apply_args* a, cudaStream_t st) {
+    if (f != nullptr) {
+        // (callers opt in by calling the fused entry point: engine.py, ACLGAN_FUSE_FINALIZE=1)
+        if (f->n != a->y.n || f->c != a->y.c || f->c % 8 != 0 || f->c > kFinMaxC || f->mode < ACLGAN_NORM_IN || f->mode > ACLGAN_NORM_LN) return -100;
+    }
     if (!rows_enabled() || a->upsample != 1 || a->act == ACLGAN_ACT_TANH) return -100;
     const int C = a->y.c, p = a->dst.pad;
     if (C % 8 != 0 || C / 8 > kThreads || a->y.h <= p || a->y.w <= p || (a->y.kind != 0 && a->y.kind != 1)) return -100;
@@ -513,9 +721,9 @@ int rows_norm_apply(const aclgan_apply_args* a, cudaStream_t st) {
     const int rpc = rows_per_cta_for(hp, a->y.n);
     dim3 grid((hp + rpc - 1) / rpc, a->y.n);
     if (a->y.kind == 0) {
-        if (a->dst.planes == 1) launch_apply_act<0, 1>(a, grid, rpc, st); else launch_apply_act<0, 2>(a, grid, rpc, st);
+        if (a->dst.planes == 1) launch_apply_act<0, 1>(a, f, grid, rpc, st); else launch_apply_act<0, 2>(a, f, grid, rpc, st);
     } else {
-        if (a->dst.planes == 1) launch_apply_act<1, 1>(a, grid, rpc, st); else launch_apply_act<1, 2>(a, grid, rpc, st);
+        if (a->dst.planes == 1) launch_apply_act<1, 1>(a, f, grid, rpc, st); else launch_apply_act<1, 2>(a, f, grid, rpc, st);
     }
     return (int)cudaGetLastError();
 }
@@ -547,7 +755,14 @@ int rows_bwd_reduce(const aclgan_block_bwd_args* a, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
-int rows_bwd_apply(const aclgan_block_bwd_args* a, cudaStream_t st) {
+int rows_bwd_apply(const aclgan_block_bwd_args* a, cudaStream_t st) { return rows_bwd_finalize_apply(nullptr, a, st); }
+
+// f != nullptr: the T1 / T2 -> coefficient step of aclgan_norm_bwd_finalize (and its parameter-gradient side effects) fused in
+int rows_bwd_finalize_apply(const aclgan_norm_bwd_finalize_args* f, const aclgan_block_bwd_args* a, cudaStream_t st) {
+    if (f != nullptr) {
+        // (callers opt in by calling the fused entry point: engine.py, ACLGAN_FUSE_FINALIZE=1)
+        if (!a->norm || f->n != a->n || f->c != a->c || f->c > kFinMaxC || f->mode < ACLGAN_NORM_IN || f->mode > ACLGAN_NORM_LN) return -100;
+    }
     if (!bwd_rows_ok(a)) return -100;
     if (a->dy.planes != 1 && a->dy.planes != 2) return -100;
     const int C = a->c, lanes = kThreads / (C / 8);
@@ -556,9 +771,9 @@ int rows_bwd_apply(const aclgan_block_bwd_args* a, cudaStream_t st) {
     dim3 grid((hz + rpc - 1) / rpc, a->n);
     const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
     if (a->g_kind == 0) {
-        if (a->dy.planes == 1) launch_apply_bwd_mode<0, 1>(a, grid, rpc, smem, st); else launch_apply_bwd_mode<0, 2>(a, grid, rpc, smem, st);
+        if (a->dy.planes == 1) launch_apply_bwd_mode<0, 1>(a, f, grid, rpc, smem, st); else launch_apply_bwd_mode<0, 2>(a, f, grid, rpc, smem, st);
     } else {
-        if (a->dy.planes == 1) launch_apply_bwd_mode<1, 1>(a, grid, rpc, smem, st); else launch_apply_bwd_mode<1, 2>(a, grid, rpc, smem, st);
+        if (a->dy.planes == 1) launch_apply_bwd_mode<1, 1>(a, f, grid, rpc, smem, st); else launch_apply_bwd_mode<1, 2>(a, f, grid, rpc, smem, st);
     }
     return (int)cudaGetLastError();
 }

@@ -429,6 +429,7 @@ class Engine:
         self.debug = None           # tests: dict collecting per-layer backward intermediates
         self.pool = None            # SumsPool of the update being recorded (trainer), or None: per-layer zeroed tensors
         self.fuse_stats = os.environ.get("ACLGAN_FUSE_STATS", "1") != "0"
+        self.fuse_finalize = os.environ.get("ACLGAN_FUSE_FINALIZE", "0") != "0"
 
     def sums(self, n, cs):
         if self.pool is not None:
@@ -586,6 +587,24 @@ class Engine:
             return layer.k - 1
         return layer.k // 2 - 1
 
+    # statistics -> coefficients -> element-wise pass.  Two launches by default; ACLGAN_FUSE_FINALIZE=1 folds the coefficient step
+    # into the row kernels (every CTA derives its own channels' coefficients: ~190 fewer launches per step-pair, but measured
+    # 0.5 ms SLOWER on the 256x256 batch-8 step - the fp64 chain then sits in front of every CTA's first load)
+    def _finalize_apply(self, f, a):
+        L = N.lib()
+        if self.fuse_finalize:
+            N.check(L.aclgan_norm_finalize_apply(C.byref(f), C.byref(a), _sp()), "norm_finalize_apply")
+        else:
+            N.check(L.aclgan_norm_finalize(C.byref(f), _sp()), "norm_finalize")
+            N.check(L.aclgan_norm_apply(C.byref(a), _sp()), "norm_apply")
+
+    def _bwd_finalize_apply(self, f, b):
+        L = N.lib()
+        if self.fuse_finalize:
+            return L.aclgan_norm_bwd_finalize_apply(C.byref(f), C.byref(b), _sp())
+        N.check(L.aclgan_norm_bwd_finalize(C.byref(f), _sp()), "norm_bwd_finalize")
+        return L.aclgan_block_bwd_apply(C.byref(b), _sp())
+
     # ------------------------------------------------------------------------------------------ conv block
     def conv_block(self, tape, layer, x, norm=N.NORM_NONE, act=N.ACT_NONE, out_pad=0, upsample=1, res=None,
                    adain=None, ln=None, train_w=True):
@@ -620,7 +639,6 @@ class Engine:
                 f.w, f.b = ln[0].data_ptr(), ln[1].data_ptr()
             f.scale, f.shift, f.mean, f.inv = (coef[i].data_ptr() for i in range(4))
             f.sigma = sigma.data_ptr()
-            N.check(L.aclgan_norm_finalize(C.byref(f), _sp()), "norm_finalize")
             out = ActT(self, n, ho * upsample, wo * upsample, cout, out_pad)
             a = N.ApplyArgs()
             a.y, a.scale, a.shift, a.act, a.slope = y4, coef[0].data_ptr(), coef[1].data_ptr(), act, slope
@@ -628,7 +646,7 @@ class Engine:
             if res is not None:
                 a.res = res.struct()
             a.upsample, a.dst = upsample, out.struct()
-            N.check(L.aclgan_norm_apply(C.byref(a), _sp()), "norm_apply")
+            self._finalize_apply(f, a)
             saved = (y, coef, sigma, sums if norm == N.NORM_LN else None)     # (pool slices live until the update ends)
         need_x_grad = x.requires_grad
         out.requires_grad = need_x_grad or train_w or (res is not None and res.requires_grad) or adain is not None
@@ -682,9 +700,11 @@ class Engine:
                     # a conv bias in front of LayerNorm is NOT cancelled (statistics span all channels): the finalize kernel
                     # adds db[c] = sum_n ca*T1 + cb*sum_hw(yhat) + cc*HW with sum_hw(yhat) = (S1 - HW*mean) * inv
                     f.fsums, f.mean, f.dbias = fwd_sums.data_ptr(), coef[2].data_ptr(), layer.db().data_ptr()
-                N.check(L.aclgan_norm_bwd_finalize(C.byref(f), _sp()), "norm_bwd_finalize")
                 b.ca, b.cb, b.cc = (cf[i].data_ptr() for i in range(3))
-            rc = L.aclgan_block_bwd_apply(C.byref(b), _sp())
+            if norm == N.NORM_NONE:
+                rc = L.aclgan_block_bwd_apply(C.byref(b), _sp())
+            else:
+                rc = self._bwd_finalize_apply(f, b)
             if rc == -3 and b.dbias:
                 # degenerate plane sizes (generic kernels): separate reduction for the bias gradient
                 b.dbias = 0
@@ -771,12 +791,11 @@ class Engine:
         f.w, f.b = ln[0].data_ptr(), ln[1].data_ptr()
         f.scale, f.shift, f.mean, f.inv = (coef[i].data_ptr() for i in range(4))
         f.sigma = sigma.data_ptr()
-        N.check(L.aclgan_norm_finalize(C.byref(f), _sp()), "norm_finalize")
         out = ActT(self, n, 2 * H, 2 * W, cout, out_pad)
         a = N.ApplyArgs()
         a.y, a.scale, a.shift, a.act, a.slope = y4, coef[0].data_ptr(), coef[1].data_ptr(), act, slope
         a.has_res, a.upsample, a.dst = 0, 1, out.struct()
-        N.check(L.aclgan_norm_apply(C.byref(a), _sp()), "norm_apply")
+        self._finalize_apply(f, a)
         need_x_grad = x.requires_grad
         out.requires_grad = need_x_grad or train_w
         if not tape.enabled or not out.requires_grad:
@@ -809,9 +828,8 @@ class Engine:
             fb.ca, fb.cb, fb.cc = (cf[i].data_ptr() for i in range(3))
             if train_w:         # conv bias in front of the LayerNorm (not cancelled): from the forward statistics
                 fb.fsums, fb.mean, fb.dbias, fb.fstat_groups = sums.data_ptr(), coef[2].data_ptr(), base.db().data_ptr(), groups
-            N.check(L.aclgan_norm_bwd_finalize(C.byref(fb), _sp()), "norm_bwd_finalize")
             b.ca, b.cb, b.cc = (cf[i].data_ptr() for i in range(3))
-            N.check(L.aclgan_block_bwd_apply(C.byref(b), _sp()), "block_bwd_apply")
+            N.check(self._bwd_finalize_apply(fb, b), "block_bwd_apply")
             # dY -> space-to-depth plane (ring zeroed) for the 3x3 main gradients + ring strips for the 5x5 strip gradients
             ds = ActT(self, n, H, W, 4 * cout, 2)
             dr = ActT(self, 2 * n, 2, 2 * W, cout, 4)

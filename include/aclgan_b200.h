@@ -265,6 +265,10 @@ typedef struct aclgan_apply_args {
     aclgan_act dst;         /* n, h*upsample, w*upsample, c; pad = consumer's reflect width */
 } aclgan_apply_args;
 int aclgan_norm_apply(const aclgan_apply_args* a, void* stream);
+/* aclgan_norm_finalize + aclgan_norm_apply (a->scale / a->shift == f->scale / f->shift) as ONE launch whenever the row-structured
+ * apply kernel takes the plane: every CTA derives the coefficients of its own channels from the statistics, CTA 0 of each image
+ * stores them (and mean / inv / sigma) for the backward pass; otherwise the two launches */
+int aclgan_norm_finalize_apply(const aclgan_norm_finalize_args* f, const aclgan_apply_args* a, void* stream);
 
 /* backward of  pad/upsample -> activation -> norm  for one block.
  * g = fold(gp) (+ gr): gradient w.r.t. the block's logical output, gathered from the gradient of the padded
@@ -311,6 +315,10 @@ typedef struct aclgan_norm_bwd_finalize_args {
     int32_t pad_;
 } aclgan_norm_bwd_finalize_args;
 int aclgan_norm_bwd_finalize(const aclgan_norm_bwd_finalize_args* a, void* stream);
+/* aclgan_norm_bwd_finalize + aclgan_block_bwd_apply (same sums / ca / cb / cc) as ONE launch whenever the row-structured apply
+ * kernel takes the plane: every CTA derives (ca, cb, cc) of its own channels from T1 / T2, CTA 0 of each image performs the
+ * parameter-gradient side effects; otherwise the two launches */
+int aclgan_norm_bwd_finalize_apply(const aclgan_norm_bwd_finalize_args* f, const aclgan_block_bwd_args* a, void* stream);
 
 /* gradient of an NCHW fp32 image (optionally through tanh: d * (1 - out^2)) -> zero-bordered 8-channel planes
  * feeding the final conv's dgrad / wgrad; also accumulates the bias gradient (sum over n,h,w) */

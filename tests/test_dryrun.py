@@ -18,7 +18,7 @@ import trainer as T
 LAUNCHERS = ["aclgan_igemm_launch", "aclgan_wgrad_launch", "aclgan_pack_img", "aclgan_norm_stats",
              "aclgan_norm_finalize", "aclgan_norm_apply", "aclgan_block_bwd_reduce", "aclgan_block_bwd_apply",
              "aclgan_norm_bwd_finalize", "aclgan_img_grad_pack", "aclgan_img_grad_unpack", "aclgan_pack_weight",
-             "aclgan_adam_step", "aclgan_adam_advance", "aclgan_adam_units", "aclgan_zero", "aclgan_copy", "aclgan_axpby",
+             "aclgan_adam_step", "aclgan_adam_advance", "aclgan_adam_units", "aclgan_norm_finalize_apply", "aclgan_norm_bwd_finalize_apply", "aclgan_zero", "aclgan_copy", "aclgan_axpby",
              "aclgan_avgpool3x3s2_fwd", "aclgan_avgpool3x3s2_bwd", "aclgan_style_head_fwd", "aclgan_style_head_bwd",
              "aclgan_mlp_fwd", "aclgan_mlp_bwd", "aclgan_dis_head_fwd", "aclgan_dis_head_bwd", "aclgan_focus_blend_fwd",
              "aclgan_focus_blend_bwd", "aclgan_loss_reduce", "aclgan_focus_grad", "aclgan_loss_combine", "aclgan_stats_to_bias", "aclgan_pack_nchw",

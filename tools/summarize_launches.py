@@ -18,7 +18,7 @@ for row in csv.DictReader(lines):
 tot = sum(v[1] for v in agg.values())
 print("# %s\n" % title)
 print("| launches | total ms | share | kernel |\n|---:|---:|---:|---|")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24]:
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(__import__("os").environ.get("TOP", "24"))]:
     print("| %d | %.3f | %.1f%% | `%s` |" % (v[0], v[1], 100 * v[1] / tot, k))
 print("\nTotal %d launches, %.1f ms serialised (cold-cache per-launch times: compare SHARES)." % (
     sum(v[0] for v in agg.values()), tot))

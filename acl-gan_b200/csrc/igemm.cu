@@ -832,18 +832,23 @@ igemm_pair_kernel(const __grid_constant__ IgemmKParams P) {
             tma_prefetch_desc(&P.b[p]);
         }
     }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kPairStages; ++s) {
-            mbar_init(&full_bar[s], 2);       // leader's expect_tx arrive + the peer's remote arrive
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 8 * (P.seg_esplit ? P.seg_egroups : 1));     // 4 epilogue warps per group of each CTA
-        }
-        fence_barrier_init();
-    }
     if (warp == 2) {
+        // barrier initialisation and TMEM allocation by the same warp, one after the other.  (compute-sanitizer's racecheck
+        // reports the cta_group::2 allocation itself: the instruction of EITHER CTA of the pair deposits the allocated address in
+        // both CTAs' shared memory, which the tool sees as an unordered remote write against the local one - both write the same
+        // value, and every reader sits behind the cluster barrier below: profiles/r2_sanitize_racecheck_dim32.log)
+        if (lane == 0) {
+            for (int s = 0; s < kPairStages; ++s) {
+                mbar_init(&full_bar[s], 2);       // leader's expect_tx arrive + the peer's remote arrive
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tfull_bar[s], 1);
+                mbar_init(&tempty_bar[s], 8 * (P.seg_esplit ? P.seg_egroups : 1));     // 4 epilogue warps per group of each CTA
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
         tmem_alloc_pair(tmem_slot, 512);
         tmem_relinquish_pair();
     }
@@ -1063,13 +1068,15 @@ __device__ __forceinline__ void seg_kernel_body(const IgemmKParams& P, uint8_t* 
             tma_prefetch_desc(&P.b_seg[p]);
         }
     }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kSegMaxStages; ++s) { mbar_init(&full_bar[s], PAIR ? 2 : 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], (PAIR ? 8 : 4) * (P.seg_esplit ? P.seg_egroups : 1)); }
-        mbar_init(bres_bar, 1);
-        fence_barrier_init();
-    }
     if (warp == 2) {
+        // (barrier initialisation and TMEM allocation by the same warp, one after the other: see igemm_pair_kernel)
+        if (lane == 0) {
+            for (int s = 0; s < kSegMaxStages; ++s) { mbar_init(&full_bar[s], PAIR ? 2 : 1); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], (PAIR ? 8 : 4) * (P.seg_esplit ? P.seg_egroups : 1)); }
+            mbar_init(bres_bar, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
         if (PAIR) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
         else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     }

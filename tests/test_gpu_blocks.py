@@ -76,7 +76,23 @@ CASES = [
 @pytest.mark.parametrize("precision", ["fp32x3", "bf16"])
 @pytest.mark.parametrize("cin,cout,k,stride,pad,norm,act,use_res,upsample,out_pad,n,h", CASES)
 def test_conv_block(precision, cin, cout, k, stride, pad, norm, act, use_res, upsample, out_pad, n, h):
+    _block_case(precision, cin, cout, k, stride, pad, norm, act, use_res, upsample, out_pad, n, h, fuse=False)
+
+
+FUSED_CASES = [c for c in CASES if c[5] != N.NORM_NONE and c[11] <= 128][:9]
+
+
+@pytest.mark.parametrize("precision", ["fp32x3", "bf16"])
+@pytest.mark.parametrize("cin,cout,k,stride,pad,norm,act,use_res,upsample,out_pad,n,h", FUSED_CASES)
+def test_conv_block_fused_finalize(precision, cin, cout, k, stride, pad, norm, act, use_res, upsample, out_pad, n, h):
+    """the opt-in one-launch forms (aclgan_norm_finalize_apply / aclgan_norm_bwd_finalize_apply, ACLGAN_FUSE_FINALIZE=1): every
+    CTA of the row kernels derives the coefficients of its own channels - same arithmetic, same results"""
+    _block_case(precision, cin, cout, k, stride, pad, norm, act, use_res, upsample, out_pad, n, h, fuse=True)
+
+
+def _block_case(precision, cin, cout, k, stride, pad, norm, act, use_res, upsample, out_pad, n, h, fuse):
     eng = E.Engine(precision)
+    eng.fuse_finalize = fuse
     tol = 2e-4 if precision == "fp32x3" else 4e-2
     torch.manual_seed(0)
     dev = "cuda"

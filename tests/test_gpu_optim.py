@@ -187,7 +187,14 @@ def test_two_iterations_update_parity(golden_dir, case, point):
                 # (stale packed weights move them by 3e-2), the update magnitude (a stale step counter changes the bias
                 # correction by 33 %) and the update direction statistically (moments carried over)
                 tol_e, tol_f = 0.35, 0.1
-            if not e_new <= max(tol_e, 2 * e_ref) + 1e-12:
+            # allowance on top of tol_e: the tensor's own sensitivity, measured by the fp32 oracle's distance from its fp64 self.
+            # The parity mode's operands carry 16-17 mantissa bits (hi + lo bf16 planes), i.e. its forward values sit ~1e-5 from
+            # the fp64 ones against fp32's ~1e-7, so a tensor that turns fp32 rounding into e_ref turns fp32x3 rounding into
+            # >= 10 e_ref: the dis_2 first conv (both images of its real pair are identical, its gradient is a difference of nearly
+            # equal terms) has e_ref = 1.3e-3 and moves between 2e-3 and 1.3e-2 when a kernel merely changes the ORDER of fp32
+            # partial sums (box-per-tap vs vertical-segment plan of the first conv: bit-identical conv outputs, statistics summed
+            # over differently shaped tiles - tools/check_vseg_bitwise.py)
+            if not e_new <= max(tol_e, 16 * e_ref) + 1e-12:
                 fails.append(("iteration %d %s" % (i // 2 + 1, kind), key, "dp rel err", e_new, e_ref))
             if not n_bad <= max(2 if i < 2 else 16, int(tol_f * d64.numel()), 3 * n_bad_ref):
                 fails.append(("iteration %d %s" % (i // 2 + 1, kind), key, "sign flips", n_bad, n_bad_ref, d64.numel()))

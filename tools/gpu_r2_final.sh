@@ -15,5 +15,6 @@ timeout 300 ncu --set full --clock-control none --profile-from-start off -k rege
 ncu -i /tmp/ncu/adam.ncu-rep --page raw --csv > gpurun_out/final_adam_raw.csv 2>/dev/null
 python tools/trace_step.py > gpurun_out/final_trace.txt 2>&1; sed -n 3,10p gpurun_out/final_trace.txt
 for tool in memcheck racecheck; do
-  SAN_DIM=32 timeout 900 compute-sanitizer --tool $tool python tools/sanitize_step.py bf16 2>&1 | tail -3 > gpurun_out/final_sanitize_$tool.log; tail -1 gpurun_out/final_sanitize_$tool.log
+  SAN_DIM=32 timeout 900 compute-sanitizer --tool $tool python tools/sanitize_step.py bf16 2>&1 | grep -v "Host Frame\|^=========         in \|^$" | awk '!seen[$0]++' | head -40 > gpurun_out/final_sanitize_$tool.log; tail -2 gpurun_out/final_sanitize_$tool.log
 done
+timeout 600 compute-sanitizer --tool racecheck python tools/sanitize_step.py bf16 2>&1 | tail -2 > gpurun_out/final_sanitize_racecheck_dim16.log; tail -1 gpurun_out/final_sanitize_racecheck_dim16.log

@@ -159,3 +159,45 @@ def test_dis_loss_attributes_are_plain_attributes_until_set():
     tr.loss_dis_total = torch.tensor(1.5)
     assert float(tr.loss_dis_total) == 1.5
     assert not [k for k in vars(tr) if "loss" in k and k.startswith("_")]
+
+
+def _adam_entry(shape, conv):
+    """an aclgan_adam_tensor as trainer._adam_group fills it (no device pointers needed for the host-side unit count)"""
+    import ctypes as C
+    t = N.AdamTensor()
+    d = [1] * (4 - len(shape)) + list(shape)
+    for j in range(4):
+        t.d[j] = d[j]
+    if conv:
+        desc = N.ConvDesc(d[1], d[0], d[2], 1, d[2] // 2, N.WINDOW_NONE)
+        L = N.lib()
+        idx = lambda a, b, c, e: L.aclgan_packed_weight_index(C.byref(desc), 0, a, b, c, e)
+        base = idx(0, 0, 0, 0)
+        strides = (idx(1, 0, 0, 0) - base, idx(0, 1, 0, 0) - base, (idx(0, 0, 1, 0) - base) if d[2] > 1 else 0,
+                   (idx(0, 0, 0, 1) - base) if d[3] > 1 else 0)
+        for j in range(4):
+            t.gs[j] = strides[j]
+        t.pk[0][0] = 1      # (any non-zero: "this tensor has packed planes")
+    else:
+        acc = 1
+        for j in reversed(range(4)):
+            t.gs[j] = acc
+            acc *= d[j]
+    return t
+
+
+@pytest.mark.parametrize("shape,conv,units", [
+    ((256, 256, 3, 3), True, 8 * 8),          # 32 x 32 x 9 tiles
+    ((128, 64, 4, 4), True, 8 * 2),           # 16 taps: 16 output channels per tile (shared-memory budget)
+    ((128, 256, 5, 5), True, 8 * 8),          # 25 taps: 16 x 32 tiles
+    ((64, 3, 7, 7), True, 2 * 1),             # few input channels: one ci tile
+    ((4, 64, 7, 7), True, 1 * 2),
+    ((256,), False, 1),                       # bias: flat, 1024 elements per unit
+    ((256, 8), False, 2),
+    ((4096, 256), False, 1024),
+])
+def test_adam_work_units(shape, conv, units):
+    """host side of the tiled Adam kernel (csrc/adam.cu): CTAs per table entry"""
+    import ctypes as C
+    t = _adam_entry(shape, conv)
+    assert N.lib().aclgan_adam_units(C.byref(t)) == units

@@ -231,7 +231,10 @@ def build(force=False, verbose=False):
     """Compile every .cu under csrc/ into libaclgan_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = sources()
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "aclgan_b200.h")]
-    if not force and os.path.exists(LIB_PATH):
+    manifest = os.path.join(CSRC, ".linked_sources")     # a source added to / removed from csrc/ forces a relink
+    names = "\n".join(os.path.basename(s) for s in srcs)
+    linked = open(manifest).read() if os.path.exists(manifest) else None
+    if not force and os.path.exists(LIB_PATH) and linked == names:
         if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -254,7 +257,28 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise NativeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    with open(manifest, "w") as f:
+        f.write(names)
     return LIB_PATH
+
+
+PROBE_SRC = os.path.join(HERE, "..", "tools", "probe", "probe.cu")
+PROBE_LIB = os.path.join(HERE, "..", "tools", "probe", "libaclgan_probe.so")
+
+
+def build_probe(force=False):
+    """The tcgen05 issue-rate / TMEM read micro-benchmarks (tools/probe/probe.cu, driven by tools/probe_umma.py) are a
+    measurement tool, not part of the product: they build into their own library next to their source."""
+    if not os.path.exists(PROBE_SRC):
+        return None
+    deps = [PROBE_SRC] + glob.glob(os.path.join(CSRC, "*.cuh"))
+    if force or not os.path.exists(PROBE_LIB) or os.path.getmtime(PROBE_LIB) < max(os.path.getmtime(d) for d in deps):
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler",
+                            "-fPIC", "-I", CSRC, "-shared", PROBE_SRC, "-o", PROBE_LIB], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise NativeError("nvcc failed for %s:\n%s\n%s" % (PROBE_SRC, r.stdout, r.stderr))
+    return PROBE_LIB
 
 
 _lib = None

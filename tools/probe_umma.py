@@ -1,4 +1,4 @@
-"""tcgen05.mma issue-rate probe (see csrc/probe.cu): cycles per 128 x N x 16 bf16 MMA for several configurations."""
+"""tcgen05.mma issue-rate probe (see tools/probe/probe.cu, built into tools/probe/libaclgan_probe.so): cycles per 128 x N x 16 bf16 MMA for several configurations."""
 import ctypes as C
 import os
 import sys
@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.join(ROOT, "acl-gan_b200"))
 import torch  # noqa: E402
 import aclgan_native as N  # noqa: E402
 
-L = N.lib()
+L = C.CDLL(N.build_probe())
 L.aclgan_umma_probe.argtypes = [C.c_int] * 9 + [C.c_uint64, C.c_void_p]
 out = torch.zeros(148, dtype=torch.int64, device="cuda")
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -365,7 +365,17 @@ def check(rc, what):
     if not what.startswith("plan"):
         launch_count += 1
     if rc != 0:
-        raise NativeError("%s failed with status %d" % (what, rc))
+        raise NativeError("%s failed with status %d (%s)" % (what, rc, status_name(rc)))
+
+
+_STATUS = {-1: "ACLGAN_ERR_SHAPE: a geometry the kernels do not take, e.g. an input smaller than its reflect padding",
+           -2: "ACLGAN_ERR_ALIGN: a pointer / stride that is not aligned for TMA", -3: "ACLGAN_ERR_UNSUPPORTED",
+           -4: "ACLGAN_ERR_DRIVER: a CUDA driver entry point (tensor-map encode) failed"}
+
+
+def status_name(rc):
+    """include/aclgan_b200.h: 0 ok, negative ACLGAN_ERR_*, positive a cudaError_t"""
+    return _STATUS.get(rc, "cudaError_t %d" % rc if rc > 0 else "unknown status")
 
 
 def exported_symbols():

@@ -107,3 +107,27 @@ def test_full_width_plans_dryrun(dry):
     x = torch.rand(1, 3, 64, 64) * 2 - 1
     tr.dis_update(x, x, cfg)
     tr.gen_update(x, x, cfg)
+
+
+@pytest.mark.parametrize("h,w", [(72, 72), (96, 80)])
+def test_ragged_image_sizes_dryrun(dry, h, w):
+    """crop sizes that are multiples of 4 but not powers of two: every plan of both updates and of sample() builds"""
+    cfg = _cfg()
+    cfg["cuda_graphs"] = 0
+    torch.manual_seed(0)
+    tr = T.aclgan_Trainer(copy.deepcopy(cfg))
+    x = torch.rand(2, 3, h, w) * 2 - 1
+    tr.dis_update(x, x, cfg)
+    tr.gen_update(x, x, cfg)
+    out = tr.sample(x, x)
+    assert tuple(out[1].shape) == (2, 3, h, w) and tuple(out[2].shape) == (2, 1, h, w)
+
+
+def test_too_small_image_is_a_shape_error(dry):
+    """100 x 60: the third discriminator scale shrinks to 3 x 1, where the reference's ReflectionPad2d(1) raises as well"""
+    cfg = _cfg()
+    cfg["cuda_graphs"] = 0
+    tr = T.aclgan_Trainer(copy.deepcopy(cfg))
+    x = torch.rand(1, 3, 100, 60) * 2 - 1
+    with pytest.raises(N.NativeError, match="ACLGAN_ERR_SHAPE"):
+        tr.dis_update(x, x, cfg)

@@ -271,3 +271,27 @@ def test_conv_fwd_fold_plan(monkeypatch, cout, n, h, w, planes):
     ref = torch.tanh(F.conv2d(xeff, weff, bias.double()))
     tol = 1e-6 if planes == 1 else 2e-4
     assert torch.allclose(img.double(), ref, rtol=tol, atol=tol), float((img.double() - ref).abs().max())
+
+
+# Ragged geometries (crop sizes that are not powers of two: the drop-in contract of INTEGRATION.md says "other sizes run with masked
+# tiles"): widths that leave partial 128-pixel row tiles, odd heights, partial 16 x 8 window tiles, odd stride-2 inputs.
+@pytest.mark.parametrize("cin,cout,k,s,pad,window,n,h,w,planes", [
+    (64, 64, 3, 1, 1, 0, 1, 7, 130, 1), (64, 64, 3, 1, 1, 0, 2, 45, 45, 1), (64, 128, 4, 2, 1, 0, 1, 10, 100, 1),
+    (128, 64, 5, 1, 2, 0, 1, 6, 72, 1), (3, 64, 7, 1, 3, 1, 1, 13, 67, 1), (64, 4, 7, 1, 3, 0, 1, 9, 100, 1),
+    (6, 16, 4, 2, 1, 1, 1, 12, 100, 1)])
+def test_conv_fwd_plan_ragged(cin, cout, k, s, pad, window, n, h, w, planes):
+    test_conv_fwd_plan(cin, cout, k, s, pad, window, n, h, w, planes)
+
+
+@pytest.mark.parametrize("cin,cout,k,s,pad,n,ho,wo,planes", [
+    (64, 64, 3, 1, 1, 1, 5, 96, 1), (64, 128, 4, 2, 1, 1, 5, 50, 1), (128, 64, 5, 1, 2, 1, 4, 72, 1), (3, 64, 7, 1, 3, 1, 6, 100, 1),
+    (64, 64, 3, 1, 1, 2, 9, 45, 2)])
+def test_conv_dgrad_plan_ragged(cin, cout, k, s, pad, n, ho, wo, planes):
+    test_conv_dgrad_plan(cin, cout, k, s, pad, n, ho, wo, planes)
+
+
+@pytest.mark.parametrize("cin,cout,k,s,pad,window,n,h,w,planes", [
+    (64, 64, 3, 1, 1, 0, 1, 5, 96, 1), (64, 128, 4, 2, 1, 0, 1, 10, 100, 1), (3, 64, 7, 1, 3, 1, 1, 10, 100, 1),
+    (64, 4, 7, 1, 3, 0, 1, 9, 100, 1), (64, 64, 3, 1, 1, 0, 2, 45, 45, 1)])
+def test_conv_wgrad_plan_ragged(cin, cout, k, s, pad, window, n, h, w, planes):
+    test_conv_wgrad_plan(cin, cout, k, s, pad, window, n, h, w, planes)

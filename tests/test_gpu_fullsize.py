@@ -1,0 +1,103 @@
+"""-m gpu: the EXACT benchmarked workload (BASELINE.json configs[1]: male2female.yaml, 256x256, batch 8, bf16; configs[2]:
+selfie2anime.yaml, 256x256, batch 8, fp32 parity mode) - full-width networks, the batch size bench.py times - checked through a
+size-independent property, because the CPU oracle needs minutes per step-pair here and the reference fixtures stop at batch 2
+(tests/test_gpu_step256.py).
+
+Batch decomposition.  Every layer on the path is per-sample (InstanceNorm / AdaIN / the custom LayerNorm normalise each sample
+on its own) and every loss term except the focus SIZE loss is a mean (LSGAN networks.py:60-106, L1
+trainer.py:61-62) or a sum (focus digit loss trainer.py:146-161) over the batch.  With the weights frozen (lr = 0, so the Adam
+kernel runs but moves nothing), one batch-8 update must therefore equal its four batch-2 sub-updates combined:
+
+    loss(batch 8) = mean_k loss(chunk k)        (digit losses: sum_k)
+    grad(batch 8) = mean_k grad(chunk k)        (all discriminator gradients; generator gradients when the focus branch is off)
+
+The batch-2 geometry is the one the reference fixtures and the live oracle pin; the property carries that parity to the batch the
+bench runs: different tile counts per launch, different wave shapes, batched [x_a; x_b] / three-image discriminator passes of 16 and
+24 images, other split points of the weight-gradient reductions."""
+import copy
+import os
+
+import pytest
+import torch
+import yaml
+
+import trainer as T
+from test_gpu_step import _cancelled_bias_keys
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BATCH, CHUNK, SIZE = 8, 2, 256
+
+
+def _grads(tr, names):
+    return {"%s.%s" % (n, k): p.grad.detach().double().cpu().clone() for n in names
+            for k, p in getattr(tr, n).named_parameters() if p.grad is not None}
+
+
+def _losses(tr, prefix):
+    return {k: float(getattr(tr, k)) for k in dir(tr) if k.startswith(prefix) and isinstance(getattr(tr, k), torch.Tensor)}
+
+
+@pytest.mark.parametrize("cfgname,precision,ltol,gtol", [("male2female.yaml", "bf16", 2e-4, 5e-3),
+                                                         ("selfie2anime.yaml", "fp32x3", 2e-5, 1e-3)])
+def test_batch8_update_equals_its_batch2_chunks(cfgname, precision, ltol, gtol):
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "acl-gan_b200", "configs", cfgname)))
+    cfg["precision"] = precision
+    cfg["display_size"] = 2
+    focus = cfg["focus_loss"] > 0
+    torch.manual_seed(0)
+    tr = T.aclgan_Trainer(copy.deepcopy(cfg)).cuda()
+    for opt in (tr.dis_opt, tr.gen_opt):
+        for grp in opt.param_groups:
+            grp["lr"] = 0.0
+    w0 = {k: v.detach().clone() for k, v in tr.gen_AB.state_dict().items()}
+    torch.manual_seed(1)
+    x_a = (torch.rand(BATCH, 3, SIZE, SIZE) * 2 - 1).cuda()
+    x_b = (torch.rand(BATCH, 3, SIZE, SIZE) * 2 - 1).cuda()
+    zs = [torch.randn(BATCH, 8, 1, 1) for _ in range(6)]
+    dnames, gnames = ("dis_A", "dis_B", "dis_2"), ("gen_AB", "gen_BA")
+
+    def step(lo, hi):
+        tr._noise = [z[lo:hi] for z in zs[:3]]
+        tr.dis_update(x_a[lo:hi], x_b[lo:hi], cfg)
+        torch.cuda.synchronize()
+        ld, gd = _losses(tr, "loss_dis"), _grads(tr, dnames)
+        tr._noise = [z[lo:hi] for z in zs[3:]]
+        tr.gen_update(x_a[lo:hi], x_b[lo:hi], cfg)
+        torch.cuda.synchronize()
+        lg = dict(_losses(tr, "loss_gen"), **_losses(tr, "loss_idt"))
+        return ld, gd, lg, _grads(tr, gnames)
+
+    full = step(0, BATCH)
+    assert len(full[0]) == 4 and len(full[2]) >= 5 and len(full[1]) > 20 and len(full[3]) > 50
+    chunks = [step(lo, lo + CHUNK) for lo in range(0, BATCH, CHUNK)]
+    nck = len(chunks)
+    for k, v in tr.gen_AB.state_dict().items():           # lr = 0: nine Adam launches later the weights are bit-identical
+        assert torch.equal(v, w0[k]), k
+
+    worst_l, worst_g = (0.0, ""), (0.0, "")
+    for idx in (0, 2):
+        for name, v in full[idx].items():
+            if "size" in name or name == "loss_gen_total" and focus:
+                continue                                    # the focus size loss is a function of batch SUMS (trainer.py:149-152)
+            parts = [c[idx][name] for c in chunks]
+            want = sum(parts) if "digit" in name else sum(parts) / nck
+            e = abs(v - want) / max(abs(want), 1e-12)
+            worst_l = max(worst_l, (e, name))
+            assert e < ltol, (name, v, want, parts)
+    cancelled = _cancelled_bias_keys(tr)      # conv biases in front of IN / AdaIN: the true gradient is zero, what is there is round-off
+    for idx in ((1,) if focus else (1, 3)):
+        for name, g in full[idx].items():
+            if name in cancelled:
+                continue
+            want = sum(c[idx][name] for c in chunks) / nck
+            if float(want.norm()) < 1e-9:
+                assert float(g.norm()) < 1e-7, name
+                continue
+            e = float((g - want).norm() / want.norm())
+            worst_g = max(worst_g, (e, name))
+            assert e < gtol, (name, e)
+    print("\n[batch-8 = mean of batch-2 chunks, %s %s 256x256] losses: worst %.1e (%s); %s gradients: worst %.1e (%s)" % (
+        cfgname, precision, worst_l[0], worst_l[1], "discriminator" if focus else "discriminator + generator", worst_g[0],
+        worst_g[1]))

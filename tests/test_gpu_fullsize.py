@@ -39,9 +39,9 @@ def _losses(tr, prefix):
     return {k: float(getattr(tr, k)) for k in dir(tr) if k.startswith(prefix) and isinstance(getattr(tr, k), torch.Tensor)}
 
 
-@pytest.mark.parametrize("cfgname,precision,ltol,gtol", [("male2female.yaml", "bf16", 2e-4, 5e-3),
-                                                         ("selfie2anime.yaml", "fp32x3", 2e-5, 1e-3)])
-def test_batch8_update_equals_its_batch2_chunks(cfgname, precision, ltol, gtol):
+@pytest.mark.parametrize("cfgname,precision,ltol,gmax", [("male2female.yaml", "bf16", 1e-4, 0.15),
+                                                         ("selfie2anime.yaml", "fp32x3", 1e-5, 6e-2)])
+def test_batch8_update_equals_its_batch2_chunks(cfgname, precision, ltol, gmax):
     cfg = yaml.safe_load(open(os.path.join(ROOT, "acl-gan_b200", "configs", cfgname)))
     cfg["precision"] = precision
     cfg["display_size"] = 2
@@ -76,16 +76,14 @@ def test_batch8_update_equals_its_batch2_chunks(cfgname, precision, ltol, gtol):
     for k, v in tr.gen_AB.state_dict().items():           # lr = 0: nine Adam launches later the weights are bit-identical
         assert torch.equal(v, w0[k]), k
 
-    worst_l, worst_g = (0.0, ""), (0.0, "")
+    errs_l, errs_g = [], []
     for idx in (0, 2):
         for name, v in full[idx].items():
             if "size" in name or name == "loss_gen_total" and focus:
                 continue                                    # the focus size loss is a function of batch SUMS (trainer.py:149-152)
             parts = [c[idx][name] for c in chunks]
             want = sum(parts) if "digit" in name else sum(parts) / nck
-            e = abs(v - want) / max(abs(want), 1e-12)
-            worst_l = max(worst_l, (e, name))
-            assert e < ltol, (name, v, want, parts)
+            errs_l.append((abs(v - want) / max(abs(want), 1e-12), name))
     cancelled = _cancelled_bias_keys(tr)      # conv biases in front of IN / AdaIN: the true gradient is zero, what is there is round-off
     for idx in ((1,) if focus else (1, 3)):
         for name, g in full[idx].items():
@@ -95,9 +93,21 @@ def test_batch8_update_equals_its_batch2_chunks(cfgname, precision, ltol, gtol):
             if float(want.norm()) < 1e-9:
                 assert float(g.norm()) < 1e-7, name
                 continue
-            e = float((g - want).norm() / want.norm())
-            worst_g = max(worst_g, (e, name))
-            assert e < gtol, (name, e)
-    print("\n[batch-8 = mean of batch-2 chunks, %s %s 256x256] losses: worst %.1e (%s); %s gradients: worst %.1e (%s)" % (
-        cfgname, precision, worst_l[0], worst_l[1], "discriminator" if focus else "discriminator + generator", worst_g[0],
-        worst_g[1]))
+            errs_g.append((float((g - want).norm() / want.norm()), name))
+    errs_l.sort(reverse=True)
+    errs_g.sort(reverse=True)
+    print("\n[batch-8 = mean of batch-2 chunks, %s %s 256x256] %d losses, worst: %s ; %d %s gradient tensors, median %.1e, worst: %s" % (
+        cfgname, precision, len(errs_l), "  ".join("%s %.1e" % (n, e) for e, n in errs_l[:4]), len(errs_g),
+        "discriminator" if focus else "discriminator + generator", errs_g[len(errs_g) // 2][0],
+        "  ".join("%s %.1e" % (n, e) for e, n in errs_g[:6])))
+    # Losses: the forward pass of a sample does not depend on its batch (measured 5e-8 in fp32x3, 4e-6 in bf16); the focus digit
+    # loss sum 1 / (|m - 0.5| + eps) sits on its cusp at a fresh initialisation and amplifies that (measured 5e-4 in bf16).
+    for e, name in errs_l:
+        assert e < (5e-3 if "digit" in name else ltol), (name, e)
+    # Gradients are judged by the statistical rule of tests/test_gpu_step.py: the statistics of a sample are summed in a
+    # batch-dependent order, a last-bit difference there moves bf16 roundings / flips ReLU units, and a flipped unit moves every
+    # gradient upstream of it (measured: median 3e-5 / 1e-4; worst 3e-2 on dis_2 in bf16, whose gradient is a difference of
+    # nearly equal terms, 1.1e-2 on the gen_AB tensors upstream of one unit in fp32x3).  A batch-handling error - a dropped or
+    # doubled sample, a wrong 1 / B - is O(0.1 .. 1) on EVERY tensor.
+    assert errs_g[len(errs_g) // 2][0] < 1e-3, ("systematic gradient error", errs_g[len(errs_g) // 2])
+    assert errs_g[0][0] < gmax, errs_g[:6]

@@ -167,7 +167,7 @@ class MlpArgs(C.Structure):
 class DisHeadArgs(C.Structure):
     _fields_ = [("x", Act), ("c_valid", C.c_int32), ("groups", C.c_int32), ("weight", C.c_uint64), ("bias", C.c_uint64),
                 ("logits", C.c_uint64), ("dlogits", C.c_uint64), ("loss", C.c_uint64), ("target", C.c_float * 4),
-                ("gweight", C.c_float * 4), ("loss_slot", C.c_int32 * 4)]
+                ("gweight", C.c_float * 4), ("loss_slot", C.c_int32 * 4), ("gan_kind", C.c_int32), ("pad_", C.c_int32)]
 
 
 class DisHeadBwdArgs(C.Structure):
@@ -182,6 +182,7 @@ class BlendArgs(C.Structure):
 
 
 LOSS_L1, LOSS_FOCUS = 0, 1
+GAN_LSGAN, GAN_NSGAN = 0, 1         # aclgan_dis_head_args.gan_kind
 
 
 class LossReduceArgs(C.Structure):

@@ -230,8 +230,17 @@ __global__ void __launch_bounds__(256) linear_bwd_x_kernel(const float* __restri
     }
 }
 
-// ------------------------------------------------------------------------------------------ K16 discriminator head + LSGAN
-// one warp per pixel: logit = b + x[pixel] . w (lanes over channels, 8-channel vectors), LSGAN term and gradient seed
+// ------------------------------------------------------------------------------------------ K16 discriminator head + GAN terms
+// NSGAN term of one logit, F.binary_cross_entropy(F.sigmoid(o), t) for t in {0, 1} as PyTorch evaluates it in fp32 (sigmoid
+// first, logs clamped at -100), and d term / d o through BCE's backward (denominator floored at 1e-12) and sigmoid's
+__device__ __forceinline__ void nsgan_term(float o, float t, float& term, float& dterm) {
+    const float p = 1.f / (1.f + expf(-o));
+    const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(1.f - p), -100.f);
+    term = -(t * lp + (1.f - t) * lq);
+    dterm = (p - t) / fmaxf((1.f - p) * p, 1e-12f) * ((1.f - p) * p);
+}
+
+// one warp per pixel: logit = b + x[pixel] . w (lanes over channels, 8-channel vectors), GAN term and gradient seed
 __global__ void __launch_bounds__(256) dis_head_fwd_kernel(aclgan_dis_head_args a) {
     __shared__ double sh[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -250,12 +259,19 @@ __global__ void __launch_bounds__(256) dis_head_fwd_kernel(aclgan_dis_head_args 
         for (int c = lane; c < a.c_valid; c += 32) s += plane_val(a.x, base + c) * __ldg(w + c);
         s = warp_sum(s) + bias;
         const int g = n / n_per;
-        const float diff = s - a.target[g];
         if (lane == 0) {
             reinterpret_cast<float*>(a.logits)[pix] = s;
-            if (a.dlogits != 0)
-                reinterpret_cast<float*>(a.dlogits)[pix] = a.gweight[g] * 2.f * diff / (float)(n_per * hw);
-            part[g] += (double)diff * (double)diff;
+            if (a.gan_kind == ACLGAN_GAN_NSGAN) {
+                float term, dterm;
+                nsgan_term(s, a.target[g], term, dterm);
+                if (a.dlogits != 0) reinterpret_cast<float*>(a.dlogits)[pix] = a.gweight[g] * dterm / (float)(n_per * hw);
+                part[g] += (double)term;
+            } else {
+                const float diff = s - a.target[g];
+                if (a.dlogits != 0)
+                    reinterpret_cast<float*>(a.dlogits)[pix] = a.gweight[g] * 2.f * diff / (float)(n_per * hw);
+                part[g] += (double)diff * (double)diff;
+            }
         }
     }
     if (a.loss == 0) return;
@@ -532,6 +548,7 @@ extern "C" int aclgan_mlp_bwd(const aclgan_mlp_args* a, void* stream) {
 
 extern "C" int aclgan_dis_head_fwd(const aclgan_dis_head_args* a, void* stream) {
     if (a->groups < 1 || a->groups > 4 || a->x.n % a->groups != 0 || a->c_valid < 1 || a->c_valid > a->x.c) return ACLGAN_ERR_SHAPE;
+    if (a->gan_kind != ACLGAN_GAN_LSGAN && a->gan_kind != ACLGAN_GAN_NSGAN) return ACLGAN_ERR_UNSUPPORTED;
     const int64_t npix = (int64_t)a->x.n * a->x.h * a->x.w;
     dis_head_fwd_kernel<<<grid1d(npix, 8, 148 * 2), 256, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();

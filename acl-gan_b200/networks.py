@@ -23,6 +23,7 @@ import aclgan_native as N
 import engine as E
 
 _ACT = {"relu": N.ACT_RELU, "lrelu": N.ACT_LRELU, "tanh": N.ACT_TANH, "none": N.ACT_NONE}
+_GAN_KIND = {"lsgan": N.GAN_LSGAN, "nsgan": N.GAN_NSGAN}     # MsImageDis gan_type (reference networks.py:66-74)
 _NORM = {"none": N.NORM_NONE, "in": N.NORM_IN, "adain": N.NORM_ADAIN, "ln": N.NORM_LN}
 
 _default_engine = {}
@@ -697,8 +698,9 @@ class MsImageDis(_EngineNet):
         return out
 
     def _head(self, tape, conv, x, tw, lsgan=None):
-        """1x1 conv dim*8 -> 1 (networks.py:45) as a warp-per-pixel dot product on the un-padded plane, fused with the LSGAN
-        terms (per image group) and d loss / d logits when `lsgan` is given"""
+        """1x1 conv dim*8 -> 1 (networks.py:45) as a warp-per-pixel dot product on the un-padded plane, fused with the GAN terms
+        (per image group; LSGAN or, for gan_type 'nsgan', sigmoid + binary cross entropy) and d loss / d logits when `lsgan`
+        (targets / weights / accumulator slots) is given"""
         eng = self._eng
         L = N.lib()
         c = x.c_valid
@@ -715,6 +717,8 @@ class MsImageDis(_EngineNet):
             for i in range(k):
                 a.target[i], a.gweight[i], a.loss_slot[i] = lsgan["targets"][i], lsgan["weights"][i], lsgan["slots"][i]
             a.loss = lsgan["acc"].data_ptr()
+            self._check_gan()            # (like the reference, an unknown gan_type only fails where a loss is formed)
+            a.gan_kind = _GAN_KIND[self.gan_type]
             if tape.enabled:
                 dl = torch.empty((x.n, 1, x.h, x.w), dtype=torch.float32, device=eng.device)
                 a.dlogits = dl.data_ptr()
@@ -751,14 +755,14 @@ class MsImageDis(_EngineNet):
         tape = E.Tape(enabled=False)
         return [o.t for o in self.dis(tape, E.ImgT(x.detach().float()))]
 
-    @staticmethod
-    def _lsgan(outs, target):
+    def _lsgan(self, outs, target):
+        """the per-scale GAN terms of networks.py:60-106 on logit tensors (the updates use the fused head kernel instead)"""
+        if self.gan_type == "nsgan":
+            return sum(F.binary_cross_entropy(torch.sigmoid(o), torch.full_like(o, target)) for o in outs)
         return sum(torch.mean((o - target) ** 2) for o in outs)
 
     def _check_gan(self):
-        if self.gan_type == "nsgan":
-            raise NotImplementedError("gan_type 'nsgan' is outside the B200 hot path")
-        if self.gan_type != "lsgan":
+        if self.gan_type not in _GAN_KIND:
             assert 0, "Unsupported GAN type: {}".format(self.gan_type)
 
     def calc_dis_loss(self, input_fake, input_real):

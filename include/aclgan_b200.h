@@ -471,18 +471,23 @@ typedef struct aclgan_mlp_args {
 int aclgan_mlp_fwd(const aclgan_mlp_args* a, void* stream);
 int aclgan_mlp_bwd(const aclgan_mlp_args* a, void* stream);
 
-/* discriminator head Conv2d(C, 1, 1) (networks.py:45) fused with the LSGAN terms mean((o - t)^2) of networks.py:67,83,98 and
- * their gradient seed.  The batch holds `groups` image groups of equal size (one discriminator evaluated once over the
- * concatenation of its inputs); group g has target[g], loss weight gweight[g] and loss accumulator slot loss_slot[g]. */
+/* discriminator head Conv2d(C, 1, 1) (networks.py:45) fused with the GAN terms of networks.py:60-106 and their gradient seed.
+ * gan_kind ACLGAN_GAN_LSGAN: mean((o - t)^2) (networks.py:67,83,98); ACLGAN_GAN_NSGAN: mean of
+ * F.binary_cross_entropy(F.sigmoid(o), t) with t in {0, 1} (networks.py:68-72,84-86,99-103; fp32 sigmoid, log clamped at -100 and
+ * the 1e-12 floor of its backward as in PyTorch).  The batch holds `groups` image groups of equal size (one discriminator
+ * evaluated once over the concatenation of its inputs); group g has target[g], loss weight gweight[g] and loss accumulator
+ * slot loss_slot[g]. */
+enum { ACLGAN_GAN_LSGAN = 0, ACLGAN_GAN_NSGAN = 1 };
 typedef struct aclgan_dis_head_args {
     aclgan_act x;             /* last feature plane */
     int32_t c_valid, groups;  /* groups <= 4 */
     uint64_t weight, bias;    /* fp32 [c_valid], [1] */
     uint64_t logits;          /* out fp32 [N][h][w] */
-    uint64_t dlogits;         /* out fp32 [N][h][w] = gweight[g] * 2 (o - target[g]) / (n_per * h * w), or 0 */
-    uint64_t loss;            /* double accumulators: loss[loss_slot[g]] += mean over the group of (o - target[g])^2, or 0 */
+    uint64_t dlogits;         /* out fp32 [N][h][w] = gweight[g] * d term / d o / (n_per * h * w)  (LSGAN: 2 (o - target[g])), or 0 */
+    uint64_t loss;            /* double accumulators: loss[loss_slot[g]] += mean over the group of the GAN term, or 0 */
     float target[4], gweight[4];
     int32_t loss_slot[4];
+    int32_t gan_kind, pad_;   /* ACLGAN_GAN_* */
 } aclgan_dis_head_args;
 int aclgan_dis_head_fwd(const aclgan_dis_head_args* a, void* stream);
 typedef struct aclgan_dis_head_bwd_args {

@@ -200,24 +200,33 @@ def dis_forward(x, p: Params, D: dict) -> List[torch.Tensor]:
     return outs
 
 
-def lsgan(outs: Sequence[torch.Tensor], target: float):
-    """sum over scales of mean((o - t)^2)  (networks.py:67, 83, 98)."""
+def lsgan(outs: Sequence[torch.Tensor], target: float, gan_type: str = "lsgan"):
+    """sum over scales of the GAN term against a constant target: 'lsgan' mean((o - t)^2) (networks.py:67, 83, 98);
+    'nsgan' F.binary_cross_entropy(F.sigmoid(o), t) (networks.py:68-72, 84-86, 99-103; the outer torch.mean there acts on the
+    sum of two already-reduced scalars)."""
     loss = 0
     for o in outs:
-        loss = loss + torch.mean((o - target) ** 2)
+        if gan_type == "lsgan":
+            loss = loss + torch.mean((o - target) ** 2)
+        elif gan_type == "nsgan":
+            loss = loss + F.binary_cross_entropy(torch.sigmoid(o), torch.full_like(o, target))
+        else:
+            assert 0, "Unsupported GAN type: {}".format(gan_type)
     return loss
 
 
 def calc_dis_loss(fake, real, p, D):   # networks.py:60-75
-    return lsgan(dis_forward(fake, p, D), 0.0) + lsgan(dis_forward(real, p, D), 1.0)
+    gt = D.get("gan_type", "lsgan")
+    return lsgan(dis_forward(fake, p, D), 0.0, gt) + lsgan(dis_forward(real, p, D), 1.0, gt)
 
 
 def calc_gen_loss(fake, p, D):         # networks.py:77-89
-    return lsgan(dis_forward(fake, p, D), 1.0)
+    return lsgan(dis_forward(fake, p, D), 1.0, D.get("gan_type", "lsgan"))
 
 
 def calc_gen_d2_loss(fake, real, p, D):  # networks.py:91-106
-    return lsgan(dis_forward(fake, p, D), 1.0) + lsgan(dis_forward(real, p, D), 0.0)
+    gt = D.get("gan_type", "lsgan")
+    return lsgan(dis_forward(fake, p, D), 1.0, gt) + lsgan(dis_forward(real, p, D), 0.0, gt)
 
 
 def focus_translation(fg, bg, focus):

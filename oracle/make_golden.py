@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
 
-    python oracle/make_golden.py            # writes tests/golden/{tiny,p0,p0nf,p1_256,p2_256}_{fp32,fp64}.pt
+    python oracle/make_golden.py            # writes tests/golden/{tiny,p0,p0nf,nsgan,p1_256,p2_256}_{fp32,fp64}.pt
                                             # (the two 256x256 cases take ~4 minutes each in fp64 on 8 cores)
 
 Recipe: torch.manual_seed(0) -> aclgan_Trainer(cfg); manual_seed(1) ->
@@ -36,7 +36,9 @@ def load_cfg(name):
 def case_config(case):
     """p0 := configs/male2female.yaml at 64x64 bs=1 (BASELINE.json configs[0]);
     p0nf := same with the focus branch off (selfie2anime variant);
-    tiny := narrow networks (dim 16) at 64x64 bs=2 for fast CPU/GPU parity sweeps."""
+    tiny := narrow networks (dim 16) at 64x64 bs=2 for fast CPU/GPU parity sweeps;
+    nsgan := the tiny networks, focus branch off, with dis.gan_type 'nsgan' (the dormant loss option of networks.py:68-72,
+    84-86, 99-103)."""
     if case == "p0":
         cfg = load_cfg("male2female.yaml")
         return cfg, 1, 64
@@ -47,6 +49,12 @@ def case_config(case):
         cfg = load_cfg("male2female.yaml")
         cfg["gen"].update(dim=16, mlp_dim=32, n_res=2)
         cfg["dis"].update(dim=16)
+        cfg["display_size"] = 2
+        return cfg, 2, 64
+    if case == "nsgan":
+        cfg = load_cfg("selfie2anime.yaml")
+        cfg["gen"].update(dim=16, mlp_dim=32, n_res=2)
+        cfg["dis"].update(dim=16, gan_type="nsgan")
         cfg["display_size"] = 2
         return cfg, 2, 64
     if case == "p1_256":       # BASELINE.json configs[1] geometry (male2female 256x256), batch 2 to bound the CPU fp64 run
@@ -201,7 +209,7 @@ def run_case(case, dtype):
 
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    cases = sys.argv[1:] or ["tiny", "p0", "p0nf", "p1_256", "p2_256"]
+    cases = sys.argv[1:] or ["tiny", "p0", "p0nf", "nsgan", "p1_256", "p2_256"]
     for case in cases:
         for dtype, tag in ((torch.float32, "fp32"), (torch.float64, "fp64")):
             res = run_case(case, dtype)

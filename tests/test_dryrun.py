@@ -131,3 +131,19 @@ def test_too_small_image_is_a_shape_error(dry):
     x = torch.rand(1, 3, 100, 60) * 2 - 1
     with pytest.raises(N.NativeError, match="ACLGAN_ERR_SHAPE"):
         tr.dis_update(x, x, cfg)
+
+
+def test_nsgan_updates_dryrun(dry):
+    """gan_type 'nsgan' (reference networks.py:68-72, 84-86, 99-103) takes the same path: the head kernel gets gan_kind = NSGAN"""
+    cfg = _cfg("selfie2anime.yaml")
+    cfg["dis"]["gan_type"] = "nsgan"
+    cfg["cuda_graphs"] = 0
+    tr = T.aclgan_Trainer(copy.deepcopy(cfg))
+    x = torch.rand(2, 3, 64, 64) * 2 - 1
+    tr.dis_update(x, x, cfg)
+    tr.gen_update(x, x, cfg)
+    assert dry["aclgan_dis_head_fwd"] == 18          # 3 discriminators x 3 scales per update
+    cfg["dis"]["gan_type"] = "wgan"
+    tr = T.aclgan_Trainer(copy.deepcopy(cfg))           # the reference, too, only fails where the loss is formed
+    with pytest.raises(AssertionError, match="Unsupported GAN type"):
+        tr.dis_update(x, x, cfg)

@@ -109,6 +109,48 @@ def test_mlp(n):
     assert G.rel_err(dx, x64.grad) < 2e-5
 
 
+@pytest.mark.parametrize("scale,seed", [(0.05, 4), (0.4, 15)])
+def test_dis_head_nsgan(scale, seed):
+    """gan_kind NSGAN: F.binary_cross_entropy(F.sigmoid(o), t) per image group and its gradient seed (reference
+    networks.py:68-72, 84-86, 99-103), against the fp32 ATen expression the reference evaluates (same clamps) and its autograd.
+    The second case (CPU-seeded so it is the same everywhere) has one target-0 logit at +26: the fp32 sigmoid is exactly 1 there
+    and the term is the -100 clamp of the logarithm; it has no target-0 logit in (11, 19), where 1 - sigmoid(o) is a handful of
+    fp32 ulps and a last-bit difference of expf would move the term by O(1)."""
+    torch.manual_seed(seed)
+    groups, n_per, c, h, w = 2, 3, 512, 4, 4
+    nimg = n_per * groups
+    x = torch.randn(nimg, c, h, w).cuda()
+    act, buf, xeff = G.make_act(x, 0, c, 2)
+    W = (torch.randn(c) * scale).cuda()
+    b = torch.randn(1).cuda()
+    targets, weights = [0.0, 1.0], [1.0, 0.2]
+    logits = torch.empty(nimg, 1, h, w, device="cuda")
+    dl = torch.empty_like(logits)
+    acc = torch.zeros(8, dtype=torch.float64, device="cuda")
+    a = N.DisHeadArgs()
+    a.x, a.c_valid, a.groups, a.gan_kind = act, c, groups, N.GAN_NSGAN
+    a.weight, a.bias, a.logits, a.dlogits, a.loss = W.data_ptr(), b.data_ptr(), logits.data_ptr(), dl.data_ptr(), acc.data_ptr()
+    for i in range(groups):
+        a.target[i], a.gweight[i], a.loss_slot[i] = targets[i], weights[i], i
+    N.check(N.lib().aclgan_dis_head_fwd(C.byref(a), SP()), "dis_head_fwd")
+    g0 = logits[:n_per].flatten()
+    assert int(((g0 > 11.0) & (g0 < 19.0)).sum()) == 0
+    o = logits.detach().clone().requires_grad_(True)           # the loss as a function of the kernel's own fp32 logits
+    total = 0
+    for i in range(groups):
+        og = o[i * n_per:(i + 1) * n_per]
+        term = F.binary_cross_entropy(torch.sigmoid(og), torch.full_like(og, targets[i]))
+        assert abs(float(acc[i]) - float(term)) < 2e-6 * float(term) + 1e-9, (i, float(acc[i]), float(term))
+        total = total + weights[i] * term
+    total.backward()
+    assert bool(torch.isfinite(dl).all())
+    assert G.rel_err(dl, o.grad) < 1e-5, G.rel_err(dl, o.grad)
+    if scale > 0.1:
+        assert float(g0.max()) > 20.0 and float(acc[0]) > 100.0 / g0.numel()      # the clamped term is in the mean
+    a.gan_kind = 7
+    assert N.lib().aclgan_dis_head_fwd(C.byref(a), SP()) == -3          # ACLGAN_ERR_UNSUPPORTED
+
+
 @pytest.mark.parametrize("planes,kind,groups", [(1, 0, 3), (2, 1, 2), (1, 0, 1)])
 def test_dis_head_lsgan(planes, kind, groups):
     """Conv2d(512, 1, 1) head (networks.py:45) + LSGAN terms / gradient seed (networks.py:67,83,98) per image group"""

@@ -111,7 +111,7 @@ def _cancelled_bias_keys(tr):
 
 
 @pytest.mark.parametrize("case,precision", [("tiny", "fp32x3"), ("p0", "fp32x3"), ("p0nf", "fp32x3"), ("tiny", "bf16"),
-                                            ("p0", "bf16")])
+                                            ("p0", "bf16"), ("nsgan", "fp32x3"), ("nsgan", "bf16")])
 def test_step_vs_golden(golden_dir, case, precision):
     g32, g64 = _load(golden_dir, case, "fp32"), _load(golden_dir, case, "fp64")
     tr, cfg = _build(g32, precision)

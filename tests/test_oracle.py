@@ -12,7 +12,7 @@ import torch
 import aclgan_oracle as O
 import ref_shim
 
-CASES = ["tiny", "p0", "p0nf"]
+CASES = ["tiny", "p0", "p0nf", "nsgan"]
 
 
 def _load(golden_dir, case, tag):
@@ -114,3 +114,10 @@ def test_forward_matches_live_reference():
     for a, b in zip(O.dis_forward(x6, pd, d_cfg), dis.forward(x6)):
         assert _rel(a, b) < 1e-12
     assert abs(float(O.calc_dis_loss(x6, x6 * 0.5, pd, d_cfg)) - float(dis.calc_dis_loss(x6, x6 * 0.5))) < 1e-12
+    # the dormant 'nsgan' option (networks.py:68-72, 84-86, 99-103): same weights, sigmoid + binary cross entropy
+    dis.gan_type = "nsgan"
+    n_cfg = dict(d_cfg, gan_type="nsgan")
+    with ref_shim.cpu_shim():
+        assert abs(float(O.calc_dis_loss(x6, x6 * 0.5, pd, n_cfg)) - float(dis.calc_dis_loss(x6, x6 * 0.5))) < 1e-12
+        assert abs(float(O.calc_gen_loss(x6, pd, n_cfg)) - float(dis.calc_gen_loss(x6))) < 1e-12
+        assert abs(float(O.calc_gen_d2_loss(x6, x6 * 0.5, pd, n_cfg)) - float(dis.calc_gen_d2_loss(x6, x6 * 0.5))) < 1e-12

@@ -133,6 +133,12 @@ class Tape:
                 main.wait_stream(streams[t])
 
 
+# Debug switch (tools/poison_check.py, ACLGAN_POISON=1): planes that are allocated WITHOUT a memset are filled with bf16 quiet
+# NaNs, so a halo / channel-pad element that a consumer reads but no producer wrote surfaces as a non-finite loss instead of
+# depending on what the allocator handed out.  Off in the product path (the fill is an ATen kernel).
+POISON = os.environ.get("ACLGAN_POISON", "0") != "0"
+
+
 class ActT:
     """Reflect-padded NHWC activation plane(s): buf [planes, numel + slack] bf16."""
 
@@ -147,6 +153,8 @@ class ActT:
         self.buf = torch.empty((self.planes, self.numel + 64), dtype=torch.bfloat16, device=eng.device)
         if zero or self.c < 64 or self.c != c_valid:
             zero_(self.buf)
+        elif POISON:
+            self.buf.view(torch.int16).fill_(0x7FC0)
         self.gp = None            # gradient of the padded plane [n, h+2p, w+2p, c] (engine gradient dtype)
         self.gr = None            # dense gradient [n, h, w, c] (residual branches / heads)
         self.requires_grad = False
@@ -443,6 +451,8 @@ class Engine:
     # ------------------------------------------------------------------------------------------ helpers
     def new_dense(self, n, h, w, c, zero=False):
         t = torch.empty((n, h, w, c), dtype=self.prec.dtype, device=self.device)
+        if POISON and not zero:
+            t.fill_(float("nan"))
         return zero_(t) if zero else t
 
     def t4(self, t):

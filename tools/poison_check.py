@@ -2,7 +2,7 @@
 writing every element a consumer reads).  Runs one dis_update + gen_update + sample() of a small trainer twice - normally and with
 engine.POISON on, where every plane that is allocated without a memset starts as bf16 NaNs - and compares every loss and every
 gradient: a consumer that reads an element no producer wrote turns the losses non-finite.
-usage (GPU box): python tools/poison_check.py [bf16|fp32x3] [dim]"""
+usage (GPU box): python tools/poison_check.py [bf16|fp32x3] [dim] [--eager-too]"""
 import copy
 import os
 import sys
@@ -47,7 +47,7 @@ def run(poison, cfgname, graphs):
 
 bad = 0
 for cfgname in ("male2female.yaml", "selfie2anime.yaml"):
-    for graphs in (1, 0):
+    for graphs in ((1, 0) if "--eager-too" in sys.argv else (1,)):
         a, b = run(False, cfgname, graphs), run(True, cfgname, graphs)
         worst = (0.0, "")
         for k in a:

@@ -9,6 +9,7 @@ Reference behaviour being reproduced (file:line under /root/reference): Conv2dBl
 ResBlock.forward :306-310, nn.Upsample :256, AdaptiveInstanceNorm2d.forward :490-503, LayerNorm.forward
 :520-536, and autograd's backward of all of them under loss.backward() (trainer.py:169,292).
 """
+import contextlib
 import ctypes as C
 import math
 import os
@@ -42,6 +43,23 @@ def zero_(t):
 
 def zeros(shape, dtype, device):
     return zero_(torch.empty(shape, dtype=dtype, device=device))
+
+
+@contextlib.contextmanager
+def _plan_env(name, value):
+    """sets a plan-time triage switch (csrc/plans.cu reads them with getenv) for the duration of one host-side plan call"""
+    if value is None:
+        yield
+        return
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        yield
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
 
 
 def copy_(dst, src):
@@ -581,8 +599,12 @@ class Engine:
     def conv_wgrad(self, layer, dy, x, transpose_taps=False):
         plan = N.WgradPlan()
         dys, xs = dy.struct(), x.struct()
-        N.check(N.lib().aclgan_plan_conv_wgrad(C.byref(layer.desc), C.byref(dys), C.byref(xs),
-                                               layer.dw().data_ptr(), C.byref(plan)), "plan_conv_wgrad")
+        # transposed taps need a box-per-tap plan (below); the plan builder would pick a segment plan whenever the strip is a
+        # multiple of 64 pixels long (2H - 4 = 64 k: inputs of 68, 136, 260 ... pixels), so that choice is switched off for this
+        # one host-side call (the switch is read with getenv at plan time; plans are built on one thread, at capture time)
+        with _plan_env("ACLGAN_WGRAD_SEG", "0" if transpose_taps else None):
+            N.check(N.lib().aclgan_plan_conv_wgrad(C.byref(layer.desc), C.byref(dys), C.byref(xs),
+                                                   layer.dw().data_ptr(), C.byref(plan)), "plan_conv_wgrad")
         if transpose_taps:
             # the operands are TRANSPOSED strips convolved with the transposed filter: tap (kh, kw) of the plan is tap (kw, kh)
             # of the stored weight gradient (box-per-tap plans only: the segment plans write consecutive tap slots)

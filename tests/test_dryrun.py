@@ -109,9 +109,10 @@ def test_full_width_plans_dryrun(dry):
     tr.gen_update(x, x, cfg)
 
 
-@pytest.mark.parametrize("h,w", [(72, 72), (96, 80)])
+@pytest.mark.parametrize("h,w", [(72, 72), (96, 80), (68, 136)])
 def test_ragged_image_sizes_dryrun(dry, h, w):
-    """crop sizes that are multiples of 4 but not powers of two: every plan of both updates and of sample() builds"""
+    """crop sizes that are multiples of 4 but not powers of two: every plan of both updates and of sample() builds
+    (68 / 136: the up blocks' column strips are 64 / 128 pixels long, tests/test_plans.py::test_conv_wgrad_strip_plan_...)"""
     cfg = _cfg()
     cfg["cuda_graphs"] = 0
     torch.manual_seed(0)

@@ -1,5 +1,6 @@
 """CPU validation of the host-side plan builders (csrc/plans.cu) by emulating their TMA/MMA/epilogue contract."""
 import ctypes as C
+import os
 
 import pytest
 import torch
@@ -226,7 +227,8 @@ def test_conv_wgrad_plan(cin, cout, k, s, pad, window, n, h, w, planes):
     dw = torch.zeros(rows.value * kt.value, dtype=torch.float64)
     plan = N.WgradPlan()
     N.check(L.aclgan_plan_conv_wgrad(C.byref(desc), C.byref(yact), C.byref(xact), mem.add(dw), C.byref(plan)), "plan wgrad")
-    assert bool(plan.seg_mode) == ((s == 1 and window == 0 and 1 < k <= 7 and wo % 64 == 0) or
+    seg_on = os.environ.get("ACLGAN_WGRAD_SEG", "1") != "0"
+    assert bool(plan.seg_mode) == ((s == 1 and window == 0 and 1 < k <= 7 and wo % 64 == 0 and seg_on) or
                                    (s == 1 and window == 1 and wo >= 16 and ho >= 4) or
                                    (s == 1 and window == 2 and w + 2 * pad >= 16 and ho >= 4))
     emul.run_wgrad(mem, plan)
@@ -295,3 +297,16 @@ def test_conv_dgrad_plan_ragged(cin, cout, k, s, pad, n, ho, wo, planes):
     (64, 4, 7, 1, 3, 0, 1, 9, 100, 1), (64, 64, 3, 1, 1, 0, 2, 45, 45, 1)])
 def test_conv_wgrad_plan_ragged(cin, cout, k, s, pad, window, n, h, w, planes):
     test_conv_wgrad_plan(cin, cout, k, s, pad, window, n, h, w, planes)
+
+
+@pytest.mark.parametrize("cin,cout,n,w,planes", [(128, 64, 2, 64, 1), (64, 64, 4, 128, 2)])
+def test_conv_wgrad_strip_plan_is_box_per_tap_at_64_pixel_multiples(monkeypatch, cin, cout, n, w, planes):
+    """the column strips of the sub-pixel up blocks (2 rows x 2H - 4 pixels, 5x5) need a box-per-tap weight-gradient plan (their
+    taps are stored transposed, engine.conv_wgrad(transpose_taps=True)); for H = 34, 66, ... the strip is a multiple of 64 pixels
+    long, where the builder prefers a segment plan: the engine switches that choice off for the call.  Same switch, same geometry
+    here, result against torch."""
+    import engine as E
+    with E._plan_env("ACLGAN_WGRAD_SEG", "0"):
+        assert os.environ["ACLGAN_WGRAD_SEG"] == "0"
+        test_conv_wgrad_plan(cin, cout, 5, 1, 2, 0, n, 3, w, planes)      # (3 rows: the test helper reflect-pads by 2)
+    assert "ACLGAN_WGRAD_SEG" not in os.environ

@@ -423,7 +423,7 @@ def run_b200(args):
     if not args.no_library_bar and world == 1:
         line["library_bar"] = library_bar(load_cfg(args.config), B, S)
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(load_cfg(args.config), S, steps=1, warmup=0)
+        line["cpu_baseline"] = cpu_baseline(load_cfg(args.config), S, steps=3, warmup=1)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -78,3 +78,36 @@ def test_augment_kernel_bit_exact_and_device_loader(tmp_path):
     full = torch.stack([dev.dataset[i] for i in range(6)])
     for img in batch.cpu():
         assert any(torch.equal(img, f) or torch.equal(img, f.flip(-1)) for f in full)
+
+
+def test_host_loaders_identical_to_reference_loaders(tmp_path):
+    """get_all_data_loaders (reference utils.py:43-100) in folder and file-list mode against the UNMODIFIED reference's own
+    loaders on the same seed: every train / test batch identical (same dataset order, shuffle, flip, resize, crop draws)."""
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference sources not available")
+    from PIL import Image
+    _, _, rutils = ref_shim.import_reference()
+    rng = np.random.RandomState(0)
+    tmp = str(tmp_path)
+    for sub in ("trainA", "trainB", "testA", "testB"):
+        os.makedirs(os.path.join(tmp, sub))
+        for i in range(5):
+            Image.fromarray(rng.randint(0, 256, (50 + 3 * i, 70, 3), dtype=np.uint8)).save(os.path.join(tmp, sub, "%d.png" % i))
+        with open(os.path.join(tmp, sub + ".txt"), "w") as f:
+            f.write("\n".join("%d.png" % i for i in (3, 1, 4, 0)) + "\n")
+    conf = dict(batch_size=2, num_workers=0, new_size=40, crop_image_height=32, crop_image_width=36, data_kind="x",
+                data_root=tmp, gpu_augment=0)
+    conf_list = {k: v for k, v in conf.items() if k != "data_root"}
+    for d, sub in (("train_a", "trainA"), ("train_b", "trainB"), ("test_a", "testA"), ("test_b", "testB")):
+        conf_list["data_folder_" + d] = os.path.join(tmp, sub)
+        conf_list["data_list_" + d] = os.path.join(tmp, sub + ".txt")
+    for c in (conf, conf_list):
+        torch.manual_seed(5)
+        mine = [[b.clone() for b in loader] for loader in utils.get_all_data_loaders(c)]
+        torch.manual_seed(5)
+        ref = [[b.clone() for b in loader] for loader in rutils.get_all_data_loaders(c)]
+        for i, (m, r) in enumerate(zip(mine, ref)):
+            assert len(m) == len(r) == 2, (i, len(m), len(r))
+            assert tuple(m[0].shape) == ((2, 3, 32, 36) if i < 2 else (2, 3, 40, 40))      # test loaders crop to new_size
+            assert all(torch.equal(a, b) for a, b in zip(m, r)), ("loader %d differs from the reference's" % i)

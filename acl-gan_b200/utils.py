@@ -66,12 +66,18 @@ def get_model_list(dirname, key):
 
 
 def pytorch03_to_pytorch04(state_dict_base, trainer_name):
-    """strips the InstanceNorm running-stat keys very old checkpoints carry (utils.py:309-330)"""
-    def clean(sd):
-        return {k: v for k, v in sd.items()
-                if not (k.endswith(("running_mean", "running_var", "num_batches_tracked")) and
-                        k.startswith(("enc_content.model", "enc.model")))}
-    return {k: clean(v) for k, v in state_dict_base.items()}
+    """reference utils.py:309-388, behaviour for behaviour: takes a checkpoint with the MUNIT-era keys 'a' / 'b'; for
+    trainer_name 'MUNIT' the InstanceNorm running statistics PyTorch 0.3 stored in the content encoder (model.0-2 and the eight
+    ResBlock convs of model.3) are dropped, for every other trainer name - 'aclgan' included - the dictionaries come back
+    unchanged (the reference's second key list sits in a nested function that is never called)."""
+    import re
+    stale = re.compile(r"enc_content\.model\.([012]|3\.model\.[0-3]\.model\.[01])\.norm\.running_(mean|var)$")
+
+    def core(sd):
+        if trainer_name != "MUNIT":
+            return dict(sd)
+        return {k: v for k, v in sd.items() if not stale.search(k)}
+    return {"a": core(state_dict_base["a"]), "b": core(state_dict_base["b"])}
 
 
 def vgg_preprocess(batch):
@@ -121,27 +127,29 @@ def _grid(image_outputs, display_image_num, file_name):
 
 
 def write_2images(image_outputs, display_image_num, image_directory, postfix):
-    n = len(image_outputs)
-    _grid(image_outputs[0:n // 2], display_image_num, "%s/gen_a2b_%s.jpg" % (image_directory, postfix))
-    _grid(image_outputs[n // 2:n], display_image_num, "%s/gen_b2a_%s.jpg" % (image_directory, postfix))
+    """the reference (utils.py:122-124) writes ALL rows sample() returns - they are one translation direction - into
+    gen_a2b_<postfix>.jpg and no gen_b2a file (its write_html still links one)"""
+    _grid(image_outputs, display_image_num, "%s/gen_a2b_%s.jpg" % (image_directory, postfix))
 
 
 def write_html(filename, iterations, image_save_iterations, image_directory, all_size=1536):
-    rows = []
+    """the reference's index page (utils.py:139-171): a 30 s auto-refresh page with the two "current" grids, then for every
+    saved iteration (newest first) the four test / train grids; same headings, links and widths"""
+    rows = ["<h3>current</h3>"]
 
-    def row(path):
-        rows.append('<h3>%s</h3><a href="%s"><img src="%s" style="width:%dpx"></a><br>' % (
-            os.path.basename(path), path, path, all_size))
+    def row(it, path):
+        rows.append('<h3>iteration [%d] (%s)</h3>\n<p><a href="%s">\n<img src="%s" style="width:%dpx">\n</a><br>\n<p>' % (
+            it, path.split("/")[-1], path, path, all_size))
 
-    row("%s/gen_a2b_train_current.jpg" % image_directory)
-    row("%s/gen_b2a_train_current.jpg" % image_directory)
+    row(iterations, "%s/gen_a2b_train_current.jpg" % image_directory)
+    row(iterations, "%s/gen_b2a_train_current.jpg" % image_directory)
     for j in range(iterations, image_save_iterations - 1, -1):
         if j % image_save_iterations == 0:
             for tag in ("a2b_test", "b2a_test", "a2b_train", "b2a_train"):
-                row("%s/gen_%s_%08d.jpg" % (image_directory, tag, j))
+                row(j, "%s/gen_%s_%08d.jpg" % (image_directory, tag, j))
     with open(filename, "w") as f:
-        f.write('<html><head><title>Experiment = %s</title><meta http-equiv="refresh" content="30"></head><body>%s'
-                "</body></html>" % (os.path.basename(filename), "\n".join(rows)))
+        f.write('<!DOCTYPE html>\n<html>\n<head>\n<title>Experiment name = %s</title>\n<meta http-equiv="refresh" content="30">\n'
+                "</head>\n<body>\n%s\n</body></html>" % (os.path.basename(filename), "\n".join(rows)))
 
 
 # ------------------------------------------------------------------------------------------ data

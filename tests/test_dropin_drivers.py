@@ -57,8 +57,8 @@ def _check_training_outputs(tmp, last_iter):
     ck = os.path.join(out, "checkpoints")
     for name in ("gen_%08d.pt" % last_iter, "dis_%08d.pt" % last_iter, "optimizer.pt"):
         assert os.path.isfile(os.path.join(ck, name)), (name, os.listdir(ck))
-    for name in ("gen_a2b_train_current.jpg", "gen_b2a_train_current.jpg", "gen_a2b_test_%08d.jpg" % last_iter,
-                 "gen_b2a_train_%08d.jpg" % last_iter):
+    # (the reference's write_2images puts every row of sample() into the gen_a2b file and writes no gen_b2a file, utils.py:122-124)
+    for name in ("gen_a2b_train_current.jpg", "gen_a2b_test_%08d.jpg" % last_iter, "gen_a2b_train_%08d.jpg" % last_iter):
         assert os.path.getsize(os.path.join(out, "images", name)) > 0
     assert os.path.isfile(os.path.join(out, "index.html")) and os.path.isfile(os.path.join(out, "config.yaml"))
     rows = [l.split("\t") for l in open(os.path.join(tmp, "out", "logs", "tiny", "scalars.tsv"))]

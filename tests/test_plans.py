@@ -310,3 +310,35 @@ def test_conv_wgrad_strip_plan_is_box_per_tap_at_64_pixel_multiples(monkeypatch,
         assert os.environ["ACLGAN_WGRAD_SEG"] == "0"
         test_conv_wgrad_plan(cin, cout, 5, 1, 2, 0, n, 3, w, planes)      # (3 rows: the test helper reflect-pads by 2)
     assert "ACLGAN_WGRAD_SEG" not in os.environ
+
+
+@pytest.mark.parametrize("w", [60, 64])
+def test_conv_wgrad_transposed_taps(w):
+    """engine.conv_wgrad(transpose_taps=True), step for step on the CPU: box-per-tap plan (segment choice off), tap slot (kh, kw)
+    redirected to (kw, kh), emulated launch - the stored gradient is the weight gradient with its two filter axes swapped.
+    w = 64 is the strip length at which the builder would otherwise choose a segment plan."""
+    import engine as E
+    L = N.lib()
+    torch.manual_seed(5)
+    cin, cout, k, n, h = 128, 64, 5, 2, 3
+    mem = emul.Memory()
+    desc = N.ConvDesc(cin, cout, k, 1, 2, 0)
+    x = torch.randn(n, cin, h, w)
+    dy = torch.randn(n, cout, h, w)
+    xact, _, xeff = make_act(mem, x, 2, cin, 1)
+    yact, _, yeff = make_act(mem, dy, k - 1, cout, 1, mode="constant")
+    yeff = yeff[:, :, k - 1:k - 1 + h, k - 1:k - 1 + w]
+    layout = L.aclgan_wgrad_layout(C.byref(desc))
+    rows, kt = C.c_int64(), C.c_int64()
+    L.aclgan_packed_weight_shape(C.byref(desc), layout, C.byref(rows), C.byref(kt))
+    dw = torch.zeros(rows.value * kt.value, dtype=torch.float64)
+    plan = N.WgradPlan()
+    with E._plan_env("ACLGAN_WGRAD_SEG", "0"):
+        N.check(L.aclgan_plan_conv_wgrad(C.byref(desc), C.byref(yact), C.byref(xact), mem.add(dw), C.byref(plan)), "plan wgrad")
+    assert plan.seg_mode == 0 and plan.num_taps == k * k
+    for t in range(k * k):
+        plan.tap_out[t] = (t % k) * k + t // k
+    emul.run_wgrad(mem, plan)
+    got = emul.unpack_wgrad(desc, dw, (cout, cin, k, k))
+    ref = torch.nn.grad.conv2d_weight(xeff, (cout, cin, k, k), yeff, stride=1).transpose(2, 3)
+    assert torch.allclose(got, ref, rtol=1e-6, atol=1e-6 * float(ref.abs().max())), float((got - ref).abs().max())
